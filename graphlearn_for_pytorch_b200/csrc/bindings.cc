@@ -1,0 +1,685 @@
+// Python bindings: the only translation unit (besides cpu/*.cc) that sees torch
+// headers.  Native surface parity with the reference's pybind module
+// (python/py_export_glt.cc:47-222): Graph, samplers, negative sampler, inducer
+// tables, subgraph op, SampleQueue, UnifiedTensor-style row tables -- plus the
+// batch sampler arena and the GraphSAGE engine kernels that have no reference
+// counterpart.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <pybind11/functional.h>
+#include <pybind11/stl.h>
+#include <torch/extension.h>
+
+#include "cpu/cpu_ops.h"
+#include "cpu/sample_queue.h"
+#include "cuda/glt_cuda.h"
+
+namespace py = pybind11;
+using torch::Tensor;
+
+namespace glt {
+
+static cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+
+static void check_cuda_err(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  TORCH_CHECK(e == cudaSuccess, what, ": ", cudaGetErrorString(e));
+}
+
+static const void* dev_ptr(const Tensor& t) {
+  // CUDA tensors (local or peer device) and pinned host tensors are both
+  // directly dereferenceable from a kernel under UVA.
+  TORCH_CHECK(t.is_cuda() || t.is_pinned(), "tensor must be CUDA or pinned host memory");
+  return t.data_ptr();
+}
+
+// ---------------------------------------------------------------------------
+// GraphHandle: device view of a (possibly multi-GPU) CSR.
+// ---------------------------------------------------------------------------
+struct GraphHandle {
+  GraphTable tbl{};
+  std::vector<Tensor> keep;
+  int device = 0;
+  bool has_eids = true, has_weights = true;
+  int64_t num_rows = 0;
+
+  explicit GraphHandle(int dev) : device(dev) { tbl.num_parts = 0; tbl.idx_bytes = 8; }
+
+  void add_shard(const Tensor& indptr, const Tensor& indices, const c10::optional<Tensor>& eids,
+                 const c10::optional<Tensor>& weights, int64_t row_begin, int64_t row_end) {
+    TORCH_CHECK(tbl.num_parts < kMaxParts, "too many graph shards");
+    TORCH_CHECK(indptr.scalar_type() == torch::kInt64 && indptr.is_contiguous());
+    TORCH_CHECK(indices.is_contiguous());
+    int ib = indices.scalar_type() == torch::kInt32 ? 4 : 8;
+    TORCH_CHECK(indices.scalar_type() == torch::kInt32 || indices.scalar_type() == torch::kInt64);
+    if (tbl.num_parts == 0) tbl.idx_bytes = ib;
+    TORCH_CHECK(tbl.idx_bytes == ib, "all shards must share the column id width");
+    TORCH_CHECK(indptr.numel() == row_end - row_begin + 1, "indptr size != rows + 1");
+    CsrShard& s = tbl.parts[tbl.num_parts++];
+    s.indptr = reinterpret_cast<const int64_t*>(dev_ptr(indptr));
+    s.indices = dev_ptr(indices);
+    s.eids = nullptr;
+    s.weights = nullptr;
+    keep.push_back(indptr);
+    keep.push_back(indices);
+    if (eids.has_value() && eids->defined()) {
+      TORCH_CHECK(eids->scalar_type() == torch::kInt64);
+      s.eids = reinterpret_cast<const int64_t*>(dev_ptr(*eids));
+      keep.push_back(*eids);
+    } else {
+      has_eids = false;
+    }
+    if (weights.has_value() && weights->defined()) {
+      TORCH_CHECK(weights->scalar_type() == torch::kFloat32);
+      s.weights = reinterpret_cast<const float*>(dev_ptr(*weights));
+      keep.push_back(*weights);
+    } else {
+      has_weights = false;
+    }
+    s.row_begin = row_begin;
+    s.row_end = row_end;
+    num_rows = std::max(num_rows, row_end);
+  }
+
+  torch::TensorOptions opts(torch::ScalarType t) const {
+    return torch::TensorOptions().dtype(t).device(torch::kCUDA, device);
+  }
+
+  // (nbrs [n,k] padded with -1, counts [n] int32, eids [n,k] | undefined)
+  std::tuple<Tensor, Tensor, Tensor> sample_one_hop(const Tensor& seeds, int64_t k, bool with_edge,
+                                                    bool weighted, bool replace, int64_t seed,
+                                                    int64_t stream) {
+    c10::cuda::CUDAGuard guard(device);
+    TORCH_CHECK(seeds.is_cuda() && seeds.scalar_type() == torch::kInt64 && seeds.is_contiguous());
+    TORCH_CHECK(k > 0 && k <= 512, "fanout must be in [1, 512] (use -1 for all neighbours)");
+    TORCH_CHECK(!with_edge || has_eids, "graph has no edge ids");
+    TORCH_CHECK(!weighted || has_weights, "graph has no edge weights on the device");
+    const int64_t n = seeds.numel();
+    Tensor nbrs = torch::empty({n, k}, opts(torch::kInt64));
+    Tensor cnt = torch::empty({n}, opts(torch::kInt32));
+    Tensor eids = with_edge ? torch::empty({n, k}, opts(torch::kInt64)) : Tensor();
+    launch_sample_one_hop(tbl, seeds.data_ptr<int64_t>(), n, k, weighted, replace, seed, stream,
+                          nbrs.data_ptr<int64_t>(), with_edge ? eids.data_ptr<int64_t>() : nullptr,
+                          cnt.data_ptr<int32_t>(), cur_stream());
+    check_cuda_err("sample_one_hop");
+    return {nbrs, cnt, eids};
+  }
+
+  Tensor lookup_degree(const Tensor& ids) {
+    c10::cuda::CUDAGuard guard(device);
+    Tensor out = torch::empty({ids.numel()}, opts(torch::kInt64));
+    launch_lookup_degree(tbl, ids.data_ptr<int64_t>(), ids.numel(), out.data_ptr<int64_t>(), cur_stream());
+    check_cuda_err("lookup_degree");
+    return out;
+  }
+
+  // all neighbours; returns (nbrs [sum], counts [n] int64, eids)
+  std::tuple<Tensor, Tensor, Tensor> full_neighbors(const Tensor& ids, bool with_edge) {
+    c10::cuda::CUDAGuard guard(device);
+    Tensor deg = lookup_degree(ids);
+    Tensor offs = torch::zeros({ids.numel() + 1}, opts(torch::kInt64));
+    if (ids.numel() > 0) offs.narrow(0, 1, ids.numel()).copy_(deg.cumsum(0));
+    const int64_t total = ids.numel() > 0 ? offs[ids.numel()].item<int64_t>() : 0;  // host sync
+    Tensor nbrs = torch::empty({total}, opts(torch::kInt64));
+    Tensor eids = with_edge ? torch::empty({total}, opts(torch::kInt64)) : Tensor();
+    launch_copy_neighbors(tbl, ids.data_ptr<int64_t>(), ids.numel(), offs.data_ptr<int64_t>(),
+                          nbrs.data_ptr<int64_t>(), with_edge ? eids.data_ptr<int64_t>() : nullptr,
+                          cur_stream());
+    check_cuda_err("full_neighbors");
+    return {nbrs, deg, eids};
+  }
+
+  // (rows, cols, count) with rows/cols sized `req`; count stays on the device
+  std::tuple<Tensor, Tensor, Tensor> negative_sample(int64_t num_rows_, int64_t num_cols, int64_t req,
+                                                     int64_t trials, bool padding, int64_t seed,
+                                                     int64_t stream) {
+    c10::cuda::CUDAGuard guard(device);
+    Tensor rows = torch::empty({req}, opts(torch::kInt64));
+    Tensor cols = torch::empty({req}, opts(torch::kInt64));
+    Tensor count = torch::zeros({1}, opts(torch::kInt32));
+    launch_negative_sample(tbl, num_rows_, num_cols, req, trials, padding, seed, stream,
+                           rows.data_ptr<int64_t>(), cols.data_ptr<int64_t>(),
+                           count.data_ptr<int32_t>(), cur_stream());
+    check_cuda_err("negative_sample");
+    return {rows, cols, count};
+  }
+
+  Tensor random_walk(const Tensor& starts, int64_t walk_len, double p, double q, int64_t seed,
+                     int64_t stream) {
+    c10::cuda::CUDAGuard guard(device);
+    Tensor out = torch::empty({starts.numel(), walk_len + 1}, opts(torch::kInt64));
+    launch_random_walk(tbl, starts.data_ptr<int64_t>(), starts.numel(), walk_len, p, q, seed, stream,
+                       out.data_ptr<int64_t>(), cur_stream());
+    check_cuda_err("random_walk");
+    return out;
+  }
+
+  Tensor nbr_prob(GraphHandle& nbr_graph, const Tensor& last, const Tensor& nbr_last, int64_t k) {
+    c10::cuda::CUDAGuard guard(device);
+    Tensor cur = torch::zeros_like(last);
+    launch_nbr_prob(tbl, nbr_graph.tbl, last.data_ptr<float>(), nbr_last.data_ptr<float>(),
+                    std::min<int64_t>(last.numel(), num_rows), nbr_last.numel(), k,
+                    cur.data_ptr<float>(), cur_stream());
+    check_cuda_err("nbr_prob");
+    return cur;
+  }
+};
+
+// ---------------------------------------------------------------------------
+// DeviceTable: GPU id table (inducer state); one per node type for hetero.
+// ---------------------------------------------------------------------------
+struct DeviceTable {
+  int device;
+  int64_t cap_nodes;
+  Tensor keys, vals, aux, nodes, cursor;
+  HashTable ht{};
+
+  DeviceTable(int dev, int64_t capacity) : device(dev), cap_nodes(std::max<int64_t>(capacity, 16)) {
+    c10::cuda::CUDAGuard guard(device);
+    int64_t slots = 64;
+    while (slots < cap_nodes * 2) slots <<= 1;
+    auto o64 = torch::TensorOptions().dtype(torch::kInt64).device(torch::kCUDA, device);
+    auto o32 = torch::TensorOptions().dtype(torch::kInt32).device(torch::kCUDA, device);
+    keys = torch::full({slots}, -1, o64);
+    vals = torch::zeros({slots}, o32);
+    aux = torch::zeros({slots}, o32);
+    nodes = torch::empty({cap_nodes}, o64);
+    cursor = torch::zeros({1}, o32);
+    ht.keys = keys.data_ptr<int64_t>();
+    ht.vals = vals.data_ptr<int32_t>();
+    ht.aux = aux.data_ptr<int32_t>();
+    ht.mask = static_cast<uint32_t>(slots - 1);
+  }
+
+  void clear() {
+    c10::cuda::CUDAGuard guard(device);
+    launch_table_clear(ht, cur_stream());
+    cursor.zero_();
+  }
+
+  // unordered insert; returns local ids (int32).  New keys are appended to `nodes`.
+  Tensor insert(const Tensor& k) {
+    c10::cuda::CUDAGuard guard(device);
+    TORCH_CHECK(k.is_cuda() && k.scalar_type() == torch::kInt64 && k.is_contiguous());
+    Tensor out = torch::empty({k.numel()}, torch::TensorOptions().dtype(torch::kInt32).device(k.device()));
+    launch_table_insert(ht, k.data_ptr<int64_t>(), k.numel(), nodes.data_ptr<int64_t>(),
+                        cursor.data_ptr<int32_t>(), cap_nodes, out.data_ptr<int32_t>(), cur_stream());
+    launch_table_resolve(ht, out.data_ptr<int32_t>(), k.numel(), cur_stream());
+    check_cuda_err("table insert");
+    return out;
+  }
+
+  // ordered (first-occurrence) insert into an empty table; returns local ids
+  Tensor init_ordered(const Tensor& k) {
+    c10::cuda::CUDAGuard guard(device);
+    TORCH_CHECK(k.is_cuda() && k.scalar_type() == torch::kInt64 && k.is_contiguous());
+    TORCH_CHECK(k.numel() <= cap_nodes, "table capacity exceeded");
+    auto o32 = torch::TensorOptions().dtype(torch::kInt32).device(k.device());
+    Tensor out = torch::empty({k.numel()}, o32);
+    Tensor scratch = torch::empty({std::max<int64_t>(k.numel(), 1)}, o32);
+    Tensor counters = torch::zeros({16}, o32);
+    BatchCounters c{counters.data_ptr<int32_t>(), counters.data_ptr<int32_t>() + 6, cursor.data_ptr<int32_t>()};
+    launch_init_seeds(k.data_ptr<int64_t>(), k.numel(), nullptr, ht, nodes.data_ptr<int64_t>(),
+                      out.data_ptr<int32_t>(), scratch.data_ptr<int32_t>(), c, cur_stream());
+    check_cuda_err("table init_ordered");
+    return out;
+  }
+
+  Tensor lookup(const Tensor& k) {
+    c10::cuda::CUDAGuard guard(device);
+    Tensor out = torch::empty({k.numel()}, torch::TensorOptions().dtype(torch::kInt32).device(k.device()));
+    launch_table_lookup(ht, k.data_ptr<int64_t>(), k.numel(), out.data_ptr<int32_t>(), cur_stream());
+    check_cuda_err("table lookup");
+    return out;
+  }
+
+  int64_t size() { return cursor.item<int32_t>(); }  // host sync
+
+  // induced subgraph of `g` on the table's current node set (n = size())
+  std::tuple<Tensor, Tensor, Tensor> subgraph(GraphHandle& g, int64_t n, bool with_edge) {
+    c10::cuda::CUDAGuard guard(device);
+    auto o64 = torch::TensorOptions().dtype(torch::kInt64).device(torch::kCUDA, device);
+    Tensor cnt = torch::zeros({n}, o64);
+    launch_subgraph_count(g.tbl, ht, nodes.data_ptr<int64_t>(), n, cnt.data_ptr<int64_t>(), cur_stream());
+    Tensor offs = torch::zeros({n + 1}, o64);
+    if (n > 0) offs.narrow(0, 1, n).copy_(cnt.cumsum(0));
+    const int64_t total = n > 0 ? offs[n].item<int64_t>() : 0;  // host sync
+    Tensor rows = torch::empty({total}, o64), cols = torch::empty({total}, o64);
+    Tensor eids = with_edge ? torch::empty({total}, o64) : Tensor();
+    launch_subgraph_fill(g.tbl, ht, nodes.data_ptr<int64_t>(), n, offs.data_ptr<int64_t>(),
+                         rows.data_ptr<int64_t>(), cols.data_ptr<int64_t>(),
+                         with_edge ? eids.data_ptr<int64_t>() : nullptr, cur_stream());
+    check_cuda_err("subgraph");
+    return {rows, cols, eids};
+  }
+};
+
+// ---------------------------------------------------------------------------
+// SamplerArena: static-shape multi-hop sampling state (no host sync).
+// ---------------------------------------------------------------------------
+struct SamplerArena {
+  int device;
+  int max_seeds;
+  std::vector<int64_t> fanouts;
+  bool with_edge;
+  std::vector<int64_t> cap_rows;  // frontier capacity per hop
+  int64_t cap_nodes;
+  Tensor nodes, deg, counters, seed_local, scratch;
+  std::vector<Tensor> ell, ell_eids;
+  std::unique_ptr<DeviceTable> table;
+
+  SamplerArena(int dev, int64_t max_seeds_, std::vector<int64_t> fanouts_, bool with_edge_,
+               int64_t num_graph_nodes)
+      : device(dev), max_seeds(max_seeds_), fanouts(std::move(fanouts_)), with_edge(with_edge_) {
+    c10::cuda::CUDAGuard guard(device);
+    TORCH_CHECK(fanouts.size() >= 1 && fanouts.size() <= 4, "1..4 hops supported by the arena");
+    auto o64 = torch::TensorOptions().dtype(torch::kInt64).device(torch::kCUDA, device);
+    auto o32 = torch::TensorOptions().dtype(torch::kInt32).device(torch::kCUDA, device);
+    int64_t rows = max_seeds;
+    cap_nodes = max_seeds;
+    for (size_t h = 0; h < fanouts.size(); ++h) {
+      TORCH_CHECK(fanouts[h] > 0 && fanouts[h] <= 512, "arena fanouts must be in [1,512]");
+      cap_rows.push_back(rows);
+      ell.push_back(torch::full({rows * fanouts[h]}, -1, o32));
+      ell_eids.push_back(with_edge ? torch::full({rows * fanouts[h]}, -1, o64) : Tensor());
+      rows = std::min<int64_t>(rows * fanouts[h], num_graph_nodes > 0 ? num_graph_nodes : INT64_MAX);
+      cap_nodes += rows;
+    }
+    if (num_graph_nodes > 0) cap_nodes = std::min(cap_nodes, num_graph_nodes + max_seeds);
+    TORCH_CHECK(cap_nodes < (1LL << 30), "sampler arena too large");
+    table = std::make_unique<DeviceTable>(device, cap_nodes);
+    nodes = table->nodes;
+    deg = torch::zeros({cap_nodes}, o32);
+    counters = torch::zeros({16}, o32);
+    seed_local = torch::zeros({max_seeds}, o32);
+    scratch = torch::zeros({max_seeds}, o32);
+  }
+
+  BatchCounters bc() {
+    int32_t* c = counters.data_ptr<int32_t>();
+    return BatchCounters{c, c + 6, table->cursor.data_ptr<int32_t>()};
+  }
+
+  void sample(GraphHandle& g, const Tensor& seeds, const c10::optional<Tensor>& n_dev, int64_t seed,
+              int64_t stream_base, bool weighted, bool replace) {
+    c10::cuda::CUDAGuard guard(device);
+    TORCH_CHECK(seeds.is_cuda() && seeds.scalar_type() == torch::kInt64 && seeds.is_contiguous());
+    TORCH_CHECK(seeds.numel() <= max_seeds, "more seeds than the arena was built for");
+    TORCH_CHECK(!with_edge || g.has_eids, "graph has no edge ids");
+    TORCH_CHECK(!weighted || g.has_weights, "graph has no device edge weights");
+    cudaStream_t s = cur_stream();
+    launch_table_clear(table->ht, s);
+    const int32_t* nd = (n_dev.has_value() && n_dev->defined()) ? n_dev->data_ptr<int32_t>() : nullptr;
+    launch_init_seeds(seeds.data_ptr<int64_t>(), seeds.numel(), nd, table->ht, nodes.data_ptr<int64_t>(),
+                      seed_local.data_ptr<int32_t>(), scratch.data_ptr<int32_t>(), bc(), s);
+    for (size_t h = 0; h < fanouts.size(); ++h) {
+      HopArgs a{};
+      a.g = g.tbl;
+      a.t = table->ht;
+      a.c = bc();
+      a.nodes = nodes.data_ptr<int64_t>();
+      a.ell = ell[h].data_ptr<int32_t>();
+      a.ell_eids = with_edge ? ell_eids[h].data_ptr<int64_t>() : nullptr;
+      a.deg = deg.data_ptr<int32_t>();
+      a.hop = h;
+      a.k = fanouts[h];
+      a.cap_rows = cap_rows[h];
+      a.cap_nodes = cap_nodes;
+      a.weighted = weighted;
+      a.replace = replace;
+      a.seed = seed;
+      a.stream = static_cast<uint32_t>(stream_base + h);
+      launch_sample_hop(a, s);
+      launch_relabel_hop(a, s);
+    }
+    check_cuda_err("arena sample");
+  }
+
+  // PyG-shaped COO (one host sync to learn the sizes):
+  // returns (node [N], row [E], col [E], eids|undef, num_sampled_nodes, num_sampled_edges)
+  std::tuple<Tensor, Tensor, Tensor, Tensor, std::vector<int64_t>, std::vector<int64_t>> to_coo() {
+    c10::cuda::CUDAGuard guard(device);
+    auto o64 = torch::TensorOptions().dtype(torch::kInt64).device(torch::kCUDA, device);
+    Tensor host = counters.cpu();  // sync
+    const int32_t* c = host.data_ptr<int32_t>();
+    const int L = fanouts.size();
+    std::vector<int64_t> nn, ne;
+    for (int h = 0; h <= L; ++h) nn.push_back(c[h + 1] - c[h]);
+    int64_t E = 0;
+    for (int h = 0; h < L; ++h) { ne.push_back(c[6 + h]); E += c[6 + h]; }
+    const int64_t N = c[L + 1], T = c[L];
+    Tensor offs = torch::zeros({T + 1}, o64);
+    if (T > 0) offs.narrow(0, 1, T).copy_(deg.narrow(0, 0, T).to(torch::kInt64).cumsum(0));
+    Tensor rows = torch::empty({E}, o64), cols = torch::empty({E}, o64);
+    Tensor eids = with_edge ? torch::empty({E}, o64) : Tensor();
+    for (int h = 0; h < L; ++h) {
+      launch_ell_to_coo(ell[h].data_ptr<int32_t>(), with_edge ? ell_eids[h].data_ptr<int64_t>() : nullptr,
+                        deg.data_ptr<int32_t>(), offs.data_ptr<int64_t>(), counters.data_ptr<int32_t>(),
+                        h, fanouts[h], cap_rows[h], rows.data_ptr<int64_t>(), cols.data_ptr<int64_t>(),
+                        with_edge ? eids.data_ptr<int64_t>() : nullptr, cur_stream());
+    }
+    check_cuda_err("to_coo");
+    return {nodes.narrow(0, 0, N).clone(), rows, cols, eids, nn, ne};
+  }
+};
+
+// ---------------------------------------------------------------------------
+// RowTableHandle: multi-source row store (UnifiedTensor).
+// ---------------------------------------------------------------------------
+struct RowTableHandle {
+  RowTable tbl{};
+  std::vector<Tensor> keep;
+  int device;
+  torch::ScalarType dtype = torch::kFloat32;
+  int64_t width = 0;
+
+  explicit RowTableHandle(int dev) : device(dev) { tbl.num_parts = 0; tbl.row_begin[0] = 0; }
+
+  void append(const Tensor& part) {
+    TORCH_CHECK(tbl.num_parts < kMaxParts, "too many row-table parts");
+    TORCH_CHECK(part.dim() >= 1 && part.is_contiguous(), "parts must be contiguous [rows, ...]");
+    const int64_t w = part.numel() / std::max<int64_t>(part.size(0), 1);
+    if (tbl.num_parts == 0) {
+      dtype = part.scalar_type();
+      width = part.dim() > 1 ? w : 1;
+      tbl.row_bytes = width * part.element_size();
+    }
+    TORCH_CHECK(part.scalar_type() == dtype, "dtype mismatch between parts");
+    TORCH_CHECK((part.dim() > 1 ? w : 1) == width || part.size(0) == 0, "row width mismatch");
+    tbl.base[tbl.num_parts] = dev_ptr(part);
+    tbl.row_begin[tbl.num_parts + 1] = tbl.row_begin[tbl.num_parts] + part.size(0);
+    tbl.num_parts++;
+    keep.push_back(part);
+  }
+
+  int64_t num_rows() const { return tbl.row_begin[tbl.num_parts]; }
+
+  Tensor gather(const Tensor& idx, const c10::optional<Tensor>& id2index, int64_t out_width) {
+    c10::cuda::CUDAGuard guard(device);
+    TORCH_CHECK(idx.is_cuda() && idx.scalar_type() == torch::kInt64 && idx.is_contiguous());
+    if (out_width <= 0) out_width = width;
+    TORCH_CHECK(out_width >= width);
+    auto o = torch::TensorOptions().dtype(dtype).device(torch::kCUDA, device);
+    Tensor out = out_width == width ? torch::empty({idx.numel(), width}, o)
+                                    : torch::zeros({idx.numel(), out_width}, o);
+    const int64_t* map = (id2index.has_value() && id2index->defined()) ? id2index->data_ptr<int64_t>() : nullptr;
+    launch_gather_rows(tbl, idx.data_ptr<int64_t>(), map, idx.numel(), nullptr, out.data_ptr(),
+                       out_width * out.element_size(), cur_stream());
+    check_cuda_err("gather_rows");
+    return out;
+  }
+
+  // static-shape gather into a caller-provided buffer with a device-side count
+  void gather_into(const Tensor& idx, const c10::optional<Tensor>& id2index,
+                   const c10::optional<Tensor>& n_dev, Tensor out) {
+    c10::cuda::CUDAGuard guard(device);
+    const int64_t* map = (id2index.has_value() && id2index->defined()) ? id2index->data_ptr<int64_t>() : nullptr;
+    const int32_t* nd = (n_dev.has_value() && n_dev->defined()) ? n_dev->data_ptr<int32_t>() : nullptr;
+    TORCH_CHECK(out.is_contiguous() && out.size(0) >= idx.numel());
+    launch_gather_rows(tbl, idx.data_ptr<int64_t>(), map, idx.numel(), nd, out.data_ptr(),
+                       out.stride(0) * out.element_size(), cur_stream());
+    check_cuda_err("gather_into");
+  }
+};
+
+// ---------------------------------------------------------------------------
+// GraphSAGE engine kernels
+// ---------------------------------------------------------------------------
+static void fill_ell(const std::vector<Tensor>& ell, const std::vector<int64_t>& ks,
+                     const int32_t** out_ell, int* out_k) {
+  TORCH_CHECK(ell.size() == ks.size() && ell.size() <= 4);
+  for (size_t i = 0; i < 4; ++i) { out_ell[i] = nullptr; out_k[i] = 1; }
+  for (size_t i = 0; i < ell.size(); ++i) { out_ell[i] = ell[i].data_ptr<int32_t>(); out_k[i] = ks[i]; }
+}
+
+static SageAggArgs make_agg(RowTableHandle* feat, const c10::optional<Tensor>& nodes,
+                            const c10::optional<Tensor>& src_local, int64_t d, const Tensor& counters,
+                            int64_t n_hops_targets, int64_t cap_targets, const std::vector<Tensor>& ell,
+                            const std::vector<int64_t>& ks, const Tensor& deg, void* out) {
+  SageAggArgs a{};
+  if (src_local.has_value() && src_local->defined()) {
+    TORCH_CHECK(src_local->scalar_type() == torch::kBFloat16 && src_local->is_contiguous());
+    a.src_local = src_local->data_ptr();
+  } else {
+    TORCH_CHECK(feat != nullptr && nodes.has_value(), "layer-1 aggregation needs a feature table + nodes");
+    TORCH_CHECK(feat->dtype == torch::kBFloat16, "engine features must be bf16");
+    TORCH_CHECK(feat->width == d, "feature width mismatch");
+    a.feat = feat->tbl;
+    a.nodes = nodes->data_ptr<int64_t>();
+  }
+  TORCH_CHECK(d % 8 == 0, "feature width must be a multiple of 8");
+  a.d = d;
+  a.cum = counters.data_ptr<int32_t>();
+  a.n_hops_targets = n_hops_targets;
+  a.cap_targets = cap_targets;
+  fill_ell(ell, ks, a.ell, a.k);
+  a.deg = deg.data_ptr<int32_t>();
+  a.out = out;
+  return a;
+}
+
+static void sage_aggregate(RowTableHandle* feat, const c10::optional<Tensor>& nodes,
+                           const c10::optional<Tensor>& src_local, int64_t d, const Tensor& counters,
+                           int64_t n_hops_targets, const std::vector<Tensor>& ell,
+                           const std::vector<int64_t>& ks, const Tensor& deg, Tensor out) {
+  c10::cuda::CUDAGuard guard(out.device());
+  TORCH_CHECK(out.scalar_type() == torch::kBFloat16 && out.is_contiguous() && out.size(1) == 2 * d);
+  SageAggArgs a = make_agg(feat, nodes, src_local, d, counters, n_hops_targets, out.size(0), ell, ks,
+                           deg, out.data_ptr());
+  launch_sage_aggregate(a, cur_stream());
+  check_cuda_err("sage_aggregate");
+}
+
+static void sage_scatter_bwd(const Tensor& dA, int64_t d, const Tensor& counters, int64_t n_hops_targets,
+                             const std::vector<Tensor>& ell, const std::vector<int64_t>& ks,
+                             const Tensor& deg, Tensor dH) {
+  c10::cuda::CUDAGuard guard(dA.device());
+  TORCH_CHECK(dA.scalar_type() == torch::kBFloat16 && dA.is_contiguous() && dA.size(1) == 2 * d);
+  TORCH_CHECK(dH.scalar_type() == torch::kFloat32 && dH.is_contiguous() && dH.size(1) == d);
+  SageScatterArgs a{};
+  a.dA = dA.data_ptr();
+  a.d = d;
+  a.cum = counters.data_ptr<int32_t>();
+  a.n_hops_targets = n_hops_targets;
+  a.cap_targets = dA.size(0);
+  fill_ell(ell, ks, a.ell, a.k);
+  a.deg = deg.data_ptr<int32_t>();
+  a.dH = dH.data_ptr<float>();
+  launch_sage_scatter_bwd(a, cur_stream());
+  check_cuda_err("sage_scatter_bwd");
+}
+
+static void relu_bwd_cast(const Tensor& dH, const Tensor& Z, const Tensor& counters, int64_t n_hops,
+                          Tensor dPre) {
+  c10::cuda::CUDAGuard guard(dH.device());
+  TORCH_CHECK(dPre.size(0) <= dH.size(0) && dPre.size(0) <= Z.size(0) && dPre.size(1) % 8 == 0);
+  launch_relu_bwd_cast(dH.data_ptr<float>(), Z.data_ptr(), counters.data_ptr<int32_t>(), n_hops,
+                       dPre.size(0), dPre.size(1), dPre.data_ptr(), cur_stream());
+  check_cuda_err("relu_bwd_cast");
+}
+
+static void bias_relu(Tensor Z, const Tensor& bias, const Tensor& counters, int64_t n_hops, bool relu) {
+  c10::cuda::CUDAGuard guard(Z.device());
+  TORCH_CHECK(Z.scalar_type() == torch::kBFloat16 && bias.scalar_type() == torch::kBFloat16);
+  TORCH_CHECK(Z.size(1) % 8 == 0 && bias.numel() == Z.size(1));
+  launch_bias_relu(Z.data_ptr(), bias.data_ptr(), counters.data_ptr<int32_t>(), n_hops, Z.size(0),
+                   Z.size(1), relu, cur_stream());
+  check_cuda_err("bias_relu");
+}
+
+static void softmax_nll(const Tensor& logits, int64_t C, const Tensor& y, const Tensor& counters,
+                        Tensor loss, Tensor dlogits, const c10::optional<Tensor>& correct) {
+  c10::cuda::CUDAGuard guard(logits.device());
+  TORCH_CHECK(logits.scalar_type() == torch::kBFloat16 && logits.is_contiguous());
+  TORCH_CHECK(dlogits.sizes() == logits.sizes() && dlogits.is_contiguous());
+  launch_softmax_nll(logits.data_ptr(), logits.size(1), C, y.data_ptr<int64_t>(),
+                     counters.data_ptr<int32_t>(), logits.size(0), loss.data_ptr<float>(),
+                     dlogits.data_ptr(),
+                     (correct.has_value() && correct->defined()) ? correct->data_ptr<int32_t>() : nullptr,
+                     cur_stream());
+  check_cuda_err("softmax_nll");
+}
+
+static void adam_step(Tensor p, const Tensor& g, Tensor m, Tensor v, const c10::optional<Tensor>& p_bf16,
+                      double lr, double b1, double b2, double eps, double wd, const Tensor& step_dev,
+                      double gscale) {
+  c10::cuda::CUDAGuard guard(p.device());
+  launch_adam(p.data_ptr<float>(), g.data_ptr<float>(), m.data_ptr<float>(), v.data_ptr<float>(),
+              (p_bf16.has_value() && p_bf16->defined()) ? p_bf16->data_ptr() : nullptr, p.numel(), lr,
+              b1, b2, eps, wd, step_dev.data_ptr<int32_t>(), gscale, cur_stream());
+  check_cuda_err("adam");
+}
+
+static void sage_fused(RowTableHandle* feat, const c10::optional<Tensor>& nodes,
+                       const c10::optional<Tensor>& src_local, int64_t d, const Tensor& counters,
+                       int64_t n_hops_targets, const std::vector<Tensor>& ell,
+                       const std::vector<int64_t>& ks, const Tensor& deg, const Tensor& w_packed,
+                       const Tensor& bias, bool relu, Tensor z, const c10::optional<Tensor>& a_save) {
+  c10::cuda::CUDAGuard guard(z.device());
+  TORCH_CHECK(z.scalar_type() == torch::kBFloat16 && z.is_contiguous());
+  const int64_t n_out = z.size(1);
+  TORCH_CHECK(sage_fused_supported(d, n_out), "unsupported fused shape d=", d, " n_out=", n_out);
+  TORCH_CHECK(w_packed.numel() == 2 * d * n_out && w_packed.scalar_type() == torch::kBFloat16);
+  SageFusedArgs f{};
+  f.agg = make_agg(feat, nodes, src_local, d, counters, n_hops_targets, z.size(0), ell, ks, deg, nullptr);
+  f.w_packed = w_packed.data_ptr();
+  f.bias = bias.data_ptr();
+  f.n_out = n_out;
+  f.relu = relu;
+  f.z = z.data_ptr();
+  f.a_save = nullptr;
+  if (a_save.has_value() && a_save->defined()) {
+    TORCH_CHECK(a_save->size(0) >= z.size(0) && a_save->size(1) == 2 * d && a_save->is_contiguous());
+    f.a_save = a_save->data_ptr();
+  }
+  launch_sage_fused(f, at::cuda::getCurrentDeviceProperties()->multiProcessorCount, cur_stream());
+  check_cuda_err("sage_fused");
+}
+
+static void enable_peer_access(int dev, int peer) {
+  if (dev == peer) return;
+  c10::cuda::CUDAGuard guard(dev);
+  int can = 0;
+  cudaDeviceCanAccessPeer(&can, dev, peer);
+  TORCH_CHECK(can, "GPU ", dev, " cannot access peer GPU ", peer);
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return; }
+  TORCH_CHECK(e == cudaSuccess, "cudaDeviceEnablePeerAccess: ", cudaGetErrorString(e));
+}
+
+static Tensor pack_weight(const Tensor& w) {
+  c10::cuda::CUDAGuard guard(w.device());
+  TORCH_CHECK(w.scalar_type() == torch::kBFloat16 && w.is_contiguous() && w.dim() == 2);
+  TORCH_CHECK(w.size(1) % 64 == 0 && w.size(0) % 16 == 0, "W must be [N%16, K%64]");
+  Tensor out = torch::empty_like(w);
+  launch_pack_weight(w.data_ptr(), w.size(0), w.size(1), out.data_ptr(), cur_stream());
+  check_cuda_err("pack_weight");
+  return out;
+}
+
+static void pack_weight_into(const Tensor& w, Tensor out) {
+  c10::cuda::CUDAGuard guard(w.device());
+  TORCH_CHECK(w.scalar_type() == torch::kBFloat16 && w.is_contiguous() && w.dim() == 2);
+  TORCH_CHECK(out.numel() == w.numel() && out.scalar_type() == torch::kBFloat16);
+  launch_pack_weight(w.data_ptr(), w.size(0), w.size(1), out.data_ptr(), cur_stream());
+  check_cuda_err("pack_weight");
+}
+
+}  // namespace glt
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  using namespace glt;
+  m.doc() = "graphlearn_for_pytorch_b200 native core (CPU reference ops + sm_100a kernels)";
+
+  // ---- CPU ops ----
+  m.def("coo_to_csr", &coo_to_csr);
+  m.def("cpu_sample_neighbors", &cpu_sample_neighbors);
+  m.def("cpu_sample_neighbors_weighted", &cpu_sample_neighbors_weighted);
+  m.def("cpu_negative_sample", &cpu_negative_sample);
+  m.def("cpu_node_subgraph", &cpu_node_subgraph);
+  m.def("cpu_random_walk", &cpu_random_walk);
+  m.def("cpu_stitch", &cpu_stitch);
+  m.def("cpu_nbr_prob", &cpu_nbr_prob);
+  py::class_<CpuIdTable>(m, "CpuIdTable")
+      .def(py::init<int64_t>())
+      .def("reset", &CpuIdTable::reset)
+      .def("insert", &CpuIdTable::insert)
+      .def("lookup", &CpuIdTable::lookup)
+      .def("keys", &CpuIdTable::keys, py::arg("start") = 0)
+      .def("size", &CpuIdTable::size);
+
+  // ---- shm sample queue ----
+  py::register_exception<QueueTimeoutError>(m, "QueueTimeoutError");
+  py::register_exception<QueueClosedError>(m, "QueueClosedError");
+  py::class_<SampleQueue>(m, "SampleQueue")
+      .def(py::init<size_t, size_t>(), py::arg("max_msgs"), py::arg("buf_bytes"))
+      .def(py::init<const std::string&>(), py::arg("name"))
+      .def_property_readonly("name", &SampleQueue::name)
+      .def("send", &SampleQueue::send, py::call_guard<py::gil_scoped_release>())
+      .def("recv", &SampleQueue::recv, py::arg("timeout_ms") = 0, py::call_guard<py::gil_scoped_release>())
+      .def("empty", &SampleQueue::empty)
+      .def("size", &SampleQueue::size)
+      .def("close", &SampleQueue::close)
+      .def("pin_memory", &SampleQueue::pin_memory);
+
+  // ---- CUDA graph / tables ----
+  py::class_<GraphHandle>(m, "GraphHandle")
+      .def(py::init<int>())
+      .def("add_shard", &GraphHandle::add_shard)
+      .def_readonly("num_rows", &GraphHandle::num_rows)
+      .def_readonly("has_eids", &GraphHandle::has_eids)
+      .def_readonly("has_weights", &GraphHandle::has_weights)
+      .def_property_readonly("num_parts", [](const GraphHandle& g) { return g.tbl.num_parts; })
+      .def("sample_one_hop", &GraphHandle::sample_one_hop)
+      .def("lookup_degree", &GraphHandle::lookup_degree)
+      .def("full_neighbors", &GraphHandle::full_neighbors)
+      .def("negative_sample", &GraphHandle::negative_sample)
+      .def("random_walk", &GraphHandle::random_walk)
+      .def("nbr_prob", &GraphHandle::nbr_prob);
+  py::class_<DeviceTable>(m, "DeviceTable")
+      .def(py::init<int, int64_t>())
+      .def("clear", &DeviceTable::clear)
+      .def("insert", &DeviceTable::insert)
+      .def("init_ordered", &DeviceTable::init_ordered)
+      .def("lookup", &DeviceTable::lookup)
+      .def("size", &DeviceTable::size)
+      .def("subgraph", &DeviceTable::subgraph)
+      .def_readonly("nodes", &DeviceTable::nodes)
+      .def_readonly("cursor", &DeviceTable::cursor)
+      .def_readonly("capacity", &DeviceTable::cap_nodes);
+  py::class_<SamplerArena>(m, "SamplerArena")
+      .def(py::init<int, int64_t, std::vector<int64_t>, bool, int64_t>())
+      .def("sample", &SamplerArena::sample)
+      .def("to_coo", &SamplerArena::to_coo)
+      .def_readonly("nodes", &SamplerArena::nodes)
+      .def_readonly("deg", &SamplerArena::deg)
+      .def_readonly("counters", &SamplerArena::counters)
+      .def_readonly("seed_local", &SamplerArena::seed_local)
+      .def_readonly("ell", &SamplerArena::ell)
+      .def_readonly("ell_eids", &SamplerArena::ell_eids)
+      .def_readonly("cap_rows", &SamplerArena::cap_rows)
+      .def_readonly("cap_nodes", &SamplerArena::cap_nodes)
+      .def_readonly("fanouts", &SamplerArena::fanouts);
+  py::class_<RowTableHandle>(m, "RowTableHandle")
+      .def(py::init<int>())
+      .def("append", &RowTableHandle::append)
+      .def("num_rows", &RowTableHandle::num_rows)
+      .def_readonly("width", &RowTableHandle::width)
+      .def_property_readonly("num_parts", [](const RowTableHandle& t) { return t.tbl.num_parts; })
+      .def("gather", &RowTableHandle::gather, py::arg("idx"), py::arg("id2index") = py::none(),
+           py::arg("out_width") = 0)
+      .def("gather_into", &RowTableHandle::gather_into);
+
+  // ---- GraphSAGE engine ----
+  m.def("sage_aggregate", &sage_aggregate);
+  m.def("sage_scatter_bwd", &sage_scatter_bwd);
+  m.def("relu_bwd_cast", &relu_bwd_cast);
+  m.def("bias_relu", &bias_relu);
+  m.def("softmax_nll", &softmax_nll);
+  m.def("adam_step", &adam_step);
+  m.def("sage_fused", &sage_fused);
+  m.def("sage_fused_supported", &sage_fused_supported);
+  m.def("enable_peer_access", &enable_peer_access);
+  m.def("pack_weight", &pack_weight);
+  m.def("pack_weight_into", &pack_weight_into);
+}

@@ -1,0 +1,115 @@
+// Device-side helpers shared by the sm_100a kernels.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "../philox.h"
+#include "glt_cuda.h"
+
+namespace glt {
+
+constexpr int64_t kEmptyKey = -1;
+
+__device__ __forceinline__ uint32_t hash_slot(int64_t key, uint32_t mask) {
+  uint64_t x = static_cast<uint64_t>(key) * 0x9E3779B97F4A7C15ULL;
+  return static_cast<uint32_t>(x >> 29) & mask;
+}
+
+// Insert `key`; returns the slot and whether this thread claimed it.
+__device__ __forceinline__ uint32_t table_insert(const HashTable& t, int64_t key, bool* is_new) {
+  uint32_t s = hash_slot(key, t.mask);
+  while (true) {
+    unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long*>(t.keys + s),
+                                        static_cast<unsigned long long>(kEmptyKey),
+                                        static_cast<unsigned long long>(key));
+    if (prev == static_cast<unsigned long long>(kEmptyKey)) { *is_new = true; return s; }
+    if (prev == static_cast<unsigned long long>(key)) { *is_new = false; return s; }
+    s = (s + 1) & t.mask;
+  }
+}
+
+__device__ __forceinline__ int32_t table_find_slot(const HashTable& t, int64_t key) {
+  uint32_t s = hash_slot(key, t.mask);
+  while (true) {
+    int64_t k = t.keys[s];
+    if (k == key) return static_cast<int32_t>(s);
+    if (k == kEmptyKey) return -1;
+    s = (s + 1) & t.mask;
+  }
+}
+
+struct RowRef {
+  int64_t start;  // offset into the owning shard's indices
+  int32_t deg;
+  int32_t part;
+};
+
+// Owner lookup + row extent.  The shard may be peer HBM: these are plain
+// ld.global on NVLink-mapped addresses, no RPC, no host staging.
+__device__ __forceinline__ RowRef load_row(const GraphTable& g, int64_t v) {
+  RowRef r;
+  r.start = 0; r.deg = 0; r.part = -1;
+#pragma unroll 1
+  for (int p = 0; p < g.num_parts; ++p) {
+    const int64_t b = g.parts[p].row_begin, e = g.parts[p].row_end;
+    if (v >= b && v < e) {
+      const int64_t* ip = g.parts[p].indptr + (v - b);
+      const int64_t s0 = __ldg(ip), s1 = __ldg(ip + 1);
+      r.start = s0; r.deg = static_cast<int32_t>(s1 - s0); r.part = p;
+      break;
+    }
+  }
+  return r;
+}
+
+__device__ __forceinline__ int64_t load_col(const GraphTable& g, int part, int64_t pos) {
+  if (g.idx_bytes == 4) return __ldg(reinterpret_cast<const int32_t*>(g.parts[part].indices) + pos);
+  return __ldg(reinterpret_cast<const int64_t*>(g.parts[part].indices) + pos);
+}
+
+__device__ __forceinline__ unsigned lanemask_lt() {
+  unsigned m;
+  asm volatile("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+// 16-byte streaming load that bypasses L1 allocation (feature rows are touched
+// once per batch; peer rows are not L2-cached locally anyway).
+__device__ __forceinline__ uint4 ld_nc_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ void bf16x8_accum(const uint4& v, float* acc) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __bfloat1622float2(h[i]);
+    acc[2 * i] += f.x;
+    acc[2 * i + 1] += f.y;
+  }
+}
+
+__device__ __forceinline__ uint4 pack_bf16x8(const float* a, float scale) {
+  uint4 r;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(a[2 * i] * scale, a[2 * i + 1] * scale);
+  return r;
+}
+
+// Row pointer of a RowTable by (already remapped) row index.
+__device__ __forceinline__ const uint8_t* row_ptr(const RowTable& t, int64_t row) {
+#pragma unroll 1
+  for (int p = 0; p < t.num_parts; ++p) {
+    if (row >= t.row_begin[p] && row < t.row_begin[p + 1])
+      return reinterpret_cast<const uint8_t*>(t.base[p]) + (row - t.row_begin[p]) * t.row_bytes;
+  }
+  return nullptr;
+}
+
+}  // namespace glt

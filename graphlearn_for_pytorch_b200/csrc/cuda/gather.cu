@@ -1,0 +1,136 @@
+// Multi-source row gather (UnifiedTensor / Feature lookup).
+//
+// out[i,:] = part(owner(idx[i]))[idx[i] - begin(owner)], where a part is local
+// HBM, a peer GPU's HBM mapped over NVLink (CUDA IPC) or pinned host memory.
+// Capability parity with the reference's GatherTensorKernel
+// (csrc/cuda/unified_tensor.cu:47-81: warp per row, scalar T loads); here rows
+// move as 16-byte vectors with L1::no_allocate, several rows share a warp when
+// rows are narrow, every lane keeps up to four loads in flight, and the row
+// count can stay on the device (n_dev) so the launch is CUDA-graph capturable.
+#include "device_utils.cuh"
+
+namespace glt {
+
+namespace {
+
+template <int LPR>
+__global__ void __launch_bounds__(256) k_gather_vec(RowTable t, const int64_t* idx,
+                                                    const int64_t* id2index, int64_t n,
+                                                    const int32_t* n_dev, uint8_t* out,
+                                                    int64_t out_row_bytes) {
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % LPR;
+  const int gw = lane / LPR;
+  const int64_t n_valid = n_dev ? min(static_cast<int64_t>(*n_dev), n) : n;
+  const int nvec = static_cast<int>(t.row_bytes >> 4);
+  const int64_t wpb = blockDim.x >> 5;
+  for (int64_t base = (blockIdx.x * wpb + (threadIdx.x >> 5)) * RPW; base < n;
+       base += static_cast<int64_t>(gridDim.x) * wpb * RPW) {
+    const int64_t r = base + gw;
+    if (r >= n) continue;
+    const uint8_t* src = nullptr;
+    if (r < n_valid) {
+      int64_t row = idx[r];
+      if (row >= 0 && id2index) row = id2index[row];
+      if (row >= 0) src = row_ptr(t, row);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out + r * out_row_bytes);
+    if (src == nullptr) {
+      for (int c = gl; c < nvec; c += LPR) dst[c] = make_uint4(0, 0, 0, 0);
+      continue;
+    }
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    int c = gl;
+    for (; c + 3 * LPR < nvec; c += 4 * LPR) {
+      const uint4 a0 = ld_nc_v4(s4 + c), a1 = ld_nc_v4(s4 + c + LPR);
+      const uint4 a2 = ld_nc_v4(s4 + c + 2 * LPR), a3 = ld_nc_v4(s4 + c + 3 * LPR);
+      dst[c] = a0; dst[c + LPR] = a1; dst[c + 2 * LPR] = a2; dst[c + 3 * LPR] = a3;
+    }
+    for (; c < nvec; c += LPR) dst[c] = ld_nc_v4(s4 + c);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_gather_scalar(RowTable t, const int64_t* idx,
+                                                       const int64_t* id2index, int64_t n,
+                                                       const int32_t* n_dev, uint8_t* out,
+                                                       int64_t out_row_bytes) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n_valid = n_dev ? min(static_cast<int64_t>(*n_dev), n) : n;
+  const int nel = static_cast<int>(t.row_bytes / sizeof(T));
+  const int64_t wpb = blockDim.x >> 5;
+  for (int64_t r = blockIdx.x * wpb + (threadIdx.x >> 5); r < n;
+       r += static_cast<int64_t>(gridDim.x) * wpb) {
+    const uint8_t* src = nullptr;
+    if (r < n_valid) {
+      int64_t row = idx[r];
+      if (row >= 0 && id2index) row = id2index[row];
+      if (row >= 0) src = row_ptr(t, row);
+    }
+    T* dst = reinterpret_cast<T*>(out + r * out_row_bytes);
+    const T* s = reinterpret_cast<const T*>(src);
+    for (int c = lane; c < nel; c += 32) dst[c] = src ? s[c] : T(0);
+  }
+}
+
+__global__ void k_gather_i64(RowTable t, const int64_t* idx, int64_t n, const int32_t* n_dev,
+                             int64_t* out) {
+  const int64_t n_valid = n_dev ? min(static_cast<int64_t>(*n_dev), n) : n;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    int64_t v = -1;
+    if (i < n_valid && idx[i] >= 0) {
+      const uint8_t* p = row_ptr(t, idx[i]);
+      if (p) v = *reinterpret_cast<const int64_t*>(p);
+    }
+    out[i] = v;
+  }
+}
+
+inline int grid_for(int64_t items, int per_block, int max_blocks = 148 * 16) {
+  int64_t b = (items + per_block - 1) / per_block;
+  if (b < 1) b = 1;
+  if (b > max_blocks) b = max_blocks;
+  return static_cast<int>(b);
+}
+
+}  // namespace
+
+void launch_gather_rows(RowTable t, const int64_t* idx, const int64_t* id2index, int64_t n,
+                        const int32_t* n_dev, void* out, int64_t out_row_bytes, cudaStream_t s) {
+  if (n <= 0) return;
+  uint8_t* o = reinterpret_cast<uint8_t*>(out);
+  bool aligned = (t.row_bytes % 16 == 0) && (out_row_bytes % 16 == 0) &&
+                 (reinterpret_cast<uintptr_t>(out) % 16 == 0);
+  for (int p = 0; p < t.num_parts; ++p) aligned &= (reinterpret_cast<uintptr_t>(t.base[p]) % 16 == 0);
+  if (aligned) {
+    const int nvec = static_cast<int>(t.row_bytes / 16);
+#define GLT_LAUNCH_VEC(LPR)                                                                   \
+  k_gather_vec<LPR><<<grid_for(n, 8 * (32 / LPR)), 256, 0, s>>>(t, idx, id2index, n, n_dev, o, \
+                                                                 out_row_bytes)
+    if (nvec <= 1) GLT_LAUNCH_VEC(1);
+    else if (nvec <= 2) GLT_LAUNCH_VEC(2);
+    else if (nvec <= 4) GLT_LAUNCH_VEC(4);
+    else if (nvec <= 8) GLT_LAUNCH_VEC(8);
+    else if (nvec <= 16) GLT_LAUNCH_VEC(16);
+    else GLT_LAUNCH_VEC(32);
+#undef GLT_LAUNCH_VEC
+    return;
+  }
+  const int g = grid_for(n, 8);
+  if (t.row_bytes % 4 == 0 && out_row_bytes % 4 == 0)
+    k_gather_scalar<uint32_t><<<g, 256, 0, s>>>(t, idx, id2index, n, n_dev, o, out_row_bytes);
+  else if (t.row_bytes % 2 == 0 && out_row_bytes % 2 == 0)
+    k_gather_scalar<uint16_t><<<g, 256, 0, s>>>(t, idx, id2index, n, n_dev, o, out_row_bytes);
+  else
+    k_gather_scalar<uint8_t><<<g, 256, 0, s>>>(t, idx, id2index, n, n_dev, o, out_row_bytes);
+}
+
+void launch_gather_i64(RowTable t, const int64_t* idx, int64_t n, const int32_t* n_dev,
+                       int64_t* out, cudaStream_t s) {
+  if (n <= 0) return;
+  k_gather_i64<<<grid_for(n, 256), 256, 0, s>>>(t, idx, n, n_dev, out);
+}
+
+}  // namespace glt

@@ -1,0 +1,193 @@
+// Host-visible declarations of the sm_100a kernels (torch-free: raw pointers and
+// a cudaStream_t) so the .cu files compile in seconds and the binding layer is
+// the only translation unit that sees torch headers.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace glt {
+
+constexpr int kMaxParts = 16;  // 8 GPUs of one NVSwitch box + optional host tiers
+
+// One CSR shard of a range-partitioned graph.  Pointers may live in local HBM,
+// in a peer GPU's HBM (mapped over NVLink via CUDA IPC) or in pinned host
+// memory; the kernels dereference them directly -- this is the generalisation
+// of the reference's pointer-table gather (csrc/cuda/unified_tensor.cu:35-81)
+// to graph topology.
+struct CsrShard {
+  const int64_t* indptr;   // [row_end - row_begin + 1], shard-local offsets
+  const void* indices;     // int32 or int64 global column ids
+  const int64_t* eids;     // optional global edge ids
+  const float* weights;    // optional edge weights
+  int64_t row_begin;       // first global row id owned by this shard
+  int64_t row_end;         // one past the last owned row
+};
+
+struct GraphTable {
+  int num_parts;
+  int idx_bytes;  // 4: int32 column ids, 8: int64
+  CsrShard parts[kMaxParts];
+};
+
+// Range-partitioned row store (features / labels).  Part p holds rows
+// [row_begin[p], row_begin[p+1]).
+struct RowTable {
+  int num_parts;
+  int64_t row_bytes;
+  const void* base[kMaxParts];
+  int64_t row_begin[kMaxParts + 1];
+};
+
+// Device-resident id -> local-id hash table (open addressing, linear probe).
+struct HashTable {
+  int64_t* keys;   // capacity slots, empty = -1
+  int32_t* vals;   // dense local id of the key in this slot
+  int32_t* aux;    // first-occurrence index (ordered insert only)
+  uint32_t mask;   // capacity - 1
+};
+
+// Per-batch device-side bookkeeping; the host never reads it on the hot path.
+//   cum[h]      : number of local nodes after hop h-1 (cum[0] = 0, cum[1] = #seeds)
+//   edges[h]    : number of sampled edges of hop h
+struct BatchCounters {
+  int32_t* cum;     // [max_hops + 2]
+  int32_t* edges;   // [max_hops]
+  int32_t* cursor;  // running number of local nodes
+};
+
+// ---- sampling.cu -----------------------------------------------------------
+void launch_table_clear(HashTable t, cudaStream_t s);
+
+// Ordered (first-occurrence) insertion of the seed ids.  Writes nodes[0..n0),
+// seed_local[i] (local id of seeds[i]), cum[0]=0, cum[1]=n0, cursor=n0.
+void launch_init_seeds(const int64_t* seeds, int n_seeds, const int32_t* n_seeds_dev,
+                       HashTable t, int64_t* nodes, int32_t* seed_local, int32_t* scratch,
+                       BatchCounters c, cudaStream_t s);
+
+struct HopArgs {
+  GraphTable g;
+  HashTable t;
+  BatchCounters c;
+  int64_t* nodes;       // local -> global id, appended by this hop
+  int32_t* ell;         // [cap_rows * k] slot ids -> local ids after relabel; -1 = empty
+  int64_t* ell_eids;    // optional [cap_rows * k]
+  int32_t* deg;         // [cap_nodes] sampled degree per target local id
+  int hop;              // reads frontier [cum[hop], cum[hop+1])
+  int k;                // fanout (>0)
+  int cap_rows;         // worst-case frontier size
+  int cap_nodes;        // node arena capacity (overflow guard)
+  int weighted;         // 1: exponential-race weighted sampling
+  int replace;          // 1: with replacement
+  uint64_t seed;
+  uint32_t stream;
+};
+void launch_sample_hop(const HopArgs& a, cudaStream_t s);
+void launch_relabel_hop(const HopArgs& a, cudaStream_t s);
+
+// One-hop API sampler (NeighborOutput): fixed-stride output, no dedup.
+void launch_sample_one_hop(GraphTable g, const int64_t* seeds, int n, int k, int weighted,
+                           int replace, uint64_t seed, uint32_t stream, int64_t* out_nbrs,
+                           int64_t* out_eids, int32_t* out_cnt, cudaStream_t s);
+// Degrees of arbitrary rows (all-neighbour fanout sizing).
+void launch_lookup_degree(GraphTable g, const int64_t* ids, int n, int64_t* out, cudaStream_t s);
+// Full-neighbourhood copy: out[offs[i] .. offs[i+1]) = N(ids[i]).
+void launch_copy_neighbors(GraphTable g, const int64_t* ids, int n, const int64_t* offs,
+                           int64_t* out_nbrs, int64_t* out_eids, cudaStream_t s);
+
+// ELL -> COO of one hop with exact offsets (exclusive scan of deg over the frontier).
+void launch_ell_to_coo(const int32_t* ell, const int64_t* ell_eids, const int32_t* deg,
+                       const int64_t* offs, const int32_t* cum, int hop, int k, int cap_rows,
+                       int64_t* rows, int64_t* cols, int64_t* eids, cudaStream_t s);
+
+// Generic table ops for the inducer API (unordered insert + lookup).
+void launch_table_insert(HashTable t, const int64_t* keys, int64_t n, int64_t* nodes,
+                         int32_t* cursor, int cap_nodes, int32_t* out_slots, cudaStream_t s);
+void launch_table_resolve(HashTable t, int32_t* slots_inout, int64_t n, cudaStream_t s);
+void launch_table_lookup(HashTable t, const int64_t* keys, int64_t n, int32_t* out, cudaStream_t s);
+
+// ---- negative / subgraph / walk / prob (graph_ops.cu) ------------------------
+void launch_negative_sample(GraphTable g, int64_t num_rows, int64_t num_cols, int req, int trials,
+                            int padding, uint64_t seed, uint32_t stream, int64_t* out_rows,
+                            int64_t* out_cols, int32_t* out_count, cudaStream_t s);
+void launch_subgraph_count(GraphTable g, HashTable t, const int64_t* nodes, int n, int64_t* cnt,
+                           cudaStream_t s);
+void launch_subgraph_fill(GraphTable g, HashTable t, const int64_t* nodes, int n,
+                          const int64_t* offs, int64_t* rows, int64_t* cols, int64_t* eids,
+                          cudaStream_t s);
+void launch_random_walk(GraphTable g, const int64_t* starts, int n, int walk_len, float p, float q,
+                        uint64_t seed, uint32_t stream, int64_t* out, cudaStream_t s);
+void launch_nbr_prob(GraphTable g, GraphTable nbr_g, const float* last, const float* nbr_last,
+                     int64_t n, int64_t n_nbr, int k, float* cur, cudaStream_t s);
+
+// ---- gather.cu ---------------------------------------------------------------
+// out[i, :] = table[idx[i]] (idx optionally remapped through id2index); rows
+// with idx < 0 or i >= *n_dev (when n_dev != nullptr) are zero-filled.
+void launch_gather_rows(RowTable t, const int64_t* idx, const int64_t* id2index, int64_t n,
+                        const int32_t* n_dev, void* out, int64_t out_row_bytes, cudaStream_t s);
+void launch_gather_i64(RowTable t, const int64_t* idx, int64_t n, const int32_t* n_dev,
+                       int64_t* out, cudaStream_t s);
+
+// ---- sage.cu (GraphSAGE engine kernels) ---------------------------------------
+struct SageAggArgs {
+  // source rows: either a RowTable indexed by global id (layer 1) or a dense
+  // local matrix (deeper layers, src_local != nullptr).
+  RowTable feat;
+  const int64_t* nodes;         // local -> global id (layer 1)
+  const void* src_local;        // bf16 [n_src, d] (deeper layers)
+  int d;                        // feature width (elements, multiple of 8)
+  const int32_t* cum;           // device node counts
+  int n_hops_targets;           // targets = cum[n_hops_targets]
+  int cap_targets;
+  // ELL blocks per hop (targets of hop h use ell[h] with stride k[h])
+  const int32_t* ell[4];
+  int k[4];
+  const int32_t* deg;
+  void* out;                    // bf16 [cap_targets, 2d] = [mean | self]
+};
+void launch_sage_aggregate(const SageAggArgs& a, cudaStream_t s);
+
+struct SageScatterArgs {
+  const void* dA;               // bf16 [cap_targets, 2d]
+  int d;
+  const int32_t* cum;
+  int n_hops_targets;
+  int cap_targets;
+  const int32_t* ell[4];
+  int k[4];
+  const int32_t* deg;
+  float* dH;                    // fp32 [cap_src, d], pre-zeroed
+};
+void launch_sage_scatter_bwd(const SageScatterArgs& a, cudaStream_t s);
+
+// dPre = (Z > 0) ? bf16(dH) : 0 for rows < cum[n_hops]; 0 beyond.
+void launch_relu_bwd_cast(const float* dH, const void* Z, const int32_t* cum, int n_hops, int cap,
+                          int d, void* dPre, cudaStream_t s);
+// bias + relu epilogue over valid rows (zero beyond): Z = relu(Z + b)
+void launch_bias_relu(void* Z, const void* bias, const int32_t* cum, int n_hops, int cap, int d,
+                      int relu, cudaStream_t s);
+// loss = mean NLL(log_softmax(logits[:n0, :C]), y); dlogits = (softmax - onehot)/n0
+void launch_softmax_nll(const void* logits, int ld, int C, const int64_t* y, const int32_t* cum,
+                        int cap, float* loss, void* dlogits, int32_t* correct, cudaStream_t s);
+// flat fp32 Adam over [n] with bf16 shadow copy refresh.
+void launch_adam(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr,
+                 float b1, float b2, float eps, float wd, const int32_t* step_dev, float gscale,
+                 cudaStream_t s);
+void launch_bf16_to_f32(const void* src, float* dst, int64_t n, cudaStream_t s);
+
+// ---- sage_tc.cu (tcgen05 fused gather+aggregate+GEMM) -------------------------
+struct SageFusedArgs {
+  SageAggArgs agg;              // agg.out may be nullptr (A tile is not materialised)
+  const void* w_packed;         // bf16, UMMA SWIZZLE_128B K-major image, [K/64][N][64]
+  const void* bias;             // bf16 [N]
+  int n_out;                    // N (multiple of 16, <= 256)
+  int relu;
+  void* z;                      // bf16 [cap_targets, N]
+  void* a_save;                 // optional bf16 [cap_targets, 2d] for backward
+};
+int sage_fused_supported(int d, int n_out);
+void launch_sage_fused(const SageFusedArgs& a, int num_sms, cudaStream_t s);
+// W [N, K] row-major bf16 -> packed swizzled image used by launch_sage_fused.
+void launch_pack_weight(const void* w, int n, int k, void* packed, cudaStream_t s);
+
+}  // namespace glt

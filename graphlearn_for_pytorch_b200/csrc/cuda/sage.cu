@@ -1,0 +1,321 @@
+// GraphSAGE engine kernels (SIMT side): neighbour-mean aggregation straight from
+// the sampler's per-hop ELL blocks, its scatter backward, fused loss and Adam.
+// Everything reads its extents from device counters (BatchCounters::cum) and is
+// launched with worst-case grids, so one training step is a fixed launch
+// sequence that is captured into a CUDA graph -- no host sync anywhere.
+//
+// The reference has no model code (PyG SAGEConv in examples/train_sage_ogbn_products.py:30-59
+// does gather -> scatter-mean -> two Linear); the aggregation here consumes the
+// feature table *in place* (local or peer HBM) like GatherTensorKernel
+// (csrc/cuda/unified_tensor.cu:47-81) but never materialises x[n_id].
+#include "device_utils.cuh"
+
+namespace glt {
+
+namespace {
+
+struct HopLoc { int hop; int row; };
+
+__device__ __forceinline__ HopLoc locate(const int32_t* cum, int n_hops, int t) {
+  HopLoc l; l.hop = 0; l.row = t;
+#pragma unroll 1
+  for (int h = 0; h < n_hops; ++h) {
+    const int b = cum[h], e = cum[h + 1];
+    if (t >= b && t < e) { l.hop = h; l.row = t - b; break; }
+  }
+  return l;
+}
+
+__device__ __forceinline__ const uint8_t* src_row(const SageAggArgs& a, int s) {
+  if (a.src_local) return reinterpret_cast<const uint8_t*>(a.src_local) + static_cast<int64_t>(s) * a.d * 2;
+  return row_ptr(a.feat, a.nodes[s]);
+}
+
+// LPR lanes cooperate on one target row; each lane owns VPL 16-byte vectors.
+template <int LPR, int VPL>
+__global__ void __launch_bounds__(256) k_sage_aggregate(SageAggArgs a) {
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % LPR;
+  const int gw = lane / LPR;
+  const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (gw * LPR));
+  const int T = min(a.cum[a.n_hops_targets], a.cap_targets);
+  const int wpb = blockDim.x >> 5;
+  const int nvec = a.d >> 3;
+  for (int base = (blockIdx.x * wpb + (threadIdx.x >> 5)) * RPW; base < T; base += gridDim.x * wpb * RPW) {
+    const int t = base + gw;
+    const bool valid = t < T;
+    float acc[VPL][8];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[v][i] = 0.f;
+    int dg = 0, k = 0;
+    const int32_t* ell = nullptr;
+    if (valid) {
+      const HopLoc l = locate(a.cum, a.n_hops_targets, t);
+      dg = a.deg[t];
+      k = a.k[l.hop];
+      ell = a.ell[l.hop] + static_cast<int64_t>(l.row) * k;
+    }
+    for (int j0 = 0; j0 < dg; j0 += LPR) {
+      const uint8_t* my_ptr = nullptr;
+      if (j0 + gl < dg) {
+        const int s = ell[j0 + gl];
+        if (s >= 0) my_ptr = src_row(a, s);
+      }
+      const int cnt = min(LPR, dg - j0);
+      for (int jj = 0; jj < cnt; ++jj) {
+        const uint8_t* p = reinterpret_cast<const uint8_t*>(
+            __shfl_sync(gmask, reinterpret_cast<unsigned long long>(my_ptr), jj, LPR));
+        if (p == nullptr) continue;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+          const int c = v * LPR + gl;
+          if (c < nvec) bf16x8_accum(ld_nc_v4(p + c * 16), acc[v]);
+        }
+      }
+    }
+    if (!valid) continue;
+    const float inv = dg > 0 ? 1.f / static_cast<float>(dg) : 0.f;
+    uint8_t* o = reinterpret_cast<uint8_t*>(a.out) + static_cast<int64_t>(t) * a.d * 4;  // 2d bf16
+    const uint8_t* self = src_row(a, t);
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const int c = v * LPR + gl;
+      if (c < nvec) {
+        reinterpret_cast<uint4*>(o)[c] = pack_bf16x8(acc[v], inv);
+        reinterpret_cast<uint4*>(o + a.d * 2)[c] =
+            self ? ld_nc_v4(self + c * 16) : make_uint4(0, 0, 0, 0);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void atomic_add8(float* dst, const float* v) {
+  atomicAdd(reinterpret_cast<float4*>(dst), make_float4(v[0], v[1], v[2], v[3]));
+  atomicAdd(reinterpret_cast<float4*>(dst + 4), make_float4(v[4], v[5], v[6], v[7]));
+}
+
+template <int LPR, int VPL>
+__global__ void __launch_bounds__(256) k_sage_scatter_bwd(SageScatterArgs a) {
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % LPR;
+  const int gw = lane / LPR;
+  const int T = min(a.cum[a.n_hops_targets], a.cap_targets);
+  const int wpb = blockDim.x >> 5;
+  const int nvec = a.d >> 3;
+  for (int base = (blockIdx.x * wpb + (threadIdx.x >> 5)) * RPW; base < T; base += gridDim.x * wpb * RPW) {
+    const int t = base + gw;
+    if (t >= T) continue;
+    const HopLoc l = locate(a.cum, a.n_hops_targets, t);
+    const int dg = a.deg[t];
+    const int k = a.k[l.hop];
+    const int32_t* ell = a.ell[l.hop] + static_cast<int64_t>(l.row) * k;
+    const uint8_t* g = reinterpret_cast<const uint8_t*>(a.dA) + static_cast<int64_t>(t) * a.d * 4;
+    const float inv = dg > 0 ? 1.f / static_cast<float>(dg) : 0.f;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const int c = v * LPR + gl;
+      if (c >= nvec) continue;
+      float gn[8], gs[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) gn[i] = gs[i] = 0.f;
+      bf16x8_accum(reinterpret_cast<const uint4*>(g)[c], gn);
+      bf16x8_accum(reinterpret_cast<const uint4*>(g + a.d * 2)[c], gs);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) gn[i] *= inv;
+      atomic_add8(a.dH + static_cast<int64_t>(t) * a.d + c * 8, gs);
+      for (int j = 0; j < dg; ++j) {
+        const int s = ell[j];
+        if (s >= 0) atomic_add8(a.dH + static_cast<int64_t>(s) * a.d + c * 8, gn);
+      }
+    }
+  }
+}
+
+__global__ void k_relu_bwd_cast(const float* dH, const __nv_bfloat16* Z, const int32_t* cum,
+                                int n_hops, int cap, int d, __nv_bfloat16* dPre) {
+  const int T = min(cum[n_hops], cap);
+  const int64_t n8 = static_cast<int64_t>(cap) * d / 8;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t e = i * 8;
+    const int row = static_cast<int>(e / d);
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (row < T) {
+      const float4 g0 = reinterpret_cast<const float4*>(dH + e)[0];
+      const float4 g1 = reinterpret_cast<const float4*>(dH + e)[1];
+      float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      float z[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) z[q] = 0.f;
+      bf16x8_accum(*reinterpret_cast<const uint4*>(Z + e), z);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) g[q] = z[q] > 0.f ? g[q] : 0.f;
+      o = pack_bf16x8(g, 1.f);
+    }
+    *reinterpret_cast<uint4*>(dPre + e) = o;
+  }
+}
+
+__global__ void k_bias_relu(__nv_bfloat16* Z, const __nv_bfloat16* bias, const int32_t* cum,
+                            int n_hops, int cap, int d, int relu) {
+  const int T = min(cum[n_hops], cap);
+  const int64_t n8 = static_cast<int64_t>(T) * d / 8;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t e = i * 8;
+    const int col = static_cast<int>(e % d);
+    float z[8], b[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) z[q] = b[q] = 0.f;
+    bf16x8_accum(*reinterpret_cast<const uint4*>(Z + e), z);
+    bf16x8_accum(*reinterpret_cast<const uint4*>(bias + col), b);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { z[q] += b[q]; if (relu) z[q] = fmaxf(z[q], 0.f); }
+    *reinterpret_cast<uint4*>(Z + e) = pack_bf16x8(z, 1.f);
+  }
+}
+
+// warp per seed row: log-softmax + NLL forward and backward in one pass.
+__global__ void k_softmax_nll(const __nv_bfloat16* logits, int ld, int C, const int64_t* y,
+                              const int32_t* cum, int cap, float* loss, __nv_bfloat16* dlogits,
+                              int32_t* correct) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int n0 = min(cum[1], cap);
+  const float invn = n0 > 0 ? 1.f / static_cast<float>(n0) : 0.f;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < cap; r += gridDim.x * wpb) {
+    __nv_bfloat16* dl = dlogits + static_cast<int64_t>(r) * ld;
+    if (r >= n0) {
+      for (int c = lane; c < ld; c += 32) dl[c] = __float2bfloat16(0.f);
+      continue;
+    }
+    const __nv_bfloat16* x = logits + static_cast<int64_t>(r) * ld;
+    float mx = -3.4e38f;
+    int arg = 0;
+    for (int c = lane; c < C; c += 32) {
+      const float v = __bfloat162float(x[c]);
+      if (v > mx) { mx = v; arg = c; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, mx, off);
+      const int oa = __shfl_xor_sync(0xffffffffu, arg, off);
+      if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }
+    }
+    float sum = 0.f;
+    for (int c = lane; c < C; c += 32) sum += __expf(__bfloat162float(x[c]) - mx);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    const float lse = mx + __logf(sum);
+    const int64_t label = y[r];
+    for (int c = lane; c < ld; c += 32) {
+      float g = 0.f;
+      if (c < C) {
+        const float p = __expf(__bfloat162float(x[c]) - lse);
+        g = (p - (c == label ? 1.f : 0.f)) * invn;
+      }
+      dl[c] = __float2bfloat16(g);
+    }
+    if (lane == 0) {
+      const float xl = (label >= 0 && label < C) ? __bfloat162float(x[label]) : lse;
+      atomicAdd(loss, (lse - xl) * invn);
+      if (correct && arg == label) atomicAdd(correct, 1);
+    }
+  }
+}
+
+__global__ void k_adam(float* p, const float* g, float* m, float* v, __nv_bfloat16* pb, int64_t n,
+                       float lr, float b1, float b2, float eps, float wd, const int32_t* step_dev,
+                       float gscale) {
+  const float t = static_cast<float>(*step_dev);
+  const float c1 = 1.f - __powf(b1, t), c2 = 1.f - __powf(b2, t);
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float gi = g[i] * gscale + wd * p[i];
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    const float upd = (mi / c1) / (sqrtf(vi / c2) + eps);
+    const float pi = p[i] - lr * upd;
+    p[i] = pi;
+    if (pb) pb[i] = __float2bfloat16(pi);
+  }
+}
+
+__global__ void k_bf16_to_f32(const __nv_bfloat16* s, float* d, int64_t n) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    d[i] = __bfloat162float(s[i]);
+}
+
+inline int grid_for(int64_t items, int per_block, int max_blocks = 148 * 16) {
+  int64_t b = (items + per_block - 1) / per_block;
+  if (b < 1) b = 1;
+  if (b > max_blocks) b = max_blocks;
+  return static_cast<int>(b);
+}
+
+}  // namespace
+
+#define GLT_DISPATCH_WIDTH(D, ...)                                            \
+  do {                                                                        \
+    const int nvec_ = (D) / 8;                                                \
+    if (nvec_ <= 4) { constexpr int LPR = 4, VPL = 1; __VA_ARGS__; }          \
+    else if (nvec_ <= 8) { constexpr int LPR = 8, VPL = 1; __VA_ARGS__; }     \
+    else if (nvec_ <= 16) { constexpr int LPR = 16, VPL = 1; __VA_ARGS__; }   \
+    else if (nvec_ <= 32) { constexpr int LPR = 32, VPL = 1; __VA_ARGS__; }   \
+    else if (nvec_ <= 64) { constexpr int LPR = 32, VPL = 2; __VA_ARGS__; }   \
+    else { constexpr int LPR = 32, VPL = 4; __VA_ARGS__; }                    \
+  } while (0)
+
+void launch_sage_aggregate(const SageAggArgs& a, cudaStream_t s) {
+  GLT_DISPATCH_WIDTH(a.d, {
+    k_sage_aggregate<LPR, VPL><<<grid_for(a.cap_targets, 8 * (32 / LPR)), 256, 0, s>>>(a);
+  });
+}
+
+void launch_sage_scatter_bwd(const SageScatterArgs& a, cudaStream_t s) {
+  GLT_DISPATCH_WIDTH(a.d, {
+    k_sage_scatter_bwd<LPR, VPL><<<grid_for(a.cap_targets, 8 * (32 / LPR)), 256, 0, s>>>(a);
+  });
+}
+
+void launch_relu_bwd_cast(const float* dH, const void* Z, const int32_t* cum, int n_hops, int cap,
+                          int d, void* dPre, cudaStream_t s) {
+  k_relu_bwd_cast<<<grid_for(static_cast<int64_t>(cap) * d / 8, 256), 256, 0, s>>>(
+      dH, reinterpret_cast<const __nv_bfloat16*>(Z), cum, n_hops, cap, d,
+      reinterpret_cast<__nv_bfloat16*>(dPre));
+}
+
+void launch_bias_relu(void* Z, const void* bias, const int32_t* cum, int n_hops, int cap, int d,
+                      int relu, cudaStream_t s) {
+  k_bias_relu<<<grid_for(static_cast<int64_t>(cap) * d / 8, 256), 256, 0, s>>>(
+      reinterpret_cast<__nv_bfloat16*>(Z), reinterpret_cast<const __nv_bfloat16*>(bias), cum, n_hops,
+      cap, d, relu);
+}
+
+void launch_softmax_nll(const void* logits, int ld, int C, const int64_t* y, const int32_t* cum,
+                        int cap, float* loss, void* dlogits, int32_t* correct, cudaStream_t s) {
+  cudaMemsetAsync(loss, 0, sizeof(float), s);
+  if (correct) cudaMemsetAsync(correct, 0, sizeof(int32_t), s);
+  k_softmax_nll<<<grid_for(cap, 8), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(logits), ld,
+                                                  C, y, cum, cap, loss,
+                                                  reinterpret_cast<__nv_bfloat16*>(dlogits), correct);
+}
+
+void launch_adam(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr,
+                 float b1, float b2, float eps, float wd, const int32_t* step_dev, float gscale,
+                 cudaStream_t s) {
+  k_adam<<<grid_for(n, 256, 148 * 4), 256, 0, s>>>(p, g, m, v, reinterpret_cast<__nv_bfloat16*>(p_bf16),
+                                                   n, lr, b1, b2, eps, wd, step_dev, gscale);
+}
+
+void launch_bf16_to_f32(const void* src, float* dst, int64_t n, cudaStream_t s) {
+  k_bf16_to_f32<<<grid_for(n, 256), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(src), dst, n);
+}
+
+}  // namespace glt

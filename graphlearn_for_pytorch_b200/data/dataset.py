@@ -1,0 +1,234 @@
+"""Dataset: graph topology + node/edge features + labels + splits, homo or hetero.
+
+API parity: reference python/data/dataset.py:30-515 (init_graph, init_node_features,
+init_edge_features, init_node_labels, init_node_split, random_node_split, getters,
+IPC pickling).  Hetero data are dicts keyed by node/edge type.
+"""
+from multiprocessing.reduction import ForkingPickler
+from typing import Callable, Dict, List, Optional, Union
+
+import torch
+
+from ..typing import EdgeType, NodeType, TensorDataType
+from ..utils.tensor import convert_to_tensor, share_memory, squeeze
+from .feature import DeviceGroup, Feature
+from .graph import Graph, Topology
+from .reorder import sort_by_in_degree  # noqa: F401 (re-export convenience)
+
+
+class Dataset(object):
+  def __init__(self, graph=None, node_features=None, edge_features=None, node_labels=None,
+               edge_dir: str = 'out', node_split=None):
+    self.graph = graph
+    self.node_features = node_features
+    self.edge_features = edge_features
+    self.node_labels = node_labels
+    self.edge_dir = edge_dir
+    self._directed = None
+    self.train_idx = self.val_idx = self.test_idx = None
+    if node_split is not None:
+      self.train_idx, self.val_idx, self.test_idx = node_split
+
+  # ------------------------------------------------------------------ graph
+  def init_graph(self, edge_index=None, edge_ids=None, edge_weights=None,
+                 layout: Union[str, Dict[EdgeType, str]] = 'COO', graph_mode: str = 'ZERO_COPY',
+                 directed: bool = False, device: Optional[int] = None,
+                 num_nodes: Union[int, Dict[NodeType, int], None] = None):
+    edge_index = convert_to_tensor(edge_index, dtype=torch.int64)
+    edge_ids = convert_to_tensor(edge_ids, dtype=torch.int64)
+    edge_weights = convert_to_tensor(edge_weights, dtype=torch.float32)
+    self._directed = directed
+    if edge_index is None:
+      return
+    target = 'CSR' if self.edge_dir == 'out' else 'CSC'
+    if isinstance(edge_index, dict):
+      edge_ids = edge_ids or {}
+      edge_weights = edge_weights or {}
+      if not isinstance(layout, dict):
+        layout = {et: layout for et in edge_index}
+      self.graph = {}
+      for et, ei in edge_index.items():
+        n = None
+        if isinstance(num_nodes, dict):
+          n = num_nodes.get(et[0] if self.edge_dir == 'out' else et[2])
+        topo = Topology(ei, edge_ids.get(et), edge_weights.get(et), input_layout=layout[et],
+                        layout=target, num_nodes=n)
+        g = Graph(topo, graph_mode, device)
+        g.lazy_init()
+        self.graph[et] = g
+    else:
+      topo = Topology(edge_index, edge_ids, edge_weights, input_layout=layout, layout=target,
+                      num_nodes=num_nodes if isinstance(num_nodes, int) else None)
+      self.graph = Graph(topo, graph_mode, device)
+      self.graph.lazy_init()
+
+  # ------------------------------------------------------------------ splits
+  def random_node_split(self, num_val: Union[int, float], num_test: Union[int, float]):
+    """Random train/val/test split of labelled nodes (per node type for hetero)."""
+    if isinstance(self.node_labels, dict):
+      tr, va, te = {}, {}, {}
+      for nt, lab in self.node_labels.items():
+        tr[nt], va[nt], te[nt] = random_split(lab.shape[0], num_val, num_test)
+      self.train_idx, self.val_idx, self.test_idx = tr, va, te
+    else:
+      n = self.node_labels.shape[0] if self.node_labels is not None else self.graph.row_count
+      self.train_idx, self.val_idx, self.test_idx = random_split(n, num_val, num_test)
+
+  def init_node_split(self, node_split=None):
+    if node_split is not None:
+      self.train_idx, self.val_idx, self.test_idx = squeeze(convert_to_tensor(node_split))
+
+  def load_vineyard(self, *args, **kwargs):
+    """GraphScope/vineyard ingestion is an optional plug-in (reference dataset.py:155-234);
+    vineyard is not available in this build."""
+    raise NotImplementedError('vineyard loader plug-in is not built (WITH_VINEYARD)')
+
+  # ------------------------------------------------------------------ features
+  def init_node_features(self, node_feature_data=None, id2idx=None,
+                         sort_func: Optional[Callable] = None,
+                         split_ratio: Union[float, Dict[NodeType, float]] = 0.0,
+                         device_group_list: Optional[List[DeviceGroup]] = None,
+                         device: Optional[int] = None, with_gpu: bool = True,
+                         dtype: torch.dtype = torch.float32):
+    if node_feature_data is None:
+      return
+    self.node_features = _build_features(
+      convert_to_tensor(node_feature_data, dtype), convert_to_tensor(id2idx), split_ratio,
+      device_group_list, device, with_gpu, dtype, sort_func, self._topo_for_sort)
+
+  def init_edge_features(self, edge_feature_data=None, id2idx=None,
+                         split_ratio: Union[float, Dict[EdgeType, float]] = 0.0,
+                         device_group_list: Optional[List[DeviceGroup]] = None,
+                         device: Optional[int] = None, with_gpu: bool = True,
+                         dtype: torch.dtype = torch.float32):
+    if edge_feature_data is None:
+      return
+    self.edge_features = _build_features(
+      convert_to_tensor(edge_feature_data, dtype), convert_to_tensor(id2idx), split_ratio,
+      device_group_list, device, with_gpu, dtype, None, None)
+
+  def _topo_for_sort(self, ntype=None):
+    if self.graph is None:
+      return None
+    if isinstance(self.graph, dict):
+      # in-degree statistics of `ntype`: any relation pointing at it
+      for et, g in self.graph.items():
+        dst = et[2] if self.edge_dir == 'out' else et[0]
+        if dst == ntype and g.topo is not None:
+          return g.topo
+      return None
+    return self.graph.topo
+
+  def init_node_labels(self, node_label_data=None):
+    if node_label_data is not None:
+      self.node_labels = squeeze(convert_to_tensor(node_label_data))
+
+  # ------------------------------------------------------------------ IPC
+  def share_ipc(self):
+    self.node_labels = share_memory(self.node_labels)
+    self.train_idx = share_memory(self.train_idx)
+    self.val_idx = share_memory(self.val_idx)
+    self.test_idx = share_memory(self.test_idx)
+    return (self.graph, self.node_features, self.edge_features, self.node_labels, self.edge_dir,
+            (self.train_idx, self.val_idx, self.test_idx))
+
+  @classmethod
+  def from_ipc_handle(cls, ipc_handle):
+    g, nf, ef, nl, edge_dir, split = ipc_handle
+    return cls(g, nf, ef, nl, edge_dir, split)
+
+  # ------------------------------------------------------------------ getters
+  def get_graph(self, etype: Optional[EdgeType] = None):
+    if isinstance(self.graph, Graph):
+      return self.graph
+    if isinstance(self.graph, dict):
+      return self.graph.get(etype)
+    return None
+
+  def get_node_types(self):
+    if isinstance(self.graph, dict):
+      if not hasattr(self, '_node_types'):
+        nts = []
+        for et in self.graph:
+          for t in (et[0], et[2]):
+            if t not in nts:
+              nts.append(t)
+        self._node_types = nts
+      return self._node_types
+    return None
+
+  def get_edge_types(self):
+    if isinstance(self.graph, dict):
+      return list(self.graph.keys())
+    return None
+
+  def get_node_feature(self, ntype: Optional[NodeType] = None):
+    if isinstance(self.node_features, Feature):
+      return self.node_features
+    if isinstance(self.node_features, dict):
+      return self.node_features.get(ntype)
+    return None
+
+  def get_edge_feature(self, etype: Optional[EdgeType] = None):
+    if isinstance(self.edge_features, Feature):
+      return self.edge_features
+    if isinstance(self.edge_features, dict):
+      return self.edge_features.get(etype)
+    return None
+
+  def get_node_label(self, ntype: Optional[NodeType] = None):
+    if isinstance(self.node_labels, torch.Tensor):
+      return self.node_labels
+    if isinstance(self.node_labels, dict):
+      return self.node_labels.get(ntype)
+    return None
+
+  def __getitem__(self, key):
+    return getattr(self, key, None)
+
+  def __setitem__(self, key, value):
+    setattr(self, key, value)
+
+
+def _build_one(feat, id2idx, ratio, groups, device, with_gpu, dtype, sort_func, topo):
+  if sort_func is not None and topo is not None and id2idx is None:
+    feat, id2idx = sort_func(feat, ratio, topo)
+  return Feature(feat, id2idx, ratio, groups, device, with_gpu, dtype)
+
+
+def _build_features(feature_data, id2idx, split_ratio, device_group_list, device, with_gpu, dtype,
+                    sort_func, topo_fn):
+  if feature_data is None:
+    return None
+  if isinstance(feature_data, dict):
+    out = {}
+    for t, feat in feature_data.items():
+      ratio = split_ratio.get(t, 0.0) if isinstance(split_ratio, dict) else split_ratio
+      i2i = id2idx.get(t) if isinstance(id2idx, dict) else None
+      topo = topo_fn(t) if (topo_fn is not None and isinstance(t, str)) else None
+      out[t] = _build_one(feat, i2i, ratio, device_group_list, device, with_gpu, dtype, sort_func, topo)
+    return out
+  topo = topo_fn() if topo_fn is not None else None
+  return _build_one(feature_data, id2idx, split_ratio, device_group_list, device, with_gpu, dtype,
+                    sort_func, topo)
+
+
+def random_split(num_total: int, num_val: Union[int, float], num_test: Union[int, float]):
+  num_val = int(num_total * num_val) if isinstance(num_val, float) else int(num_val)
+  num_test = int(num_total * num_test) if isinstance(num_test, float) else int(num_test)
+  perm = torch.randperm(num_total)
+  val = perm[:num_val]
+  test = perm[num_val:num_val + num_test]
+  train = perm[num_val + num_test:]
+  return train, val, test
+
+
+def rebuild_dataset(ipc_handle):
+  return Dataset.from_ipc_handle(ipc_handle)
+
+
+def reduce_dataset(dataset: Dataset):
+  return (rebuild_dataset, (dataset.share_ipc(),))
+
+
+ForkingPickler.register(Dataset, reduce_dataset)

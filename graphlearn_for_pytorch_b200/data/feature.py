@@ -1,0 +1,192 @@
+"""Feature store with a hot GPU tier and a cold pinned-host tier.
+
+API parity: reference python/data/feature.py:32-283.  Rows [0, split_ratio*N) of the
+(hotness-sorted) feature tensor are the hot part: sharded evenly over the GPUs of
+the caller's DeviceGroup (each group holds one full replica of the hot rows,
+peers inside the group are read over NVLink by the gather kernel); the rest is
+pinned host memory read in place.  `id2index` (id -> row after reordering) is
+applied on the device inside the gather kernel.
+"""
+import threading
+from multiprocessing.reduction import ForkingPickler
+from typing import List, Optional
+
+import torch
+
+from ..utils.device import get_available_device
+from .unified_tensor import UnifiedTensor
+
+
+class DeviceGroup(object):
+  """A set of GPUs with mutual peer access (an NVLink clique / one NVSwitch box)."""
+
+  def __init__(self, group_id: int, device_list: List):
+    self.group_id = group_id
+    self.device_list = [d.index if isinstance(d, torch.device) else int(d) for d in device_list]
+
+  @property
+  def size(self):
+    return len(self.device_list)
+
+
+class Feature(object):
+  def __init__(self, feature_tensor: torch.Tensor, id2index: Optional[torch.Tensor] = None,
+               split_ratio: float = 0.0, device_group_list: Optional[List[DeviceGroup]] = None,
+               device: Optional[int] = None, with_gpu: bool = True,
+               dtype: torch.dtype = torch.float32):
+    self.feature_tensor = feature_tensor.to(dtype) if feature_tensor is not None and \
+        feature_tensor.dtype != dtype else feature_tensor
+    self.id2index = id2index
+    self.split_ratio = float(split_ratio)
+    self.device_group_list = device_group_list
+    self.device = device.index if isinstance(device, torch.device) else device
+    self.with_gpu = bool(with_gpu) and torch.cuda.is_available()
+    self.dtype = dtype
+    self._lock = threading.RLock()
+    self._unified: Optional[UnifiedTensor] = None
+    self._id2index_dev = None
+    self._ipc_handle = None
+    self._cuda_parts_by_group = None  # group_id -> list of per-device shards
+    self._cpu_part = None
+    self._shape = list(feature_tensor.shape) if feature_tensor is not None else None
+
+  # ------------------------------------------------------------------ lookup
+  def __getitem__(self, ids: torch.Tensor) -> torch.Tensor:
+    if not self.with_gpu:
+      return self.cpu_get(ids)
+    self.lazy_init()
+    dev = torch.device('cuda', self.device)
+    ids = ids.to(dev, dtype=torch.int64).contiguous()
+    out = self._unified._table().gather(ids, self._id2index_dev, 0)
+    tail = self._shape[1:]
+    return out if len(tail) == 1 else out.view(ids.numel(), *tail)
+
+  def cpu_get(self, ids: torch.Tensor) -> torch.Tensor:
+    """Host-side lookup (used by the RPC callee in multi-node mode)."""
+    ids = ids.to('cpu', dtype=torch.int64)
+    idx = self.id2index[ids] if self.id2index is not None else ids
+    src = self.feature_tensor if self.feature_tensor is not None else self._cpu_full()
+    return src[idx]
+
+  def _cpu_full(self):
+    raise RuntimeError('host copy of the feature tensor was released; use __getitem__')
+
+  # ------------------------------------------------------------------ init
+  def _check_and_set_device(self):
+    if self.device is None:
+      self.device = get_available_device().index or 0
+    if self.device_group_list is None:
+      self.device_group_list = [DeviceGroup(0, [self.device])]
+    self._group = None
+    for g in self.device_group_list:
+      if self.device in g.device_list:
+        self._group = g
+    if self._group is None:
+      self._group = DeviceGroup(len(self.device_group_list), [self.device])
+
+  def lazy_init(self):
+    if self._unified is not None or not self.with_gpu:
+      return
+    with self._lock:
+      if self._unified is not None:
+        return
+      self._check_and_set_device()
+      if self._ipc_handle is not None:
+        self._init_from_ipc()
+      else:
+        self._split_and_init()
+      if self.id2index is not None:
+        self._id2index_dev = self.id2index.to(torch.device('cuda', self.device), dtype=torch.int64)
+
+  def _split_and_init(self):
+    n = self.feature_tensor.shape[0]
+    hot = int(n * self.split_ratio)
+    ut = UnifiedTensor(self.device, self.dtype)
+    self._cuda_parts_by_group = {}
+    if hot > 0:
+      hot_rows = self.feature_tensor[:hot]
+      for group in self.device_group_list:
+        shards, per = [], (hot + group.size - 1) // group.size
+        for i, dev in enumerate(group.device_list):
+          part = hot_rows[i * per: min((i + 1) * per, hot)]
+          if part.shape[0] > 0:
+            shards.append(part.to(torch.device('cuda', dev)))
+        self._cuda_parts_by_group[group.group_id] = shards
+      if self._group.group_id not in self._cuda_parts_by_group:
+        self._cuda_parts_by_group[self._group.group_id] = [hot_rows.to(torch.device('cuda', self.device))]
+      for shard in self._cuda_parts_by_group[self._group.group_id]:
+        ut.append_shared_tensor(shard)
+    if hot < n:
+      self._cpu_part = self.feature_tensor[hot:]
+      ut.append_cpu_tensor(self._cpu_part)
+    self._unified = ut
+
+  # ------------------------------------------------------------------ IPC
+  def share_ipc(self):
+    """Handle for spawned processes: GPU shards travel as CUDA IPC, host part as shm."""
+    with self._lock:
+      if self._ipc_handle is not None:
+        return self._ipc_handle
+      if self.with_gpu:
+        self.lazy_init()
+        cpu = self._cpu_part
+        if cpu is not None and not cpu.is_shared():
+          cpu = cpu.clone().share_memory_()
+        full = self.feature_tensor
+        if full is not None and not full.is_shared():
+          full = full.share_memory_()
+        if self.id2index is not None:
+          self.id2index = self.id2index.cpu().share_memory_()
+        return (self._cuda_parts_by_group, cpu, full, self.id2index, self.split_ratio,
+                self.device_group_list, self.with_gpu, self.dtype, self._shape)
+      if self.feature_tensor is not None:
+        self.feature_tensor.share_memory_()
+      if self.id2index is not None:
+        self.id2index = self.id2index.cpu().share_memory_()
+      return (None, None, self.feature_tensor, self.id2index, self.split_ratio,
+              self.device_group_list, self.with_gpu, self.dtype, self._shape)
+
+  @classmethod
+  def from_ipc_handle(cls, ipc_handle):
+    (_, _, full, id2index, split_ratio, groups, with_gpu, dtype, shape) = ipc_handle
+    f = cls(full, id2index, split_ratio, groups, None, with_gpu, dtype)
+    f._ipc_handle = ipc_handle
+    f._shape = shape
+    return f
+
+  def _init_from_ipc(self):
+    parts_by_group, cpu, _, _, _, _, _, _, _ = self._ipc_handle
+    ut = UnifiedTensor(self.device, self.dtype)
+    shards = (parts_by_group or {}).get(self._group.group_id)
+    if shards is None and parts_by_group:
+      shards = next(iter(parts_by_group.values()))
+    for s in shards or []:
+      ut.append_shared_tensor(s)
+    if cpu is not None:
+      self._cpu_part = cpu
+      ut.append_cpu_tensor(cpu)
+    self._unified = ut
+
+  # ------------------------------------------------------------------ info
+  @property
+  def shape(self):
+    return self._shape
+
+  def size(self, dim):
+    return self._shape[dim]
+
+  @property
+  def unified_tensor(self):
+    self.lazy_init()
+    return self._unified
+
+
+def rebuild_feature(ipc_handle):
+  return Feature.from_ipc_handle(ipc_handle)
+
+
+def reduce_feature(feature: Feature):
+  return (rebuild_feature, (feature.share_ipc(),))
+
+
+ForkingPickler.register(Feature, reduce_feature)

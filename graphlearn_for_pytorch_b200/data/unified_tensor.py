@@ -1,0 +1,143 @@
+"""UnifiedTensor: one logical [rows, ...] tensor backed by several physical parts
+(local HBM, peer-GPU HBM over NVLink, pinned host memory) with a single-kernel
+row gather across all of them.
+
+API parity: reference python/data/unified_tensor.py:23-133 and the native class in
+csrc/cuda/unified_tensor.cu:168-381.  The gather kernel is csrc/cuda/gather.cu.
+"""
+from typing import List, Optional
+
+import torch
+
+from ..ops import require_native
+
+
+def _enable_peer(cur: int, other: int):
+  if cur == other or other < 0:
+    return
+  nat = require_native()
+  nat.enable_peer_access(int(cur), int(other))
+
+
+class UnifiedTensor(object):
+  """Args:
+    current_device: CUDA device index that runs lookups.
+    dtype: element type of every part.
+  """
+
+  def __init__(self, current_device: int, dtype: torch.dtype = torch.float32):
+    self.current_device = int(current_device)
+    self.dtype = dtype
+    self._parts: List[torch.Tensor] = []
+    self._part_devices: List[int] = []
+    self._handle = None
+    self._cpu_part: Optional[torch.Tensor] = None
+
+  # ------------------------------------------------------------------ build
+  def _table(self):
+    if self._handle is None:
+      nat = require_native()
+      h = nat.RowTableHandle(self.current_device)
+      for p in self._parts:
+        h.append(p)
+      self._handle = h
+    return self._handle
+
+  def _append(self, t: torch.Tensor, dev: int):
+    assert t.dtype == self.dtype, f'dtype mismatch: {t.dtype} vs {self.dtype}'
+    self._parts.append(t)
+    self._part_devices.append(dev)
+    self._handle = None
+
+  def append_shared_tensor(self, shared_tensor: torch.Tensor):
+    """Append a CUDA tensor (possibly on a peer device / opened from CUDA IPC)."""
+    assert shared_tensor.is_cuda
+    _enable_peer(self.current_device, shared_tensor.device.index)
+    self._append(shared_tensor.contiguous(), shared_tensor.device.index)
+
+  def append_cpu_tensor(self, cpu_tensor: torch.Tensor):
+    """Append a host part; it is page-locked so kernels can read it in place."""
+    assert cpu_tensor.device.type == 'cpu'
+    t = cpu_tensor.contiguous()
+    self._cpu_part = t
+    if torch.cuda.is_available():
+      if not t.is_pinned():
+        if t.is_shared():
+          # keep the shared-memory mapping (other processes see the same rows)
+          torch.cuda.cudart().cudaHostRegister(t.data_ptr(), t.numel() * t.element_size(), 0)
+        else:
+          t = t.pin_memory()
+    self._append(t, -1)
+
+  def init_from(self, tensors: List[torch.Tensor], tensor_devices: List[int]):
+    """Place CPU tensors: device index >= 0 -> that GPU's HBM, -1 -> pinned host."""
+    assert len(tensors) == len(tensor_devices)
+    for t, d in zip(tensors, tensor_devices):
+      if t is None or t.numel() == 0:
+        continue
+      t = t.to(self.dtype)
+      if d >= 0:
+        self.append_shared_tensor(t.to(torch.device('cuda', d)))
+      else:
+        self.append_cpu_tensor(t.cpu())
+
+  # ------------------------------------------------------------------ lookup
+  def __getitem__(self, ids: torch.Tensor) -> torch.Tensor:
+    dev = torch.device('cuda', self.current_device)
+    ids = ids.to(dev, dtype=torch.int64).contiguous()
+    out = self._table().gather(ids, None, 0)
+    tail = self._parts[0].shape[1:] if self._parts else ()
+    return out.view(ids.numel(), *tail) if len(tail) != 1 else out
+
+  def gather_into(self, ids, out, n_dev=None, id2index=None):
+    self._table().gather_into(ids, id2index, n_dev, out)
+
+  # ------------------------------------------------------------------ info
+  @property
+  def shape(self):
+    rows = sum(p.shape[0] for p in self._parts)
+    tail = list(self._parts[0].shape[1:]) if self._parts else []
+    return [rows] + tail
+
+  @property
+  def device(self):
+    return self.current_device
+
+  @property
+  def numel(self):
+    n = 1
+    for s in self.shape:
+      n *= s
+    return n
+
+  def size(self, dim):
+    return self.shape[dim]
+
+  def stride(self, dim):
+    return self._parts[0].stride(dim) if self._parts else 0
+
+  @property
+  def parts(self):
+    return list(zip(self._parts, self._part_devices))
+
+  # ------------------------------------------------------------------ IPC
+  def share_ipc(self):
+    """(list of CUDA parts [torch shares them through CUDA IPC on pickling], cpu part)."""
+    cuda_parts = [p for p, d in zip(self._parts, self._part_devices) if d >= 0]
+    cpu = self._cpu_part
+    if cpu is not None and not cpu.is_shared():
+      cpu = cpu.clone().share_memory_()
+    return cuda_parts, cpu
+
+  def from_ipc_handle(self, cuda_ipc_list, cpu_part):
+    for t in cuda_ipc_list:
+      self.append_shared_tensor(t)
+    if cpu_part is not None:
+      self.append_cpu_tensor(cpu_part)
+
+  @classmethod
+  def new_from_ipc(cls, ipc_handles, current_device: int, dtype: torch.dtype):
+    cuda_ipc_list, cpu_part = ipc_handles
+    ut = cls(current_device, dtype)
+    ut.from_ipc_handle(cuda_ipc_list, cpu_part)
+    return ut

@@ -1,0 +1,7 @@
+from .data import Data, HeteroData
+from .transform import to_data, to_hetero_data
+from .node_loader import NodeLoader, SeedBatcher
+from .neighbor_loader import NeighborLoader
+from .link_loader import LinkLoader, get_edge_label_index
+from .link_neighbor_loader import LinkNeighborLoader
+from .subgraph_loader import SubGraphLoader
