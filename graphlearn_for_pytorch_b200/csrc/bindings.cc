@@ -183,7 +183,7 @@ struct DeviceTable {
     keys = torch::full({slots}, -1, o64);
     vals = torch::zeros({slots}, o32);
     aux = torch::zeros({slots}, o32);
-    nodes = torch::empty({cap_nodes}, o64);
+    nodes = torch::zeros({cap_nodes}, o64);
     cursor = torch::zeros({1}, o32);
     ht.keys = keys.data_ptr<int64_t>();
     ht.vals = vals.data_ptr<int32_t>();
@@ -264,7 +264,7 @@ struct SamplerArena {
   bool with_edge;
   std::vector<int64_t> cap_rows;  // frontier capacity per hop
   int64_t cap_nodes;
-  Tensor nodes, deg, counters, seed_local, scratch;
+  Tensor nodes, deg, counters, seed_local, scratch, step;
   std::vector<Tensor> ell, ell_eids;
   std::unique_ptr<DeviceTable> table;
 
@@ -293,6 +293,7 @@ struct SamplerArena {
     counters = torch::zeros({16}, o32);
     seed_local = torch::zeros({max_seeds}, o32);
     scratch = torch::zeros({max_seeds}, o32);
+    step = torch::zeros({1}, o32);
   }
 
   BatchCounters bc() {
@@ -301,7 +302,7 @@ struct SamplerArena {
   }
 
   void sample(GraphHandle& g, const Tensor& seeds, const c10::optional<Tensor>& n_dev, int64_t seed,
-              int64_t stream_base, bool weighted, bool replace) {
+              int64_t stream_base, bool weighted, bool replace, bool use_dev_step) {
     c10::cuda::CUDAGuard guard(device);
     TORCH_CHECK(seeds.is_cuda() && seeds.scalar_type() == torch::kInt64 && seeds.is_contiguous());
     TORCH_CHECK(seeds.numel() <= max_seeds, "more seeds than the arena was built for");
@@ -329,6 +330,7 @@ struct SamplerArena {
       a.replace = replace;
       a.seed = seed;
       a.stream = static_cast<uint32_t>(stream_base + h);
+      a.stream_dev = use_dev_step ? step.data_ptr<int32_t>() : nullptr;
       launch_sample_hop(a, s);
       launch_relabel_hop(a, s);
     }
@@ -655,6 +657,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def_readonly("deg", &SamplerArena::deg)
       .def_readonly("counters", &SamplerArena::counters)
       .def_readonly("seed_local", &SamplerArena::seed_local)
+      .def_readonly("step", &SamplerArena::step)
       .def_readonly("ell", &SamplerArena::ell)
       .def_readonly("ell_eids", &SamplerArena::ell_eids)
       .def_readonly("cap_rows", &SamplerArena::cap_rows)

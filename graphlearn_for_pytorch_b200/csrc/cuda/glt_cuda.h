@@ -81,6 +81,7 @@ struct HopArgs {
   int replace;          // 1: with replacement
   uint64_t seed;
   uint32_t stream;
+  const int32_t* stream_dev;  // optional device step counter mixed into the Philox stream
 };
 void launch_sample_hop(const HopArgs& a, cudaStream_t s);
 void launch_relabel_hop(const HopArgs& a, cudaStream_t s);

@@ -110,6 +110,8 @@ __global__ void __launch_bounds__(256) k_sample_hop(HopArgs a) {
   const int n_rows = min(a.c.cum[a.hop + 1] - f_begin, a.cap_rows);
   const int warps_per_block = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5;
+  // under CUDA-graph replay the host-side stream id is frozen: advance it from the device
+  const uint32_t rng_stream = a.stream + (a.stream_dev ? static_cast<uint32_t>(*a.stream_dev) * 8u : 0u);
   int edge_acc = 0;
   for (int base = (blockIdx.x * warps_per_block + warp) * RPW; base < n_rows;
        base += gridDim.x * warps_per_block * RPW) {
@@ -120,7 +122,7 @@ __global__ void __launch_bounds__(256) k_sample_hop(HopArgs a) {
     if (valid) row = load_row(a.g, v);
     uint32_t picks[MAXC];
     int take = 0;
-    pick_positions<G, MAXC>(a.g, row, v, a.k, gl, gmask, a.weighted, a.replace, a.seed, a.stream,
+    pick_positions<G, MAXC>(a.g, row, v, a.k, gl, gmask, a.weighted, a.replace, a.seed, rng_stream,
                             picks, take);
     if (a.replace && row.deg > a.k) take = a.k;
 #pragma unroll

@@ -1,0 +1,349 @@
+"""GraphSAGE: a generic PyG-style module and the fused, CUDA-graphed training engine.
+
+The reference ships no model code; its examples use PyG's SAGEConv
+(examples/train_sage_ogbn_products.py:30-59: 3 x SAGEConv, hidden 256, mean aggregation,
+fanout [15,10,5], batch 1024).  `GraphSAGE` below is the drop-in eager module for the
+`NeighborLoader` path.  `GraphSageEngine` is the B200-first path:
+
+  sample (static-shape arena, no host sync)
+    -> layer 1: ONE tcgen05 kernel = peer/local HBM row gather + neighbour mean +
+       [mean | self] x W1 + bias + ReLU (csrc/cuda/sage_tc.cu)
+    -> layers 2..L: ELL aggregation kernel + cuBLAS GEMM (small)
+    -> fused log-softmax/NLL fwd+bwd -> hand-written backward -> NCCL all-reduce -> fused Adam
+
+with every extent read from device counters, so the whole step is a fixed launch sequence
+replayed from a CUDA graph.
+"""
+import math
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ..ops import require_native
+
+
+# ----------------------------------------------------------------------------- eager modules
+class SAGEConv(nn.Module):
+  """out_i = W_l . mean_{j in N(i)} x_j + W_r . x_i + b   (PyG SAGEConv semantics)."""
+
+  def __init__(self, in_channels: int, out_channels: int, bias: bool = True):
+    super().__init__()
+    self.lin_l = nn.Linear(in_channels, out_channels, bias=bias)
+    self.lin_r = nn.Linear(in_channels, out_channels, bias=False)
+
+  def forward(self, x, edge_index, num_dst: Optional[int] = None):
+    x_src, x_dst = (x, x) if not isinstance(x, tuple) else x
+    n_dst = num_dst if num_dst is not None else x_dst.shape[0]
+    x_dst = x_dst[:n_dst]
+    src, dst = edge_index[0], edge_index[1]
+    agg = torch.zeros(n_dst, x_src.shape[1], dtype=x_src.dtype, device=x_src.device)
+    agg.index_add_(0, dst, x_src[src])
+    deg = torch.zeros(n_dst, dtype=x_src.dtype, device=x_src.device)
+    deg.index_add_(0, dst, torch.ones_like(dst, dtype=x_src.dtype))
+    agg = agg / deg.clamp(min=1).unsqueeze(1)
+    return self.lin_l(agg) + self.lin_r(x_dst)
+
+
+class GraphSAGE(nn.Module):
+  """Eager GraphSAGE for `NeighborLoader` batches; trims targets layer by layer using
+  `num_sampled_nodes/edges` when given (the reference relies on PyG trim_to_layer,
+  examples/train_sage_prod_with_trim.py:60-65)."""
+
+  def __init__(self, in_channels: int, hidden_channels: int, out_channels: int, num_layers: int = 3,
+               dropout: float = 0.0):
+    super().__init__()
+    dims = [in_channels] + [hidden_channels] * (num_layers - 1) + [out_channels]
+    self.convs = nn.ModuleList([SAGEConv(dims[i], dims[i + 1]) for i in range(num_layers)])
+    self.dropout = dropout
+
+  def forward(self, x, edge_index, num_sampled_nodes=None, num_sampled_edges=None):
+    L = len(self.convs)
+    for i, conv in enumerate(self.convs):
+      n_dst = None
+      ei = edge_index
+      if num_sampled_nodes is not None and num_sampled_edges is not None:
+        keep_hops = L - i                       # hops whose edges are still needed
+        n_e = int(sum(num_sampled_edges[:keep_hops]))
+        n_dst = int(sum(num_sampled_nodes[:keep_hops]))
+        ei = edge_index[:, :n_e]
+      x = conv(x, ei, n_dst)
+      if i < L - 1:
+        x = F.relu(x)
+        if self.dropout > 0:
+          x = F.dropout(x, self.dropout, self.training)
+    return x
+
+
+# ----------------------------------------------------------------------------- engine
+def _round_up(x, m):
+  return (x + m - 1) // m * m
+
+
+class GraphSageEngine(object):
+  """Static-shape, CUDA-graph-captured GraphSAGE training step.
+
+  Args:
+    graph: `data.Graph` in a device mode (single shard or multi-GPU shards).
+    feature_table: native RowTableHandle of bf16 rows indexed by global node id
+      (`UnifiedTensor._table()` / `PartitionedFeature.table`); width = in_dim.
+    labels: int64 [num_nodes] on the device.
+    in_dim: feature width (multiple of 64 for the fused kernel).
+    num_nodes: number of graph nodes (arena sizing).
+    fanouts / batch_size / hidden / num_classes: model + sampling config.
+    group: torch.distributed group for the gradient all-reduce (None = single process).
+    use_fused: use the tcgen05 gather+GEMM kernel where the shape allows.
+    use_cuda_graph: capture sample+forward+backward(+adam) into CUDA graphs.
+  """
+
+  def __init__(self, graph, feature_table, labels: torch.Tensor, in_dim: int, num_nodes: int,
+               fanouts: List[int] = (15, 10, 5), batch_size: int = 1024, hidden: int = 256,
+               num_classes: int = 47, lr: float = 3e-3, weight_decay: float = 0.0, seed: int = 0,
+               device: Optional[torch.device] = None, group=None, use_fused: bool = True,
+               use_cuda_graph: bool = True):
+    self.nat = require_native()
+    self.graph = graph
+    graph.lazy_init()
+    self.gh = graph.graph_handler
+    self.feat = feature_table
+    self.device = torch.device(device) if device is not None else torch.device('cuda', graph.device)
+    self.labels = labels.to(self.device)
+    self.fanouts = [int(k) for k in fanouts]
+    self.L = len(self.fanouts)
+    assert 1 <= self.L <= 4
+    self.bs = int(batch_size)
+    self.in_dim, self.hidden, self.C = int(in_dim), int(hidden), int(num_classes)
+    assert self.in_dim % 8 == 0 and self.hidden % 8 == 0
+    self.n_out_pad = _round_up(self.C, 64)
+    self.lr, self.wd = lr, weight_decay
+    self.seed = int(seed)
+    self.group = group
+    import torch.distributed as dist
+    self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    self.use_cuda_graph = use_cuda_graph
+    self.step_idx = 0
+    self.kernels_per_step = 0
+
+    dev = self.device
+    with torch.cuda.device(dev):
+      self.arena = self.nat.SamplerArena(dev.index, self.bs, self.fanouts, False, int(num_nodes))
+      self.cap_rows = list(self.arena.cap_rows)           # frontier capacity per hop
+      # layer l (1-based) targets = nodes of hops 0..L-l
+      self.cap_T = [0] + [int(sum(self.cap_rows[:self.L - l + 1])) for l in range(1, self.L + 1)]
+      self.cap_T = [min(c, self.arena.cap_nodes) for c in self.cap_T]
+      self.dims_in = [self.in_dim] + [self.hidden] * (self.L - 1)
+      self.dims_out = [self.hidden] * (self.L - 1) + [self.n_out_pad]
+      self._init_params()
+      bf, f32 = torch.bfloat16, torch.float32
+      self.A = [None] + [torch.zeros(self.cap_T[l], 2 * self.dims_in[l - 1], dtype=bf, device=dev)
+                         for l in range(1, self.L + 1)]
+      self.Z = [None] + [torch.zeros(self.cap_T[l], self.dims_out[l - 1], dtype=bf, device=dev)
+                         for l in range(1, self.L + 1)]
+      self.dPre = [None] + [torch.zeros(self.cap_T[l], self.dims_out[l - 1], dtype=bf, device=dev)
+                            for l in range(1, self.L + 1)]
+      self.dA = [None, None] + [torch.zeros(self.cap_T[l], 2 * self.dims_in[l - 1], dtype=bf, device=dev)
+                                for l in range(2, self.L + 1)]
+      self.dH = [None] + [torch.zeros(self.cap_T[l], self.dims_out[l - 1], dtype=f32, device=dev)
+                          for l in range(1, self.L)]
+      self.seeds_dev = torch.zeros(self.bs, dtype=torch.int64, device=dev)
+      self.y = torch.zeros(self.bs, dtype=torch.int64, device=dev)
+      self.loss = torch.zeros(1, dtype=f32, device=dev)
+      self.correct = torch.zeros(1, dtype=torch.int32, device=dev)
+      self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+      self.fused_ok = [False] + [bool(use_fused and self.nat.sage_fused_supported(self.dims_in[l - 1],
+                                                                                    self.dims_out[l - 1]))
+                                 for l in range(1, self.L + 1)]
+      self.w_packed = [None] + [torch.zeros(self.dims_out[l - 1] * 2 * self.dims_in[l - 1], dtype=bf, device=dev)
+                                if self.fused_ok[l] else None for l in range(1, self.L + 1)]
+      self._repack()
+    self._graph_fb = None
+    self._graph_opt = None
+
+  # ------------------------------------------------------------------ parameters
+  def _init_params(self):
+    dev = self.device
+    sizes = []
+    for l in range(self.L):
+      sizes.append(self.dims_out[l] * 2 * self.dims_in[l])   # W [N, 2d] = [W_neigh | W_self]
+      sizes.append(self.dims_out[l])                          # bias
+    total = sum(sizes)
+    self.p32 = torch.zeros(total, dtype=torch.float32, device=dev)
+    g = torch.Generator(device='cpu')
+    g.manual_seed(self.seed)
+    off = 0
+    self.W32, self.b32, self._w_off, self._b_off = [], [], [], []
+    for l in range(self.L):
+      n, k = self.dims_out[l], 2 * self.dims_in[l]
+      bound = 1.0 / math.sqrt(self.dims_in[l])
+      w = (torch.rand(n, k, generator=g) * 2 - 1) * bound
+      if l == self.L - 1 and self.n_out_pad > self.C:
+        w[self.C:] = 0
+      self.p32[off:off + n * k].copy_(w.flatten())
+      self._w_off.append((off, n, k)); off += n * k
+      self._b_off.append((off, n)); off += n
+    self.p16 = self.p32.to(torch.bfloat16)
+    self.g32 = torch.zeros_like(self.p32)
+    self.m = torch.zeros_like(self.p32)
+    self.v = torch.zeros_like(self.p32)
+
+  def W(self, l, buf=None):      # l is 1-based
+    off, n, k = self._w_off[l - 1]
+    return (buf if buf is not None else self.p16)[off:off + n * k].view(n, k)
+
+  def b(self, l, buf=None):
+    off, n = self._b_off[l - 1]
+    return (buf if buf is not None else self.p16)[off:off + n]
+
+  def _repack(self):
+    for l in range(1, self.L + 1):
+      if self.fused_ok[l]:
+        self.nat.pack_weight_into(self.W(l), self.w_packed[l])
+        self._k(1)
+
+  def state_dict(self):
+    return {'p32': self.p32.clone(), 'm': self.m.clone(), 'v': self.v.clone(),
+            'step': int(self.step_dev.item()), 'sample_step': int(self.arena.step.item()),
+            'step_idx': self.step_idx, 'seed': self.seed}
+
+  def load_state_dict(self, s):
+    self.p32.copy_(s['p32']); self.m.copy_(s['m']); self.v.copy_(s['v'])
+    self.p16.copy_(self.p32)
+    self.step_dev.fill_(s['step'])
+    self.arena.step.fill_(s.get('sample_step', 0))
+    self.step_idx, self.seed = s['step_idx'], s['seed']
+    self._repack()
+
+  # ------------------------------------------------------------------ step pieces
+  def _k(self, n):
+    self._tally += n
+
+  _tally = 0
+
+  def _ell(self, l):
+    """ELL blocks + strides used by layer l: hops 0..L-l."""
+    nh = self.L - l + 1
+    return list(self.arena.ell[:nh]), self.fanouts[:nh], nh
+
+  def _sample(self):
+    # the Philox stream advances from a device-side step counter (arena.step) so that a
+    # CUDA-graph replay draws fresh samples every step
+    self.arena.step.add_(1)
+    self.arena.sample(self.gh, self.seeds_dev, None, self.seed, 0, False, False, True)
+    self._k(2 + 2 * self.L)  # memset + init_seeds + (sample, relabel) per hop
+
+  def _forward(self):
+    nat, ar = self.nat, self.arena
+    for l in range(1, self.L + 1):
+      ell, ks, nh = self._ell(l)
+      d = self.dims_in[l - 1]
+      relu = l < self.L
+      feat = self.feat if l == 1 else None
+      nodes = ar.nodes if l == 1 else None
+      src_local = None if l == 1 else self.Z[l - 1]
+      if self.fused_ok[l]:
+        nat.sage_fused(feat, nodes, src_local, d, ar.counters, nh, ell, ks, ar.deg, self.w_packed[l],
+                       self.b(l), relu, self.Z[l], self.A[l])
+        self._k(1)
+      else:
+        nat.sage_aggregate(feat, nodes, src_local, d, ar.counters, nh, ell, ks, ar.deg, self.A[l])
+        torch.mm(self.A[l], self.W(l).t(), out=self.Z[l])
+        nat.bias_relu(self.Z[l], self.b(l), ar.counters, nh, relu)
+        self._k(2)
+    torch.index_select(self.labels, 0, ar.nodes[:self.bs].clamp(min=0), out=self.y)
+    nat.softmax_nll(self.Z[self.L], self.C, self.y, ar.counters, self.loss, self.dPre[self.L], self.correct)
+    self._k(1)
+
+  def _backward(self):
+    nat, ar = self.nat, self.arena
+    for l in range(self.L, 0, -1):
+      ell, ks, nh = self._ell(l)
+      off, n, k = self._w_off[l - 1]
+      boff, _ = self._b_off[l - 1]
+      gW = self.g32[off:off + n * k].view(n, k)
+      gW.copy_(torch.mm(self.dPre[l].t(), self.A[l]))
+      self.g32[boff:boff + n].copy_(self.dPre[l].sum(0, dtype=torch.float32))
+      if l > 1:
+        torch.mm(self.dPre[l], self.W(l), out=self.dA[l])
+        self.dH[l - 1].zero_()
+        nat.sage_scatter_bwd(self.dA[l], self.dims_in[l - 1], ar.counters, nh, ell, ks, ar.deg, self.dH[l - 1])
+        nat.relu_bwd_cast(self.dH[l - 1], self.Z[l - 1], ar.counters, nh + 1, self.dPre[l - 1])
+        self._k(2)
+
+  def _optimizer(self):
+    self.step_dev.add_(1)
+    self.nat.adam_step(self.p32, self.g32, self.m, self.v, self.p16, self.lr, 0.9, 0.999, 1e-8, self.wd,
+                       self.step_dev, 1.0 / self.world)
+    self._k(1)
+    self._repack()
+
+  def _allreduce(self):
+    if self.world > 1:
+      import torch.distributed as dist
+      dist.all_reduce(self.g32, group=self.group)
+
+  def _step_eager(self):
+    self._sample()
+    self._forward()
+    self._backward()
+    self._allreduce()
+    self._optimizer()
+
+  # ------------------------------------------------------------------ public API
+  def warmup_and_capture(self, n_eager: int = 2):
+    """Run a few eager steps (lazy inits, cuBLAS workspaces), then capture the CUDA graphs."""
+    with torch.cuda.device(self.device):
+      saved = self.state_dict()
+      side = torch.cuda.Stream()
+      side.wait_stream(torch.cuda.current_stream())
+      with torch.cuda.stream(side):
+        for _ in range(n_eager):
+          self._tally = 0
+          self._step_eager()
+          self.kernels_per_step = self._tally
+      torch.cuda.current_stream().wait_stream(side)
+      torch.cuda.synchronize()
+      self.load_state_dict(saved)
+      if not self.use_cuda_graph:
+        return
+      self._graph_fb = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(self._graph_fb):
+        self._forward_backward_for_capture()
+      self._graph_opt = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(self._graph_opt):
+        self._optimizer()
+      torch.cuda.synchronize()
+      self.load_state_dict(saved)
+
+  def _forward_backward_for_capture(self):
+    self._sample()
+    self._forward()
+    self._backward()
+
+  def train_step(self, seeds: torch.Tensor) -> torch.Tensor:
+    """One training step on a batch of seed node ids.  `seeds` may be a (pinned) host
+    tensor -- it is copied H2D asynchronously -- or a device tensor.  Returns the device
+    scalar holding the mean NLL loss of the batch (read it with .item() / a D2H copy)."""
+    n = seeds.numel()
+    assert n <= self.bs
+    if n < self.bs:
+      self.seeds_dev.fill_(-1)
+    self.seeds_dev[:n].copy_(seeds, non_blocking=True)
+    if self._graph_fb is not None:
+      self._graph_fb.replay()
+      self._allreduce()
+      self._graph_opt.replay()
+    else:
+      self._step_eager()
+    self.step_idx += 1
+    return self.loss
+
+  @torch.no_grad()
+  def evaluate_batch(self, seeds: torch.Tensor):
+    """(loss, #correct, #seeds) for a batch without updating parameters."""
+    n = seeds.numel()
+    self.seeds_dev.fill_(-1)
+    self.seeds_dev[:n].copy_(seeds)
+    self._sample()
+    self._forward()
+    return float(self.loss.item()), int(self.correct.item()), int(self.arena.counters[1].item())

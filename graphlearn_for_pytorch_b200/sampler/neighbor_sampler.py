@@ -208,7 +208,7 @@ class NeighborSampler(BaseSampler):
         h = self.graph.graph_handler
         stream = self._next_stream(len(self.num_neighbors))
         weighted = bool(self.with_weight and h.has_weights)
-        arena.sample(h, seeds.contiguous(), None, self.seed, stream, weighted, self.replace)
+        arena.sample(h, seeds.contiguous(), None, self.seed, stream, weighted, self.replace, False)
         node, nbr_local, tgt_local, eids, nn, ne = arena.to_coo()
       # messages flow neighbour -> seed: row = neighbour, col = target
       while len(nn) > 1 and nn[-1] == 0 and ne[-1] == 0:

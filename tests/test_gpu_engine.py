@@ -1,0 +1,163 @@
+"""GraphSAGE engine kernels (tcgen05 fused layer, aggregation, backward, loss, Adam) vs. fp32 PyTorch."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import graphlearn_for_pytorch_b200 as glt
+from graphlearn_for_pytorch_b200.models import GraphSageEngine
+from helpers import rmat_csr
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device('cuda', 0)
+
+
+def _setup(N=6000, E=120000, Fdim=128, C=47, fan=(5, 4, 3), bs=256, fused=True, graph=False, hidden=256):
+  ei, topo = rmat_csr(N, E, seed=3)
+  g = glt.data.Graph(topo, 'CUDA', 0)
+  torch.manual_seed(0)
+  feats = torch.randn(N, Fdim, device=DEV).to(torch.bfloat16)
+  labels = torch.randint(0, C, (N,), device=DEV)
+  ut = glt.data.UnifiedTensor(0, torch.bfloat16)
+  ut.append_shared_tensor(feats)
+  eng = GraphSageEngine(g, ut._table(), labels, in_dim=Fdim, num_nodes=N, fanouts=list(fan), batch_size=bs,
+                        hidden=hidden, num_classes=C, device=DEV, use_fused=fused, use_cuda_graph=graph, seed=5)
+  eng._keep = (ut, feats, topo)
+  return eng, feats, labels
+
+
+def _dense_reference(eng, feats, labels, n_valid_seeds):
+  """fp32 PyTorch recomputation of the engine's forward/backward from the sampled structure."""
+  ar = eng.arena
+  c = ar.counters.cpu().tolist()
+  L = eng.L
+  cum = c[:L + 2]
+  nodes = ar.nodes[:cum[L + 1]]
+  deg = ar.deg
+  params = []
+  for l in range(1, L + 1):
+    W = eng.W(l).float().clone().requires_grad_(True)
+    b = eng.b(l).float().clone().requires_grad_(True)
+    params.append((W, b))
+  H = feats[nodes].float()
+  acts = []
+  for l in range(1, L + 1):
+    nh = L - l + 1
+    T = cum[nh]
+    d = H.shape[1]
+    mean = torch.zeros(T, d, device=DEV)
+    for h in range(nh):
+      k = eng.fanouts[h]
+      rows = cum[h + 1] - cum[h]
+      if rows == 0:
+        continue
+      ell = ar.ell[h][:rows * k].view(rows, k).long()
+      valid = ell >= 0
+      gathered = H[ell.clamp(min=0)] * valid.unsqueeze(-1)
+      dg = deg[cum[h]:cum[h + 1]].float().clamp(min=1).unsqueeze(1)
+      mean[cum[h]:cum[h + 1]] = gathered.sum(1) / dg
+      assert torch.equal(valid.sum(1).int(), deg[cum[h]:cum[h + 1]])
+    A = torch.cat([mean, H[:T]], dim=1)
+    A = A.to(torch.bfloat16).float()          # the kernels round the A operand to bf16
+    W, b = params[l - 1]
+    Z = A @ W.t() + b
+    if l < L:
+      Z = F.relu(Z)
+      Z = Z + (Z.to(torch.bfloat16).float() - Z).detach()   # bf16 storage, straight-through grad
+    acts.append((A, Z))
+    H = Z
+  logits = H[:cum[1], :eng.C]
+  y = labels[nodes[:cum[1]]]
+  loss = F.cross_entropy(logits, y)
+  loss.backward()
+  return loss.item(), acts, params, cum
+
+
+@pytest.mark.parametrize('fused', [False, True])
+def test_forward_backward_matches_pytorch(native, fused):
+  eng, feats, labels = _setup(fused=fused)
+  assert eng.fused_ok[1] == fused
+  seeds = torch.randperm(6000, device=DEV)[:256]
+  eng.seeds_dev.copy_(seeds)
+  eng._sample(); eng._forward(); eng._backward()
+  torch.cuda.synchronize()
+  ref_loss, acts, params, cum = _dense_reference(eng, feats, labels, 256)
+  assert abs(float(eng.loss.item()) - ref_loss) < 2e-2 * max(1.0, abs(ref_loss))
+  for l in range(1, eng.L + 1):
+    T = cum[eng.L - l + 1]
+    A_ref, Z_ref = acts[l - 1]
+    A = eng.A[l][:T].float()
+    assert torch.allclose(A, A_ref, atol=2e-2, rtol=2e-2), f'A{l}'
+    Z = eng.Z[l][:T].float()
+    assert torch.allclose(Z, Z_ref.detach(), atol=6e-2, rtol=3e-2), f'Z{l} max err {(Z - Z_ref).abs().max()}'
+    off, n, k = eng._w_off[l - 1]
+    gW = eng.g32[off:off + n * k].view(n, k)
+    gW_ref = params[l - 1][0].grad
+    denom = gW_ref.abs().max().clamp(min=1e-6)
+    assert (gW - gW_ref).abs().max() / denom < 5e-2, f'dW{l}'
+    boff, _ = eng._b_off[l - 1]
+    gb_ref = params[l - 1][1].grad
+    assert (eng.g32[boff:boff + n] - gb_ref).abs().max() / gb_ref.abs().max().clamp(min=1e-6) < 5e-2
+
+
+def test_pack_weight_roundtrip(native):
+  w = torch.randn(256, 256, device=DEV).to(torch.bfloat16)
+  p = native.pack_weight(w)
+  # undo: [K/64][N][64] with 16-B chunks XOR-swizzled by (row & 7)
+  p = p.view(4, 256, 8, 8)
+  rows = torch.arange(256, device=DEV)
+  out = torch.empty_like(p)
+  for cv in range(8):
+    src = (cv ^ (rows & 7))
+    out[:, rows, cv] = p[:, rows, src]
+  rec = out.permute(1, 0, 2, 3).reshape(256, 256)
+  assert torch.equal(rec, w)
+
+
+def test_softmax_nll_and_adam(native):
+  torch.manual_seed(1)
+  logits = torch.randn(128, 64, device=DEV).to(torch.bfloat16)
+  y = torch.randint(0, 47, (128,), device=DEV)
+  counters = torch.zeros(16, dtype=torch.int32, device=DEV); counters[1] = 100
+  loss = torch.zeros(1, device=DEV); dl = torch.zeros_like(logits); corr = torch.zeros(1, dtype=torch.int32, device=DEV)
+  native.softmax_nll(logits, 47, y, counters, loss, dl, corr)
+  x = logits[:100, :47].float().requires_grad_(True)
+  ref = F.cross_entropy(x, y[:100]); ref.backward()
+  assert abs(loss.item() - ref.item()) < 1e-3
+  assert torch.allclose(dl[:100, :47].float(), x.grad, atol=2e-4)
+  assert dl[100:].abs().sum() == 0 and dl[:, 47:].abs().sum() == 0
+  assert corr.item() == int((x.argmax(1) == y[:100]).sum())
+  p = torch.randn(1000, device=DEV); g = torch.randn(1000, device=DEV)
+  p_ref = p.clone().requires_grad_(True); opt = torch.optim.Adam([p_ref], lr=1e-2)
+  m = torch.zeros_like(p); v = torch.zeros_like(p); p16 = p.to(torch.bfloat16); step = torch.zeros(1, dtype=torch.int32, device=DEV)
+  for _ in range(3):
+    step += 1
+    native.adam_step(p, g, m, v, p16, 1e-2, 0.9, 0.999, 1e-8, 0.0, step, 1.0)
+    p_ref.grad = g.clone(); opt.step()
+  assert torch.allclose(p, p_ref.detach(), atol=1e-5)
+  assert torch.allclose(p16.float(), p, atol=2e-2)
+
+
+@pytest.mark.parametrize('graph', [False, True])
+def test_engine_learns(native, graph):
+  # labels are a linear function of the features: the loss must drop quickly
+  eng, feats, _ = _setup(N=8000, E=100000, bs=512, fan=(4, 3), graph=graph, C=8)
+  w = torch.randn(128, 8, device=DEV)
+  eng.labels = (feats.float() @ w).argmax(1)
+  eng.warmup_and_capture(n_eager=1)
+  losses = []
+  for i in range(60):
+    seeds = torch.randperm(8000, device=DEV)[:512]
+    eng.train_step(seeds)
+    losses.append(float(eng.loss.item()))
+  assert losses[-1] < 0.6 * losses[0], (losses[0], losses[-1])
+  loss, correct, n = eng.evaluate_batch(torch.randperm(8000, device=DEV)[:512])
+  assert n == 512 and correct / n > 0.5
+
+
+def test_graph_replay_resamples(native):
+  eng, _, _ = _setup(N=8000, E=160000, bs=64, fan=(3, 2), graph=True)
+  eng.warmup_and_capture(n_eager=1)
+  seeds = torch.arange(64, device=DEV)
+  eng.train_step(seeds); a = eng.arena.nodes[:eng.arena.counters[3].item()].clone()
+  eng.train_step(seeds); b = eng.arena.nodes[:eng.arena.counters[3].item()].clone()
+  assert a.numel() != b.numel() or not torch.equal(a.sort().values, b.sort().values)

@@ -1,0 +1,202 @@
+"""sm_100a kernels vs. the CPU reference ops / plain PyTorch fp32 (needs a B200)."""
+import pytest
+import torch
+
+import graphlearn_for_pytorch_b200 as glt
+from graphlearn_for_pytorch_b200.sampler import NeighborSampler, NodeSamplerInput
+from helpers import adjacency_sets, canonical_edges, ring_dataset, rmat_csr
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device('cuda', 0)
+
+
+def _graphs(num_nodes=3000, num_edges=60000, weights=False, seed=0):
+  ei, topo = rmat_csr(num_nodes, num_edges, seed)
+  if weights:
+    w = (torch.arange(ei.shape[1]) % 7 + 1).float()
+    topo = glt.data.Topology(ei, edge_weights=w, layout='CSR', num_nodes=num_nodes)
+  return topo, glt.data.Graph(topo, 'CPU'), glt.data.Graph(topo, 'CUDA', 0)
+
+
+@pytest.mark.parametrize('k', [3, 10, 25, 40])
+def test_one_hop_matches_cpu(native, k):
+  topo, gc, gg = _graphs()
+  seeds = torch.randperm(3000)[:700]
+  for with_edge in (False, True):
+    sc = NeighborSampler(gc, [k], with_edge=with_edge, seed=11)
+    sg = NeighborSampler(gg, [k], with_edge=with_edge, seed=11, device=DEV)
+    a = sc.sample_one_hop(seeds, k, stream=5)
+    b = sg.sample_one_hop(seeds.to(DEV), k, stream=5)
+    assert torch.equal(a.nbr_num, b.nbr_num.cpu())
+    assert torch.equal(a.nbr, b.nbr.cpu())          # same Philox streams -> identical picks
+    if with_edge:
+      assert torch.equal(a.edge, b.edge.cpu())
+
+
+def test_one_hop_zero_copy_and_full(native):
+  topo, gc, _ = _graphs(500, 9000)
+  gz = glt.data.Graph(topo, 'ZERO_COPY', 0)
+  seeds = torch.arange(0, 500, 3)
+  a = NeighborSampler(gc, [4], seed=1).sample_one_hop(seeds, 4, stream=0)
+  b = NeighborSampler(gz, [4], seed=1, device=DEV).sample_one_hop(seeds.to(DEV), 4, stream=0)
+  assert torch.equal(a.nbr, b.nbr.cpu())
+  a = NeighborSampler(gc, [-1], with_edge=True).sample_one_hop(seeds, -1)
+  b = NeighborSampler(gz, [-1], with_edge=True, device=DEV).sample_one_hop(seeds.to(DEV), -1)
+  assert torch.equal(a.nbr, b.nbr.cpu()) and torch.equal(a.edge, b.edge.cpu())
+  assert torch.equal(a.nbr_num, b.nbr_num.cpu())
+
+
+def test_weighted_one_hop_statistics(native):
+  indptr = torch.tensor([0, 4])
+  topo = glt.data.Topology((indptr, torch.tensor([10, 11, 12, 13])), edge_weights=torch.tensor([1., 1., 2., 4.]),
+                           input_layout='CSR', layout='CSR')
+  g = glt.data.Graph(topo, 'CUDA', 0)
+  s = NeighborSampler(g, [1], with_weight=True, seed=3, device=DEV)
+  hits = torch.zeros(4)
+  seeds = torch.zeros(1, dtype=torch.int64, device=DEV)
+  for t in range(3000):
+    o = s.sample_one_hop(seeds, 1, stream=t)
+    hits[o.nbr.item() - 10] += 1
+  p = hits / 3000
+  assert (p - torch.tensor([1., 1., 2., 4.]) / 8).abs().max() < 0.04
+
+
+@pytest.mark.parametrize('fanouts', [[3, 2], [15, 10, 5], [40, 2]])
+def test_arena_multihop_matches_cpu(native, fanouts):
+  topo, gc, gg = _graphs(5000, 100000)
+  seeds = torch.randperm(5000)[:333]
+  sc = NeighborSampler(gc, fanouts, with_edge=True, seed=21)
+  sg = NeighborSampler(gg, fanouts, with_edge=True, seed=21, device=DEV)
+  a = sc.sample_from_nodes(seeds)
+  b = sg.sample_from_nodes(seeds.to(DEV))
+  assert a.num_sampled_nodes == b.num_sampled_nodes
+  assert a.num_sampled_edges == b.num_sampled_edges
+  assert torch.equal(a.node[:333], b.node[:333].cpu())            # seeds keep their order
+  # hop-contiguous node sets match; ids inside a hop may be permuted
+  off = 0
+  for n in a.num_sampled_nodes:
+    assert set(a.node[off:off + n].tolist()) == set(b.node[off:off + n].cpu().tolist())
+    off += n
+  assert canonical_edges(a) == canonical_edges(b)
+  eb = dict(zip(zip(b.node[b.row].cpu().tolist(), b.node[b.col].cpu().tolist()), b.edge.cpu().tolist()))
+  ea = dict(zip(zip(a.node[a.row].tolist(), a.node[a.col].tolist()), a.edge.tolist()))
+  assert ea == eb
+  # per-hop edge blocks: targets of hop h are nodes of hop h-1
+  cum = [0]
+  for n in b.num_sampled_nodes:
+    cum.append(cum[-1] + n)
+  e0 = 0
+  for h, ne in enumerate(b.num_sampled_edges):
+    cols = b.col[e0:e0 + ne]
+    assert int(cols.min()) >= cum[h] and int(cols.max()) < cum[h + 1]
+    e0 += ne
+
+
+def test_generic_path_on_gpu_with_full_fanout(native):
+  ds = ring_dataset(40, graph_mode='CUDA', device=0)
+  s = NeighborSampler(ds.graph, [-1, 2], device=DEV)
+  out = s.sample_from_nodes(torch.tensor([0, 10], device=DEV))
+  assert set(out.node.cpu().tolist()) == {0, 1, 2, 3, 4, 10, 11, 12, 13, 14}
+  src, dst = out.node[out.row], out.node[out.col]
+  assert torch.all(((src - dst) % 40 == 1) | ((src - dst) % 40 == 2))
+
+
+@pytest.mark.parametrize('dtype,width', [(torch.float32, 100), (torch.bfloat16, 128), (torch.float16, 7),
+                                         (torch.int64, 1), (torch.uint8, 33), (torch.float64, 16),
+                                         (torch.float32, 1024)])
+def test_unified_tensor_gather(native, dtype, width):
+  n = 5000
+  if dtype.is_floating_point:
+    full = torch.randn(n, width).to(dtype)
+  else:
+    full = torch.randint(0, 100, (n, width)).to(dtype)
+  ut = glt.data.UnifiedTensor(0, dtype)
+  ut.init_from([full[:2000], full[2000:3500], full[3500:]], [0, 0, -1])   # 2 HBM parts + pinned host
+  ids = torch.randint(0, n, (3000,))
+  got = ut[ids.to(DEV)]
+  assert torch.equal(got.cpu(), full[ids])
+  assert ut.shape == [n, width]
+
+
+def test_feature_split_and_reorder(native):
+  ei, topo = rmat_csr(2000, 30000)
+  feat = glt.utils.id_features(2000, 16)
+  for ratio in (0.0, 0.3, 1.0):
+    sorted_feat, id2idx = glt.data.sort_by_in_degree(feat, ratio, topo)
+    f = glt.data.Feature(sorted_feat, id2idx, split_ratio=ratio, device=0)
+    ids = torch.randint(0, 2000, (777,), device=DEV)
+    out = f[ids]
+    assert torch.equal(out[:, 0].long(), ids)
+    assert torch.equal(f.cpu_get(ids.cpu())[:, 0].long(), ids.cpu())
+
+
+def test_negative_sampler_gpu(native):
+  ei, topo = rmat_csr(300, 6000)
+  g = glt.data.Graph(topo, 'CUDA', 0)
+  edges = set(zip(ei[0].tolist(), ei[1].tolist()))
+  ns = glt.sampler.RandomNegativeSampler(g, 'CUDA')
+  out = ns.sample(2000, trials_num=5)
+  assert 1500 < out.shape[1] <= 2000
+  assert all((r, c) not in edges for r, c in zip(out[0].tolist(), out[1].tolist()))
+  out = ns.sample(2000, trials_num=1, padding=True)
+  assert out.shape[1] == 2000
+  # rows and columns are drawn independently (the reference correlates them)
+  assert abs(torch.corrcoef(out.float().cpu())[0, 1]) < 0.2
+
+
+def test_subgraph_gpu_matches_cpu(native):
+  topo, gc, gg = _graphs(800, 16000)
+  seeds = torch.randperm(800)[:50]
+  a = NeighborSampler(gc, [3], with_edge=True, seed=4).subgraph(NodeSamplerInput(seeds))
+  b = NeighborSampler(gg, [3], with_edge=True, seed=4, device=DEV).subgraph(NodeSamplerInput(seeds.to(DEV)))
+  assert set(a.node.tolist()) == set(b.node.cpu().tolist())
+  assert canonical_edges(a) == canonical_edges(b)
+  assert torch.equal(b.node[b.metadata].cpu(), seeds)
+  assert sorted(a.edge.tolist()) == sorted(b.edge.cpu().tolist())
+
+
+def test_random_walk_gpu_matches_cpu(native):
+  topo, gc, gg = _graphs(600, 12000)
+  starts = torch.arange(0, 600, 3)
+  for p, q in ((1.0, 1.0), (0.25, 4.0)):
+    a = NeighborSampler(gc, [1], seed=9)
+    b = NeighborSampler(gg, [1], seed=9, device=DEV)
+    wa = a.random_walk(starts, 8, p, q)
+    wb = b.random_walk(starts.to(DEV), 8, p, q)
+    assert torch.equal(wa, wb.cpu())
+
+
+def test_sample_prob_gpu_matches_cpu(native):
+  topo, gc, gg = _graphs(700, 9000)
+  seeds = torch.arange(0, 700, 9)
+  pa = NeighborSampler(gc, [5, 3]).sample_prob(NodeSamplerInput(seeds), 700)
+  pb = NeighborSampler(gg, [5, 3], device=DEV).sample_prob(NodeSamplerInput(seeds.to(DEV)), 700)
+  assert torch.allclose(pa, pb.cpu(), atol=1e-5)
+
+
+def test_device_table(native):
+  t = native.DeviceTable(0, 1000)
+  keys = torch.tensor([7, 3, 7, 9, 3, 100], device=DEV)
+  ids = t.init_ordered(keys)
+  assert ids.tolist() == [0, 1, 0, 2, 1, 3] and t.size() == 4
+  assert t.nodes[:4].tolist() == [7, 3, 9, 100]
+  more = t.insert(torch.tensor([9, 55, 56, 55, -1], device=DEV))
+  assert more[0].item() == 2 and more[4].item() == -1 and more[1].item() == more[3].item()
+  assert sorted(more[1:3].tolist()) == [4, 5] and t.size() == 6
+  assert t.lookup(torch.tensor([100, 12345], device=DEV)).tolist() == [3, -1]
+  t.clear()
+  assert t.size() == 0 and t.lookup(torch.tensor([7], device=DEV)).tolist() == [-1]
+
+
+def test_neighbor_loader_cuda_ring(native):
+  from test_loaders_cpu import check_homo_batch
+  ds = ring_dataset(40, graph_mode='CUDA', with_gpu=True, device=0, split_ratio=0.5)
+  loader = glt.loader.NeighborLoader(ds, [2, 2], torch.arange(40), batch_size=8, shuffle=True, with_edge=True,
+                                     device=DEV, seed=1)
+  seen = []
+  for b in loader:
+    assert b.x.is_cuda and b.edge_index.is_cuda
+    b = b.to('cpu')
+    check_homo_batch(b)
+    seen += b.batch.tolist()
+  assert sorted(seen) == list(range(40))
