@@ -49,60 +49,68 @@ def parse_args():
   p.add_argument('--no-fused', action='store_true')
   p.add_argument('--no-graph', action='store_true')
   p.add_argument('--seed', type=int, default=0)
+  p.add_argument('--profile-steps', type=int, default=0,
+                 help='run this many eager steps between cudaProfilerStart/Stop (for ncu) and exit')
   return p.parse_args()
 
 
 class ClockSampler(threading.Thread):
-  """Polls nvidia-smi during the timed region (clocks + throttle reasons)."""
-
-  Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
-       'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
-       'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+  """Polls SM clocks + throttle reasons during the timed region (NVML in-process at ~1 kHz;
+  `nvidia-smi -lms` cannot resolve a region that lasts tens of milliseconds)."""
 
   def __init__(self, gpu_index=0):
     super().__init__(daemon=True)
     self.gpu_index = gpu_index
-    self.samples = []
+    self.samples = []          # (sm_mhz, reasons bitmask)
+    self.sm_max = None
     self._stop_evt = threading.Event()
-    self.proc = None
 
   def run(self):
     try:
-      self.proc = subprocess.Popen(
-        ['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
-         '-i', str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-      for line in self.proc.stdout:
-        if self._stop_evt.is_set():
-          break
-        parts = [x.strip() for x in line.split(',')]
-        if len(parts) >= 9:
-          self.samples.append(parts)
+      import pynvml as nv
+      nv.nvmlInit()
+      h = nv.nvmlDeviceGetHandleByIndex(self.gpu_index)
+      self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+      get_reasons = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or \
+          nv.nvmlDeviceGetCurrentClocksThrottleReasons
+      while not self._stop_evt.is_set():
+        self.samples.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(get_reasons(h))))
+        time.sleep(0.001)
     except Exception:
-      pass
+      self._smi_fallback()
+
+  def _smi_fallback(self):
+    q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    while not self._stop_evt.is_set():
+      try:
+        out = subprocess.run(['nvidia-smi', f'--query-gpu={q}', '--format=csv,noheader,nounits', '-i',
+                              str(self.gpu_index)], capture_output=True, text=True, timeout=5).stdout
+        p = [x.strip() for x in out.strip().split(',')]
+        mask = 0
+        for bit, val in zip((0x8, 0x40, 0x20, 0x4), p[2:6]):
+          if val.lower().startswith('active'):
+            mask |= bit
+        self.samples.append((float(p[0]), mask))
+        self.sm_max = float(p[1])
+      except Exception:
+        return
 
   def stop(self):
     self._stop_evt.set()
-    if self.proc is not None:
-      try:
-        self.proc.terminate()
-      except Exception:
-        pass
 
   def summary(self):
-    sm, mx, reasons = [], [], set()
-    for p in self.samples:
-      try:
-        sm.append(float(p[1])); mx.append(float(p[2]))
-      except ValueError:
-        continue
-      for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'),
-                           p[5:9]):
-        if val.lower().startswith('active'):
-          reasons.add(name)
-    if not sm:
-      return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
-    return {'sm_mhz': statistics.median(sm), 'sm_max_mhz': max(mx), 'reasons': sorted(reasons),
-            'samples': len(sm)}
+    # NVML reason bits: 0x4 sw_power_cap, 0x8 hw_slowdown, 0x20 sw_thermal, 0x40 hw_thermal
+    names = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown', 0x4: 'sw_power_cap'}
+    if not self.samples:
+      return {'sm_mhz': None, 'sm_max_mhz': self.sm_max, 'reasons': [], 'samples': 0}
+    reasons = set()
+    for _, m in self.samples:
+      for bit, n in names.items():
+        if m & bit:
+          reasons.add(n)
+    return {'sm_mhz': statistics.median(c for c, _ in self.samples), 'sm_max_mhz': self.sm_max,
+            'reasons': sorted(reasons), 'samples': len(self.samples)}
 
 
 def setup_dist(args):
@@ -196,6 +204,19 @@ def run_ours(args):
   eng, pool = build_ours(args, rank, world, device)
   bs, K, W = args.batch, args.steps, args.warmup
   eng.warmup_and_capture(n_eager=2)
+  if args.profile_steps > 0:
+    # ncu --profile-from-start off: only these eager steps are captured
+    eng._graph_fb = eng._graph_opt = None
+    sd = pool[:bs].to(device)
+    for _ in range(3):
+      eng.train_step(sd)
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStart()
+    for _ in range(args.profile_steps):
+      eng.train_step(sd)
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStop()
+    return
 
   n_batches = K + W
   need = n_batches * bs

@@ -509,17 +509,39 @@ static void bias_relu(Tensor Z, const Tensor& bias, const Tensor& counters, int6
   check_cuda_err("bias_relu");
 }
 
-static void softmax_nll(const Tensor& logits, int64_t C, const Tensor& y, const Tensor& counters,
-                        Tensor loss, Tensor dlogits, const c10::optional<Tensor>& correct) {
+static void softmax_nll(const Tensor& logits, int64_t C, const c10::optional<Tensor>& y,
+                        const c10::optional<Tensor>& labels_all, const c10::optional<Tensor>& nodes,
+                        const Tensor& counters, Tensor loss, Tensor dlogits,
+                        const c10::optional<Tensor>& correct) {
   c10::cuda::CUDAGuard guard(logits.device());
   TORCH_CHECK(logits.scalar_type() == torch::kBFloat16 && logits.is_contiguous());
   TORCH_CHECK(dlogits.sizes() == logits.sizes() && dlogits.is_contiguous());
-  launch_softmax_nll(logits.data_ptr(), logits.size(1), C, y.data_ptr<int64_t>(),
+  const bool direct = y.has_value() && y->defined();
+  TORCH_CHECK(direct || (labels_all.has_value() && nodes.has_value()), "need y or (labels_all, nodes)");
+  launch_softmax_nll(logits.data_ptr(), logits.size(1), C, direct ? y->data_ptr<int64_t>() : nullptr,
+                     direct ? nullptr : labels_all->data_ptr<int64_t>(),
+                     direct ? nullptr : nodes->data_ptr<int64_t>(),
                      counters.data_ptr<int32_t>(), logits.size(0), loss.data_ptr<float>(),
                      dlogits.data_ptr(),
                      (correct.has_value() && correct->defined()) ? correct->data_ptr<int32_t>() : nullptr,
                      cur_stream());
   check_cuda_err("softmax_nll");
+}
+
+static void colsum_bf16(const Tensor& X, const Tensor& counters, int64_t n_hops, Tensor out) {
+  c10::cuda::CUDAGuard guard(X.device());
+  TORCH_CHECK(X.scalar_type() == torch::kBFloat16 && X.is_contiguous() && X.size(1) % 8 == 0);
+  TORCH_CHECK(out.scalar_type() == torch::kFloat32 && out.numel() == X.size(1) && X.size(1) <= 2048);
+  launch_colsum_bf16(X.data_ptr(), counters.data_ptr<int32_t>(), n_hops, X.size(0), X.size(1),
+                     out.data_ptr<float>(), cur_stream());
+  check_cuda_err("colsum_bf16");
+}
+
+static void zero_rows(Tensor p, const Tensor& counters, int64_t n_hops) {
+  c10::cuda::CUDAGuard guard(p.device());
+  TORCH_CHECK(p.scalar_type() == torch::kFloat32 && p.is_contiguous() && p.size(1) % 4 == 0);
+  launch_zero_rows(p.data_ptr<float>(), counters.data_ptr<int32_t>(), n_hops, p.size(0), p.size(1), cur_stream());
+  check_cuda_err("zero_rows");
 }
 
 static void adam_step(Tensor p, const Tensor& g, Tensor m, Tensor v, const c10::optional<Tensor>& p_bf16,
@@ -680,6 +702,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("bias_relu", &bias_relu);
   m.def("softmax_nll", &softmax_nll);
   m.def("adam_step", &adam_step);
+  m.def("colsum_bf16", &colsum_bf16);
+  m.def("zero_rows", &zero_rows);
   m.def("sage_fused", &sage_fused);
   m.def("sage_fused_supported", &sage_fused_supported);
   m.def("enable_peer_access", &enable_peer_access);

@@ -168,8 +168,14 @@ void launch_relu_bwd_cast(const float* dH, const void* Z, const int32_t* cum, in
 void launch_bias_relu(void* Z, const void* bias, const int32_t* cum, int n_hops, int cap, int d,
                       int relu, cudaStream_t s);
 // loss = mean NLL(log_softmax(logits[:n0, :C]), y); dlogits = (softmax - onehot)/n0
-void launch_softmax_nll(const void* logits, int ld, int C, const int64_t* y, const int32_t* cum,
-                        int cap, float* loss, void* dlogits, int32_t* correct, cudaStream_t s);
+// labels come from y[r], or (labels_all != nullptr) from labels_all[nodes[r]].
+void launch_softmax_nll(const void* logits, int ld, int C, const int64_t* y, const int64_t* labels_all,
+                        const int64_t* nodes, const int32_t* cum, int cap, float* loss, void* dlogits,
+                        int32_t* correct, cudaStream_t s);
+// out[c] = sum over valid rows of X[:, c]  (d multiple of 8, d <= 2048)
+void launch_colsum_bf16(const void* X, const int32_t* cum, int n_hops, int cap, int d, float* out,
+                        cudaStream_t s);
+void launch_zero_rows(float* p, const int32_t* cum, int n_hops, int cap, int d, cudaStream_t s);
 // flat fp32 Adam over [n] with bf16 shadow copy refresh.
 void launch_adam(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr,
                  float b1, float b2, float eps, float wd, const int32_t* step_dev, float gscale,

@@ -181,6 +181,7 @@ __global__ void k_bias_relu(__nv_bfloat16* Z, const __nv_bfloat16* bias, const i
 
 // warp per seed row: log-softmax + NLL forward and backward in one pass.
 __global__ void k_softmax_nll(const __nv_bfloat16* logits, int ld, int C, const int64_t* y,
+                              const int64_t* labels_all, const int64_t* nodes,
                               const int32_t* cum, int cap, float* loss, __nv_bfloat16* dlogits,
                               int32_t* correct) {
   const int lane = threadIdx.x & 31;
@@ -211,7 +212,8 @@ __global__ void k_softmax_nll(const __nv_bfloat16* logits, int ld, int C, const 
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
     const float lse = mx + __logf(sum);
-    const int64_t label = y[r];
+    // labels are looked up through the batch's node list: no separate gather launch
+    const int64_t label = labels_all ? labels_all[nodes[r]] : y[r];
     for (int c = lane; c < ld; c += 32) {
       float g = 0.f;
       if (c < C) {
@@ -244,6 +246,40 @@ __global__ void k_adam(float* p, const float* g, float* m, float* v, __nv_bfloat
     p[i] = pi;
     if (pb) pb[i] = __float2bfloat16(pi);
   }
+}
+
+// column sums of the valid rows of a bf16 [rows, d] matrix (bias gradients); replaces a
+// cap-sized torch reduce kernel that was the most expensive launch of the step.
+__global__ void __launch_bounds__(256) k_colsum(const __nv_bfloat16* X, const int32_t* cum, int n_hops,
+                                                int cap, int d, float* out) {
+  extern __shared__ float s_part[];  // [rows_per_block][d]
+  const int T = min(cum[n_hops], cap);
+  const int groups = d >> 3;               // 8-column groups per row
+  const int rpb = blockDim.x / groups;     // rows handled per block iteration
+  const int cg = threadIdx.x % groups, rl = threadIdx.x / groups;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  if (rl < rpb) {
+    for (int r = blockIdx.x * rpb + rl; r < T; r += gridDim.x * rpb)
+      bf16x8_accum(*reinterpret_cast<const uint4*>(X + static_cast<int64_t>(r) * d + cg * 8), acc);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s_part[rl * d + cg * 8 + i] = acc[i];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    float v = 0.f;
+    for (int q = 0; q < rpb; ++q) v += s_part[q * d + c];
+    if (v != 0.f) atomicAdd(out + c, v);
+  }
+}
+
+__global__ void k_zero_rows(float* p, const int32_t* cum, int n_hops, int cap, int d) {
+  const int T = min(cum[n_hops], cap);
+  const int64_t n4 = static_cast<int64_t>(T) * d / 4;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    reinterpret_cast<float4*>(p)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 __global__ void k_bf16_to_f32(const __nv_bfloat16* s, float* d, int64_t n) {
@@ -298,12 +334,13 @@ void launch_bias_relu(void* Z, const void* bias, const int32_t* cum, int n_hops,
       cap, d, relu);
 }
 
-void launch_softmax_nll(const void* logits, int ld, int C, const int64_t* y, const int32_t* cum,
-                        int cap, float* loss, void* dlogits, int32_t* correct, cudaStream_t s) {
+void launch_softmax_nll(const void* logits, int ld, int C, const int64_t* y, const int64_t* labels_all,
+                        const int64_t* nodes, const int32_t* cum, int cap, float* loss, void* dlogits,
+                        int32_t* correct, cudaStream_t s) {
   cudaMemsetAsync(loss, 0, sizeof(float), s);
   if (correct) cudaMemsetAsync(correct, 0, sizeof(int32_t), s);
   k_softmax_nll<<<grid_for(cap, 8), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(logits), ld,
-                                                  C, y, cum, cap, loss,
+                                                  C, y, labels_all, nodes, cum, cap, loss,
                                                   reinterpret_cast<__nv_bfloat16*>(dlogits), correct);
 }
 
@@ -312,6 +349,19 @@ void launch_adam(float* p, const float* g, float* m, float* v, void* p_bf16, int
                  cudaStream_t s) {
   k_adam<<<grid_for(n, 256, 148 * 4), 256, 0, s>>>(p, g, m, v, reinterpret_cast<__nv_bfloat16*>(p_bf16),
                                                    n, lr, b1, b2, eps, wd, step_dev, gscale);
+}
+
+void launch_colsum_bf16(const void* X, const int32_t* cum, int n_hops, int cap, int d, float* out,
+                        cudaStream_t s) {
+  cudaMemsetAsync(out, 0, sizeof(float) * d, s);
+  const int groups = d / 8;
+  const int rpb = 256 / groups > 0 ? 256 / groups : 1;
+  k_colsum<<<grid_for(cap, rpb * 8, 148 * 2), 256, sizeof(float) * rpb * d, s>>>(
+      reinterpret_cast<const __nv_bfloat16*>(X), cum, n_hops, cap, d, out);
+}
+
+void launch_zero_rows(float* p, const int32_t* cum, int n_hops, int cap, int d, cudaStream_t s) {
+  k_zero_rows<<<grid_for(static_cast<int64_t>(cap) * d / 4, 256 * 4), 256, 0, s>>>(p, cum, n_hops, cap, d);
 }
 
 void launch_bf16_to_f32(const void* src, float* dst, int64_t n, cudaStream_t s) {

@@ -250,8 +250,9 @@ class GraphSageEngine(object):
         torch.mm(self.A[l], self.W(l).t(), out=self.Z[l])
         nat.bias_relu(self.Z[l], self.b(l), ar.counters, nh, relu)
         self._k(2)
-    torch.index_select(self.labels, 0, ar.nodes[:self.bs].clamp(min=0), out=self.y)
-    nat.softmax_nll(self.Z[self.L], self.C, self.y, ar.counters, self.loss, self.dPre[self.L], self.correct)
+    # labels[nodes[r]] is looked up inside the loss kernel (no gather launch)
+    nat.softmax_nll(self.Z[self.L], self.C, None, self.labels, ar.nodes, ar.counters, self.loss,
+                    self.dPre[self.L], self.correct)
     self._k(1)
 
   def _backward(self):
@@ -261,14 +262,39 @@ class GraphSageEngine(object):
       off, n, k = self._w_off[l - 1]
       boff, _ = self._b_off[l - 1]
       gW = self.g32[off:off + n * k].view(n, k)
-      gW.copy_(torch.mm(self.dPre[l].t(), self.A[l]))
-      self.g32[boff:boff + n].copy_(self.dPre[l].sum(0, dtype=torch.float32))
+      # dW = dPre^T A accumulated in fp32 straight into the flat gradient buffer
+      self._mm_f32(self.dPre[l].t(), self.A[l], gW)
+      nat.colsum_bf16(self.dPre[l], ar.counters, nh, self.g32[boff:boff + n])
+      self._k(1)
       if l > 1:
         torch.mm(self.dPre[l], self.W(l), out=self.dA[l])
-        self.dH[l - 1].zero_()
+        nat.zero_rows(self.dH[l - 1], ar.counters, nh + 1)
         nat.sage_scatter_bwd(self.dA[l], self.dims_in[l - 1], ar.counters, nh, ell, ks, ar.deg, self.dH[l - 1])
         nat.relu_bwd_cast(self.dH[l - 1], self.Z[l - 1], ar.counters, nh + 1, self.dPre[l - 1])
-        self._k(2)
+        self._k(3)
+
+  _f32_mode = None
+
+  def _mm_f32(self, a, b, out):
+    """out(fp32) = a(bf16) @ b(bf16) with fp32 accumulation/output when cuBLASLt offers it."""
+    if GraphSageEngine._f32_mode is None:
+      try:
+        torch.mm(a, b, out_dtype=torch.float32, out=out)
+        GraphSageEngine._f32_mode = 'out'
+        return
+      except Exception:
+        try:
+          out.copy_(torch.mm(a, b, out_dtype=torch.float32))
+          GraphSageEngine._f32_mode = 'ret'
+          return
+        except Exception:
+          GraphSageEngine._f32_mode = 'bf16'
+    if GraphSageEngine._f32_mode == 'out':
+      torch.mm(a, b, out_dtype=torch.float32, out=out)
+    elif GraphSageEngine._f32_mode == 'ret':
+      out.copy_(torch.mm(a, b, out_dtype=torch.float32))
+    else:
+      out.copy_(torch.mm(a, b))
 
   def _optimizer(self):
     self.step_dev.add_(1)

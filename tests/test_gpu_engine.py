@@ -119,13 +119,26 @@ def test_softmax_nll_and_adam(native):
   y = torch.randint(0, 47, (128,), device=DEV)
   counters = torch.zeros(16, dtype=torch.int32, device=DEV); counters[1] = 100
   loss = torch.zeros(1, device=DEV); dl = torch.zeros_like(logits); corr = torch.zeros(1, dtype=torch.int32, device=DEV)
-  native.softmax_nll(logits, 47, y, counters, loss, dl, corr)
+  native.softmax_nll(logits, 47, y, None, None, counters, loss, dl, corr)
   x = logits[:100, :47].float().requires_grad_(True)
   ref = F.cross_entropy(x, y[:100]); ref.backward()
   assert abs(loss.item() - ref.item()) < 1e-3
   assert torch.allclose(dl[:100, :47].float(), x.grad, atol=2e-4)
   assert dl[100:].abs().sum() == 0 and dl[:, 47:].abs().sum() == 0
   assert corr.item() == int((x.argmax(1) == y[:100]).sum())
+  # fused label lookup through the node list
+  nodes = torch.randperm(500, device=DEV)[:128]; labels_all = torch.randint(0, 47, (500,), device=DEV)
+  loss2 = torch.zeros(1, device=DEV)
+  native.softmax_nll(logits, 47, None, labels_all, nodes, counters, loss2, dl, None)
+  assert abs(loss2.item() - F.cross_entropy(logits[:100, :47].float(), labels_all[nodes[:100]]).item()) < 1e-3
+  # column sums / row zeroing with device-side extents
+  X = torch.randn(300, 256, device=DEV).to(torch.bfloat16); out = torch.zeros(256, device=DEV)
+  counters[2] = 257
+  native.colsum_bf16(X, counters, 2, out)
+  assert torch.allclose(out, X[:257].float().sum(0), atol=1e-2, rtol=1e-3)
+  Y = torch.ones(300, 64, device=DEV)
+  native.zero_rows(Y, counters, 2)
+  assert Y[:257].abs().sum() == 0 and Y[257:].sum() == 43 * 64
   p = torch.randn(1000, device=DEV); g = torch.randn(1000, device=DEV)
   p_ref = p.clone().requires_grad_(True); opt = torch.optim.Adam([p_ref], lr=1e-2)
   m = torch.zeros_like(p); v = torch.zeros_like(p); p16 = p.to(torch.bfloat16); step = torch.zeros(1, dtype=torch.int32, device=DEV)
