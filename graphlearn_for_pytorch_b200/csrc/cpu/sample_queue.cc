@@ -77,8 +77,13 @@ TensorMap tensor_map_read(std::shared_ptr<ShmBlock> block) {
     off = align_up(off);
     auto opts = torch::TensorOptions().dtype(static_cast<torch::ScalarType>(dt)).device(torch::kCPU);
     // zero-copy view; every tensor keeps the block (and thus the ring space) alive
-    std::shared_ptr<ShmBlock> keep = block;
-    out[key] = torch::from_blob(base + off, shape, [keep](void*) mutable { keep.reset(); }, opts);
+    if (nbytes == 0) {
+      // no storage to alias: a from_blob deleter would never fire and pin the ring block
+      out[key] = torch::empty(shape, opts);
+    } else {
+      std::shared_ptr<ShmBlock> keep = block;
+      out[key] = torch::from_blob(base + off, shape, [keep](void*) mutable { keep.reset(); }, opts);
+    }
     off = align_up(off + nbytes);
   }
   return out;

@@ -15,10 +15,10 @@
 // (csrc/cuda/unified_tensor.cu:47-81) + PyG scatter-mean + two cuBLAS GEMMs +
 // bias/ReLU elementwise kernels, and keeps the row count on the device.
 //
-// Roles (416 threads, one persistent CTA per SM):
-//   warps 0-7   producers   (8-lane group per target row)
-//   warp  8     TMEM alloc, weight bulk-load, MMA issue (one elected lane)
-//   warps 9-12  epilogue    (TMEM lane quadrant = warp_id % 4)
+// Roles (672 threads, one persistent CTA per SM):
+//   warps 0-15  producers   (8-lane group per target row, 2 rows per group per tile)
+//   warp  16    TMEM alloc, weight bulk-load, MMA issue (one elected lane)
+//   warps 17-20 epilogue    (TMEM lane quadrant = warp_id % 4)
 #include "device_utils.cuh"
 
 namespace glt {
@@ -26,9 +26,9 @@ namespace glt {
 namespace {
 
 constexpr int kTileM = 128;
-constexpr int kProducerWarps = 8;
-constexpr int kMmaWarp = 8;
-constexpr int kThreads = 13 * 32;
+constexpr int kProducerWarps = 16;
+constexpr int kMmaWarp = 16;
+constexpr int kThreads = 21 * 32;
 constexpr int kChunkBytes = 128;                    // 64 bf16 = one SWIZZLE_128B atom row
 constexpr int kAChunkTile = kTileM * kChunkBytes;   // 16 KB per K-chunk of an A tile
 
@@ -170,39 +170,67 @@ __global__ void __launch_bounds__(kThreads, 1) k_sage_fused(SageFusedArgs f) {
 
   if (warp < kProducerWarps) {
     // ------------------------------ producers ------------------------------
-    const int gl = lane & 7;         // lane in the 8-lane row group
-    const int gw = lane >> 3;        // group in warp
+    // 64 eight-lane groups; each owns rows {g, g+64} of the 128-row tile.  The pointer
+    // chase (deg -> ELL -> node id -> owner shard) of both rows is issued up front so
+    // the four dependent-load chains overlap; feature rows then stream in batches of
+    // four neighbours x NC 16-byte vectors per lane.
+    const int gl = lane & 7;
+    const int gw = lane >> 3;
     const unsigned gmask = 0xFFu << (gw * 8);
-    const int group = warp * 4 + gw; // 0..31
+    const int group = warp * 4 + gw;  // 0..63
+    constexpr int RPG = kTileM / (kProducerWarps * 4);  // rows per group per tile (2)
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-      uint4 res_mean[4][NC], res_self[4][NC];
-      bool row_ok[4];
+      int dg[RPG];
+      const int32_t* ell[RPG];
+      const uint8_t* p_lo[RPG];
+      const uint8_t* p_hi[RPG];
+      const uint8_t* p_self[RPG];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int r = group + q * 32;
+      for (int q = 0; q < RPG; ++q) {
+        const int t = tile * kTileM + group + q * (kTileM / RPG);
+        dg[q] = 0; ell[q] = nullptr; p_lo[q] = p_hi[q] = p_self[q] = nullptr;
+        if (t < T) {
+          const HopLoc2 l = locate2(a.cum, a.n_hops_targets, t);
+          dg[q] = a.deg[t];
+          ell[q] = a.ell[l.hop] + static_cast<int64_t>(l.row) * a.k[l.hop];
+        }
+      }
+      int s_lo[RPG], s_hi[RPG];
+#pragma unroll
+      for (int q = 0; q < RPG; ++q) {
+        s_lo[q] = (gl < dg[q]) ? ell[q][gl] : -1;
+        s_hi[q] = (gl + 8 < dg[q]) ? ell[q][gl + 8] : -1;
+      }
+#pragma unroll
+      for (int q = 0; q < RPG; ++q) {
+        const int t = tile * kTileM + group + q * (kTileM / RPG);
+        if (s_lo[q] >= 0) p_lo[q] = src_row2(a, s_lo[q]);
+        if (s_hi[q] >= 0) p_hi[q] = src_row2(a, s_hi[q]);
+        if (t < T && gl == 0) p_self[q] = src_row2(a, t);
+        p_self[q] = reinterpret_cast<const uint8_t*>(
+            __shfl_sync(gmask, reinterpret_cast<unsigned long long>(p_self[q]), 0, 8));
+      }
+      bool waited = false;
+#pragma unroll
+      for (int q = 0; q < RPG; ++q) {
+        const int r = group + q * (kTileM / RPG);
         const int t = tile * kTileM + r;
-        row_ok[q] = t < T;
         float acc[NC][8];
 #pragma unroll
         for (int c = 0; c < NC; ++c)
 #pragma unroll
           for (int i = 0; i < 8; ++i) acc[c][i] = 0.f;
-        int dg = 0;
-        const int32_t* ell = nullptr;
-        if (row_ok[q]) {
-          const HopLoc2 l = locate2(a.cum, a.n_hops_targets, t);
-          dg = a.deg[t];
-          ell = a.ell[l.hop] + static_cast<int64_t>(l.row) * a.k[l.hop];
-        }
-        for (int j0 = 0; j0 < dg; j0 += 8) {
-          const uint8_t* my_ptr = nullptr;
-          if (j0 + gl < dg) {
-            const int s = ell[j0 + gl];
-            if (s >= 0) my_ptr = src_row2(a, s);
+        for (int j0 = 0; j0 < dg[q]; j0 += 8) {
+          const uint8_t* my_ptr = (j0 == 0) ? p_lo[q] : p_hi[q];
+          if (j0 >= 16) {
+            my_ptr = nullptr;
+            if (j0 + gl < dg[q]) {
+              const int s = ell[q][j0 + gl];
+              if (s >= 0) my_ptr = src_row2(a, s);
+            }
           }
-          const int cnt = min(8, dg - j0);
-          // loads of four neighbours are issued back to back before their first use
+          const int cnt = min(8, dg[q] - j0);
 #pragma unroll
           for (int jb = 0; jb < 8; jb += 4) {
             uint4 v[4][NC];
@@ -220,32 +248,28 @@ __global__ void __launch_bounds__(kThreads, 1) k_sage_fused(SageFusedArgs f) {
               for (int c = 0; c < NC; ++c) bf16x8_accum(v[jj][c], acc[c]);
           }
         }
-        const float inv = dg > 0 ? 1.f / static_cast<float>(dg) : 0.f;
-        const uint8_t* self = row_ok[q] ? src_row2(a, t) : nullptr;
+        const float inv = dg[q] > 0 ? 1.f / static_cast<float>(dg[q]) : 0.f;
+        uint4 res_mean[NC], res_self[NC];
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
-          res_mean[q][c] = pack_bf16x8(acc[c], inv);
-          res_self[q][c] = self ? ld_nc_v4(self + c * kChunkBytes + gl * 16) : make_uint4(0, 0, 0, 0);
+          res_mean[c] = pack_bf16x8(acc[c], inv);
+          res_self[c] = p_self[q] ? ld_nc_v4(p_self[q] + c * kChunkBytes + gl * 16) : make_uint4(0, 0, 0, 0);
         }
-        if (row_ok[q] && f.a_save) {
+        if (t < T && f.a_save) {
           uint8_t* o = reinterpret_cast<uint8_t*>(f.a_save) + static_cast<int64_t>(t) * a.d * 4;
 #pragma unroll
           for (int c = 0; c < NC; ++c) {
-            *reinterpret_cast<uint4*>(o + c * kChunkBytes + gl * 16) = res_mean[q][c];
-            *reinterpret_cast<uint4*>(o + a.d * 2 + c * kChunkBytes + gl * 16) = res_self[q][c];
+            *reinterpret_cast<uint4*>(o + c * kChunkBytes + gl * 16) = res_mean[c];
+            *reinterpret_cast<uint4*>(o + a.d * 2 + c * kChunkBytes + gl * 16) = res_self[c];
           }
         }
-      }
-      // the single A buffer is free once the previous tile's MMAs have retired
-      mbar_wait(bar_a_empty, (it & 1) ^ 1);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int r = group + q * 32;
+        // the single A buffer is free once the previous tile's MMAs have retired
+        if (!waited) { mbar_wait(bar_a_empty, (it & 1) ^ 1); waited = true; }
         const uint32_t off = r * kChunkBytes + ((gl ^ (r & 7)) << 4);
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
-          *reinterpret_cast<uint4*>(smem_a + c * kAChunkTile + off) = res_mean[q][c];
-          *reinterpret_cast<uint4*>(smem_a + (NC + c) * kAChunkTile + off) = res_self[q][c];
+          *reinterpret_cast<uint4*>(smem_a + c * kAChunkTile + off) = res_mean[c];
+          *reinterpret_cast<uint4*>(smem_a + (NC + c) * kAChunkTile + off) = res_self[c];
         }
       }
       fence_proxy_async();  // generic-proxy writes -> visible to the tensor-core (async) proxy
