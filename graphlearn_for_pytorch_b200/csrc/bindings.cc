@@ -591,6 +591,71 @@ static void enable_peer_access(int dev, int peer) {
   TORCH_CHECK(e == cudaSuccess, "cudaDeviceEnablePeerAccess: ", cudaGetErrorString(e));
 }
 
+// ---------------------------------------------------------------------------
+// PeerBuffer: cudaMalloc'ed shard that other processes map with CUDA IPC *on their own
+// device* (cudaIpcMemLazyEnablePeerAccess), so their kernels can dereference it over
+// NVLink.  (Memory imported through torch's own IPC path is opened in the exporter
+// device's context and is not reachable from kernels running on the importer's GPU.)
+// ---------------------------------------------------------------------------
+struct PeerBuffer : public std::enable_shared_from_this<PeerBuffer> {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  int device = 0;       // device whose kernels may use `ptr`
+  bool imported = false;
+
+  ~PeerBuffer() {
+    if (ptr == nullptr) return;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    cudaSetDevice(device);
+    if (imported) cudaIpcCloseMemHandle(ptr); else cudaFree(ptr);
+    cudaSetDevice(cur);
+  }
+
+  static std::shared_ptr<PeerBuffer> allocate(int device, int64_t nbytes) {
+    c10::cuda::CUDAGuard guard(device);
+    auto b = std::make_shared<PeerBuffer>();
+    b->device = device;
+    b->bytes = std::max<int64_t>(nbytes, 256);
+    cudaError_t e = cudaMalloc(&b->ptr, b->bytes);
+    TORCH_CHECK(e == cudaSuccess, "cudaMalloc(", b->bytes, ") failed: ", cudaGetErrorString(e));
+    return b;
+  }
+
+  py::bytes handle() const {
+    TORCH_CHECK(!imported, "only the owner can export a handle");
+    c10::cuda::CUDAGuard guard(device);
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, ptr);
+    TORCH_CHECK(e == cudaSuccess, "cudaIpcGetMemHandle failed: ", cudaGetErrorString(e));
+    return py::bytes(reinterpret_cast<const char*>(&h), sizeof(h));
+  }
+
+  static std::shared_ptr<PeerBuffer> open(const std::string& handle_bytes, int my_device, int64_t nbytes) {
+    TORCH_CHECK(handle_bytes.size() == sizeof(cudaIpcMemHandle_t), "bad IPC handle size");
+    c10::cuda::CUDAGuard guard(my_device);
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle_bytes.data(), sizeof(h));
+    auto b = std::make_shared<PeerBuffer>();
+    b->device = my_device;
+    b->bytes = nbytes;
+    b->imported = true;
+    cudaError_t e = cudaIpcOpenMemHandle(&b->ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    TORCH_CHECK(e == cudaSuccess, "cudaIpcOpenMemHandle failed: ", cudaGetErrorString(e));
+    return b;
+  }
+
+  // non-owning tensor view (keeps the buffer alive through the deleter)
+  Tensor as_tensor(torch::ScalarType dtype, std::vector<int64_t> sizes) {
+    int64_t n = 1;
+    for (auto v : sizes) n *= v;
+    TORCH_CHECK(static_cast<size_t>(n) * c10::elementSize(dtype) <= bytes, "view exceeds the peer buffer");
+    std::shared_ptr<PeerBuffer> keep = shared_from_this();
+    auto opts = torch::TensorOptions().dtype(dtype).device(torch::kCUDA, device);
+    return torch::from_blob(ptr, sizes, [keep](void*) mutable { keep.reset(); }, opts);
+  }
+};
+
 static Tensor pack_weight(const Tensor& w) {
   c10::cuda::CUDAGuard guard(w.device());
   TORCH_CHECK(w.scalar_type() == torch::kBFloat16 && w.is_contiguous() && w.dim() == 2);
@@ -706,6 +771,14 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("zero_rows", &zero_rows);
   m.def("sage_fused", &sage_fused);
   m.def("sage_fused_supported", &sage_fused_supported);
+  py::class_<PeerBuffer, std::shared_ptr<PeerBuffer>>(m, "PeerBuffer")
+      .def_static("allocate", &PeerBuffer::allocate)
+      .def_static("open", &PeerBuffer::open)
+      .def("handle", &PeerBuffer::handle)
+      .def("as_tensor", &PeerBuffer::as_tensor)
+      .def_readonly("bytes", &PeerBuffer::bytes)
+      .def_readonly("device", &PeerBuffer::device)
+      .def_readonly("imported", &PeerBuffer::imported);
   m.def("enable_peer_access", &enable_peer_access);
   m.def("pack_weight", &pack_weight);
   m.def("pack_weight_into", &pack_weight_into);

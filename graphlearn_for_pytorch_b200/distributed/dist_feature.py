@@ -1,0 +1,153 @@
+"""DistFeature: partitioned feature lookup.
+
+Parity: reference python/distributed/dist_feature.py:69-452 (local select + remote fan-out +
+stitch; optional collective exchange).  Two data planes:
+  * 'p2p'  (one NVSwitch box): the local store is a UnifiedTensor whose parts are *all*
+    ranks' shards mapped over NVLink -> a lookup is ONE gather kernel, no RPC, no stitch;
+  * 'rpc'  (across machines / CPU): ids are split by the feature partition book, remote
+    partitions are asked through RPC (owner gathers on its side), results are scattered
+    back in request order.
+"""
+from typing import Dict, List, Optional, Tuple, Union
+
+import torch
+
+from ..data import Feature
+from ..partition import PartitionBook
+from ..typing import EdgeType, NodeType
+from .rpc import RpcCalleeBase, RpcDataPartitionRouter, rpc_register, rpc_request_async
+
+PartialFeature = Tuple[torch.Tensor, torch.Tensor]  # (features, positions in the request)
+
+
+class RpcFeatureLookupCallee(RpcCalleeBase):
+  def __init__(self, dist_feature: 'DistFeature'):
+    self.dist_feature = dist_feature
+
+  def call(self, ids: torch.Tensor, is_node_feat: bool = True, input_type=None):
+    return self.dist_feature.local_get(ids, is_node_feat, input_type).cpu()
+
+
+class DistFeature(object):
+  """Args:
+    num_partitions, partition_idx: layout.
+    local_feature: Feature / Dict[type, Feature] holding this partition's rows (+ cache).
+    feature_pb: partition book(s) of the feature ids.
+    local_only: every id is resolvable locally (replicated features / p2p tables).
+    rpc_router: RpcDataPartitionRouter for remote lookups.
+    device: where results are produced.
+  """
+
+  def __init__(self, num_partitions: int, partition_idx: int, local_feature, feature_pb,
+               local_only: bool = False, rpc_router: Optional[RpcDataPartitionRouter] = None,
+               device: Optional[torch.device] = None):
+    self.num_partitions = num_partitions
+    self.partition_idx = partition_idx
+    self.local_feature = local_feature
+    self.data_cls = 'hetero' if isinstance(local_feature, dict) else 'homo'
+    self.feature_pb = feature_pb
+    self.local_only = local_only
+    self.rpc_router = rpc_router
+    self.device = torch.device(device) if device is not None else torch.device('cpu')
+    self.rpc_callee_id = None
+    if not local_only and rpc_router is not None:
+      self.rpc_callee_id = rpc_register(RpcFeatureLookupCallee(self))
+
+  # ------------------------------------------------------------------ local
+  def _feat(self, input_type=None) -> Feature:
+    if self.data_cls == 'hetero':
+      return self.local_feature[input_type]
+    return self.local_feature
+
+  def _pb(self, input_type=None):
+    if isinstance(self.feature_pb, dict):
+      return self.feature_pb[input_type]
+    return self.feature_pb
+
+  def local_get(self, ids: torch.Tensor, is_node_feat: bool = True, input_type=None) -> torch.Tensor:
+    feat = self._feat(input_type)
+    if getattr(feat, 'with_gpu', False):
+      return feat[ids]
+    return feat.cpu_get(ids)
+
+  # ------------------------------------------------------------------ lookup
+  def __getitem__(self, ids) -> torch.Tensor:
+    input_type = None
+    if isinstance(ids, tuple):
+      input_type, ids = ids
+    return self.async_get(ids, input_type).wait()
+
+  def async_get(self, ids: torch.Tensor, input_type=None) -> torch.futures.Future:
+    """Future of features[ids] (request order), stitched from local + remote partitions."""
+    fut = torch.futures.Future()
+    if self.local_only or self.num_partitions == 1:
+      fut.set_result(self.local_get(ids, True, input_type).to(self.device))
+      return fut
+    ids_cpu = ids.cpu()
+    pb = self._pb(input_type)
+    owners = pb[ids_cpu]
+    feat = self._feat(input_type)
+    width = feat.shape[1:]
+    out = torch.zeros((ids_cpu.numel(), *width), dtype=feat.dtype, device=self.device)
+    local_mask = owners == self.partition_idx
+    if bool(local_mask.any()):
+      pos = torch.nonzero(local_mask, as_tuple=False).view(-1)
+      out[pos.to(self.device)] = self.local_get(ids_cpu[pos], True, input_type).to(self.device)
+    pending = []
+    for p in range(self.num_partitions):
+      if p == self.partition_idx:
+        continue
+      pos = torch.nonzero(owners == p, as_tuple=False).view(-1)
+      if pos.numel() == 0:
+        continue
+      to = self.rpc_router.get_to_worker(p)
+      pending.append((pos, rpc_request_async(to, self.rpc_callee_id, args=(ids_cpu[pos], True, input_type))))
+    if not pending:
+      fut.set_result(out)
+      return fut
+    remaining = [len(pending)]
+    import threading
+    lock = threading.Lock()
+
+    def on_done(f, pos):
+      try:
+        out[pos.to(self.device)] = f.value().to(self.device)
+      except Exception as e:  # noqa: BLE001
+        with lock:
+          if not fut.done():
+            fut.set_exception(e)
+        return
+      with lock:
+        remaining[0] -= 1
+        if remaining[0] == 0 and not fut.done():
+          fut.set_result(out)
+    for pos, f in pending:
+      f.add_done_callback(lambda ff, pos=pos: on_done(ff, pos))
+    return fut
+
+  # ------------------------------------------------------------------ collective exchange
+  def get_all2all(self, ids: torch.Tensor, input_type=None, group=None) -> torch.Tensor:
+    """Feature exchange with collectives instead of RPC (reference `use_all2all`,
+    dist_feature.py:239-378): counts -> ids -> rows, three all_to_all rounds.  Works on
+    gloo (CPU tensors) and NCCL (device tensors)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    assert world == self.num_partitions
+    backend_dev = self.device if dist.get_backend(group) == 'nccl' else torch.device('cpu')
+    ids_b = ids.to(backend_dev)
+    owners = self._pb(input_type)[ids.cpu()].to(backend_dev)
+    order = torch.argsort(owners, stable=True)
+    send_ids = ids_b[order]
+    send_counts = torch.bincount(owners, minlength=world)
+    recv_counts = torch.empty_like(send_counts)
+    dist.all_to_all_single(recv_counts, send_counts, group=group)
+    sc, rc = send_counts.tolist(), recv_counts.tolist()
+    recv_ids = torch.empty(sum(rc), dtype=torch.int64, device=backend_dev)
+    dist.all_to_all_single(recv_ids, send_ids, rc, sc, group=group)
+    rows = self.local_get(recv_ids, True, input_type).to(backend_dev)
+    feat = self._feat(input_type)
+    got = torch.empty((sum(sc), *feat.shape[1:]), dtype=rows.dtype, device=backend_dev)
+    dist.all_to_all_single(got, rows.contiguous(), sc, rc, group=group)
+    out = torch.empty_like(got)
+    out[order] = got
+    return out.to(self.device)

@@ -21,30 +21,36 @@ def world_info(group=None):
 
 
 def exchange_peer_tensors(t: torch.Tensor, group=None) -> List[torch.Tensor]:
-  """All-gather *views*: returns [tensor of rank 0, ..., tensor of rank W-1] where entry r
-  aliases rank r's device memory (CUDA IPC mapping; own entry is `t` itself).
+  """All-gather *views*: returns [view of rank 0's shard, ..., view of rank W-1's shard].
 
-  The caller must keep `t` alive for as long as any peer may read it.
+  `t` is copied once into a cudaMalloc'ed PeerBuffer (the symmetric-heap segment of this
+  rank); every other rank maps that segment with CUDA IPC **on its own device** with lazy
+  peer access, so entry r of the result is a tensor on the *local* device whose storage is
+  rank r's HBM: kernels launched here dereference it over NVLink.  The own entry aliases
+  the local segment -- drop `t` and keep the returned view to avoid a duplicate.
   """
   rank, world = world_info(group)
   if world == 1:
     return [t]
   assert t.is_cuda and t.is_contiguous()
-  from torch.multiprocessing.reductions import reduce_tensor
-  fn, args = reduce_tensor(t)
-  gathered = [None] * world
-  dist.all_gather_object(gathered, (fn, args), group=group)
   nat = require_native()
-  out = []
   my_dev = t.device.index
-  for r, (f, a) in enumerate(gathered):
+  nbytes = t.numel() * t.element_size()
+  buf = nat.PeerBuffer.allocate(my_dev, nbytes)
+  own = buf.as_tensor(t.dtype, list(t.shape))
+  own.copy_(t)
+  torch.cuda.synchronize(t.device)
+  meta = (buf.handle(), nbytes, str(t.dtype), list(t.shape))
+  gathered = [None] * world
+  dist.all_gather_object(gathered, meta, group=group)
+  out = []
+  for r, (handle, nb, dtype_s, shape) in enumerate(gathered):
     if r == rank:
-      out.append(t)
+      out.append(own)
       continue
-    peer = f(*a)
-    nat.enable_peer_access(my_dev, peer.device.index)
-    out.append(peer)
-  # nobody may free / reuse its shard before every peer has mapped it
+    peer = nat.PeerBuffer.open(handle, my_dev, nb)
+    out.append(peer.as_tensor(getattr(torch, dtype_s.split('.')[-1]), shape))
+  # nobody may free its segment before every peer has mapped it
   dist.barrier(group=group)
   return out
 
