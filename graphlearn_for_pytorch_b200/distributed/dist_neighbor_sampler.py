@@ -47,9 +47,8 @@ class RpcSubGraphCallee(RpcCalleeBase):
     self.sampler, self.device = sampler, device
 
   def call(self, nodes: torch.Tensor, with_edge: bool):
-    out = self.sampler.subgraph(NodeSamplerInput(nodes.to(self.device)))
-    node = out.node
-    return node[out.row].cpu(), node[out.col].cpu(), (out.edge.cpu() if out.edge is not None else None)
+    node, rows, cols, eids, _ = self.sampler.node_subgraph(nodes.to(self.device))
+    return node[rows].cpu(), node[cols].cpu(), (eids.cpu() if eids is not None else None)
 
 
 def stitch_one_hop(n_seeds: int, parts: List[Tuple[torch.Tensor, NeighborOutput]], device, with_edge: bool):
@@ -339,7 +338,9 @@ class DistNeighborSampler(ConcurrentEventLoop):
       raise NotImplementedError('distributed subgraph sampling supports homogeneous graphs')
     seeds = inputs.node.to(self.device, dtype=torch.int64)
     if not self._remote:
-      return self.sampler.subgraph(NodeSamplerInput(seeds))
+      out = self.sampler.subgraph(NodeSamplerInput(seeds))
+      out.batch = seeds
+      return out
     nodes = [seeds]
     if self.num_neighbors is not None:
       frontier = torch.unique(seeds)
@@ -359,10 +360,10 @@ class DistNeighborSampler(ConcurrentEventLoop):
       if not bool((owners == p).any()):
         continue
       if p == self.partition_idx:
-        o = self.sampler.subgraph(NodeSamplerInput(node))
-        rows_g.append(o.node[o.row]); cols_g.append(o.node[o.col])
-        if o.edge is not None:
-          eids_g.append(o.edge)
+        n2, r2, c2, e2, _ = self.sampler.node_subgraph(node)
+        rows_g.append(n2[r2]); cols_g.append(n2[c2])
+        if e2 is not None:
+          eids_g.append(e2)
       else:
         to = self.rpc_router.get_to_worker(p)
         futs.append(wrap_torch_future(rpc_request_async(to, self.rpc_subgraph_callee_id,
@@ -377,7 +378,7 @@ class DistNeighborSampler(ConcurrentEventLoop):
     cg = torch.cat(cols_g) if cols_g else empty
     return SamplerOutput(node=node, row=table.lookup(rg), col=table.lookup(cg),
                          edge=(torch.cat(eids_g) if eids_g else empty) if self.with_edge else None,
-                         device=self.device, metadata=local[:seeds.numel()])
+                         batch=seeds, device=self.device, metadata=local[:seeds.numel()])
 
   # ------------------------------------------------------------------ message collation
   async def _get_node_feats(self, ids: torch.Tensor, ntype=None):

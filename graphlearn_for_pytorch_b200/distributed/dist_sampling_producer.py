@@ -53,6 +53,7 @@ def _sampling_worker_loop(rank: int, data: DistDataset, sampler_input, unshuffle
                           channel: ChannelBase, task_queue, status_queue, mp_barrier):
   """Body of one sampling subprocess."""
   dist_sampler = None
+  graceful = False
   try:
     ctx = get_context()
     # the sampling subprocesses form their own RPC world
@@ -78,6 +79,8 @@ def _sampling_worker_loop(rank: int, data: DistDataset, sampler_input, unshuffle
       except queue.Empty:
         continue
       if cmd == MpCommand.STOP:
+        # keep serving peers' remote requests until *every* sampling worker is done
+        graceful = True
         break
       index, epoch = args
       n = 0
@@ -96,7 +99,7 @@ def _sampling_worker_loop(rank: int, data: DistDataset, sampler_input, unshuffle
       except Exception:  # noqa: BLE001
         pass
     try:
-      shutdown_rpc(graceful=False)
+      shutdown_rpc(graceful=graceful)
     except Exception:  # noqa: BLE001
       pass
 
@@ -172,7 +175,7 @@ class DistMpSamplingProducer(object):
       except Exception:  # noqa: BLE001
         pass
     for w in self._workers:
-      w.join(timeout=MP_STATUS_CHECK_INTERVAL)
+      w.join(timeout=120)   # graceful RPC shutdown waits for the slowest peer worker
     for w in self._workers:
       if w.is_alive():
         w.terminate()

@@ -445,24 +445,32 @@ class NeighborSampler(BaseSampler):
         nodes.append(torch.unique(nbr))
         frontier = nodes[-1]
     all_nodes = torch.cat(nodes)
+    node, rows, cols, eids, mapping = self.node_subgraph(all_nodes, seeds.numel())
+    return SamplerOutput(node=node, row=rows, col=cols, edge=eids if self.with_edge else None,
+                         device=self.device, metadata=mapping)
+
+  def node_subgraph(self, all_nodes: torch.Tensor, num_seeds: int = 0):
+    """Induced subgraph on exactly `all_nodes` (no neighbourhood expansion).
+    -> (unique nodes, rows, cols, eids, local ids of the first `num_seeds` inputs)."""
+    all_nodes = all_nodes.to(self.device, dtype=torch.int64).contiguous()
+    self.lazy_init_sampler()
     if self.is_cuda:
       table = IdTable(self.device, all_nodes.numel())
       local = table.init(all_nodes)
       n = table.size()
       rows, cols, eids = table.native.subgraph(self.graph.graph_handler, n, self.with_edge)
       node = table.keys(0)
-      mapping = local[:seeds.numel()]
+      mapping = local[:num_seeds]
     else:
       topo = self.graph.topo
       node, rows, cols, eids = self._nat.cpu_node_subgraph(topo.indptr, topo.indices, topo.edge_ids,
-                                                           all_nodes.contiguous(), self.with_edge)
+                                                           all_nodes, self.with_edge)
       t = self._nat.CpuIdTable(node.numel())
       t.insert(node)
-      mapping = t.lookup(seeds.contiguous())
+      mapping = t.lookup(all_nodes[:num_seeds].contiguous())
     if self.edge_dir == 'in':
       rows, cols = cols, rows
-    return SamplerOutput(node=node, row=rows, col=cols, edge=eids if self.with_edge else None,
-                         device=self.device, metadata=mapping)
+    return node, rows, cols, (eids if self.with_edge else None), mapping
 
   # ------------------------------------------------------------------ random walk
   def random_walk(self, starts: torch.Tensor, walk_length: int, p: float = 1.0, q: float = 1.0,

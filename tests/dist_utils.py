@@ -1,0 +1,85 @@
+"""Fixtures for distributed tests: a 40-node ring (v -> v+1, v+2) split in two partitions, feature
+row v == [v]*dim, edge feature e == [e]*4, label v == v (idea: reference test/python/dist_test_utils.py)."""
+import os
+import sys
+import traceback
+
+import torch
+import torch.multiprocessing as mp
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+N = 40
+
+
+def build_partition(rank: int, world: int = 2, scheme: str = 'hash', edge_dir: str = 'out', dim: int = 8):
+  import graphlearn_for_pytorch_b200 as glt
+  from graphlearn_for_pytorch_b200.distributed import DistDataset
+  from graphlearn_for_pytorch_b200.partition import GLTPartitionBook, RangePartitionBook
+  from graphlearn_for_pytorch_b200.utils.synthetic import id_features, ring_graph
+  from graphlearn_for_pytorch_b200.utils.tensor import id2idx
+  ei = ring_graph(N)
+  eids = torch.arange(ei.shape[1])
+  if scheme == 'hash':
+    node_pb = GLTPartitionBook(torch.arange(N) % world)
+  else:
+    per = N // world
+    node_pb = RangePartitionBook([(r * per, (r + 1) * per) for r in range(world)], rank)
+  key = ei[0] if edge_dir == 'out' else ei[1]
+  owners = node_pb[key]
+  edge_pb = GLTPartitionBook(owners.clone())
+  m = owners == rank
+  ds = DistDataset(edge_dir=edge_dir)
+  ds.num_partitions, ds.partition_idx = world, rank
+  ds.init_graph(ei[:, m], eids[m], graph_mode='CPU', num_nodes=N)
+  own = torch.nonzero(node_pb[torch.arange(N)] == rank).view(-1)
+  ds.init_node_features(id_features(N, dim)[own], id2idx(own), with_gpu=False)
+  own_e = eids[m]
+  ds.init_edge_features(id_features(ei.shape[1], 4)[own_e], id2idx(own_e), with_gpu=False)
+  ds.init_node_labels(torch.arange(N))
+  ds.node_pb, ds.edge_pb = node_pb, edge_pb
+  return ds
+
+
+def check_batch(b, with_edge=True):
+  n = N
+  assert torch.equal(b.x[:, 0].long(), b.node), (b.x[:, 0], b.node)
+  assert torch.equal(b.y, b.node)
+  src, dst = b.node[b.edge_index[0]], b.node[b.edge_index[1]]
+  assert torch.all(((src - dst) % n == 1) | ((src - dst) % n == 2))
+  if with_edge and b.edge is not None and b.edge_attr is not None:
+    assert torch.equal(b.edge_attr[:, 0].long(), b.edge)
+  assert sum(b.num_sampled_nodes) == b.node.numel()
+
+
+def _entry(rank, world, port, fn, args, err_q):
+  try:
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    fn(rank, world, port, *args)
+  except Exception:  # noqa: BLE001
+    err_q.put((rank, traceback.format_exc()))
+    raise
+
+
+def run_workers(fn, world=2, args=(), timeout=240):
+  """Spawn `world` processes running fn(rank, world, port, *args); assert clean exit codes."""
+  from graphlearn_for_pytorch_b200.utils.common import get_free_port
+  ctx = mp.get_context('spawn')
+  port = get_free_port()
+  err_q = ctx.Queue()
+  procs = [ctx.Process(target=_entry, args=(r, world, port, fn, args, err_q)) for r in range(world)]
+  for p in procs:
+    p.start()
+  for p in procs:
+    p.join(timeout)
+  errs = []
+  while not err_q.empty():
+    errs.append(err_q.get())
+  for p in procs:
+    if p.is_alive():
+      p.terminate()
+      errs.append(('?', 'timeout'))
+  assert not errs, '\n'.join(f'[rank {r}] {e}' for r, e in errs)
+  assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]

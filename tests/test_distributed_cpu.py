@@ -1,0 +1,196 @@
+"""Worker-mode and server-client-mode distributed tests on CPU: 2 spawned processes talking over
+localhost RPC (the reference's strategy, test/python/test_dist_neighbor_loader.py:297-594), with
+child exit codes asserted."""
+import os
+import tempfile
+
+import pytest
+import torch
+
+from dist_utils import N, build_partition, check_batch, run_workers
+
+
+def _w_rpc_basics(rank, world, port):
+  import graphlearn_for_pytorch_b200.distributed as d
+  d.init_worker_group(world, rank)
+  d.init_rpc('127.0.0.1', port)
+  got = d.all_gather(rank * 10)
+  assert sorted(got.values()) == [0, 10]
+  d.barrier()
+  table = d.rpc_sync_data_partitions(world, rank)
+  assert [len(t) for t in table] == [1, 1]
+
+  class Echo(d.RpcCalleeBase):
+    def call(self, x):
+      return x + rank
+  cid = d.rpc_register(Echo())
+  other = table[1 - rank][0]
+  assert d.rpc_request(other, cid, args=(torch.tensor([5]),)).item() == 5 + (1 - rank)
+  d.barrier()
+  d.shutdown_rpc()
+
+
+def test_rpc_basics():
+  run_workers(_w_rpc_basics)
+
+
+def _w_dist_feature(rank, world, port):
+  import graphlearn_for_pytorch_b200.distributed as d
+  d.init_worker_group(world, rank)
+  d.init_rpc('127.0.0.1', port)
+  ds = build_partition(rank, world)
+  router = d.RpcDataPartitionRouter(d.rpc_sync_data_partitions(world, rank))
+  df = d.DistFeature(world, rank, ds.node_features, ds.node_feat_pb, rpc_router=router)
+  ids = torch.tensor([0, 1, 2, 3, 39, 38, 7, 7])
+  out = df[ids]
+  assert torch.equal(out[:, 0].long(), ids)
+  d.barrier()
+  d.shutdown_rpc()
+
+
+def test_dist_feature():
+  run_workers(_w_dist_feature)
+
+
+def _w_neighbor_loader(rank, world, port, scheme, mode, edge_dir):
+  import graphlearn_for_pytorch_b200.distributed as d
+  d.init_worker_group(world, rank)
+  ds = build_partition(rank, world, scheme, edge_dir)
+  seeds = torch.nonzero(ds.node_pb[torch.arange(N)] == rank).view(-1)
+  if mode == 'collocated':
+    opts = d.CollocatedDistSamplingWorkerOptions(master_addr='127.0.0.1', master_port=port)
+  else:
+    opts = d.MpDistSamplingWorkerOptions(num_workers=2, worker_concurrency=2, master_addr='127.0.0.1',
+                                         master_port=port, channel_size='16MB')
+  loader = d.DistNeighborLoader(ds, [2, 2], seeds, batch_size=5, shuffle=True, with_edge=True, edge_dir=edge_dir,
+                                collect_features=True, to_device=torch.device('cpu'), worker_options=opts,
+                                random_seed=3)
+  for epoch in range(2):
+    seen = []
+    for b in loader:
+      if edge_dir == 'out':
+        check_batch(b)
+      else:
+        assert torch.equal(b.x[:, 0].long(), b.node)
+        src, dst = b.node[b.edge_index[0]], b.node[b.edge_index[1]]
+        assert torch.all(((dst - src) % N == 1) | ((dst - src) % N == 2))
+      assert len(b.num_sampled_nodes) == 3 and b.batch_size == b.batch.numel()
+      seen += b.batch.tolist()
+    assert sorted(seen) == sorted(seeds.tolist()), (epoch, sorted(seen))
+  loader.shutdown()
+  if mode == 'collocated':
+    d.barrier()
+    d.shutdown_rpc()
+
+
+@pytest.mark.parametrize('scheme,mode,edge_dir', [('hash', 'collocated', 'out'), ('range', 'collocated', 'out'),
+                                                  ('hash', 'collocated', 'in'), ('hash', 'mp', 'out')])
+def test_dist_neighbor_loader(scheme, mode, edge_dir):
+  run_workers(_w_neighbor_loader, args=(scheme, mode, edge_dir), timeout=300)
+
+
+def _w_link_and_subgraph(rank, world, port):
+  import graphlearn_for_pytorch_b200.distributed as d
+  from graphlearn_for_pytorch_b200.sampler import NegativeSampling
+  d.init_worker_group(world, rank)
+  ds = build_partition(rank, world)
+  opts = d.CollocatedDistSamplingWorkerOptions(master_addr='127.0.0.1', master_port=port)
+  ei = torch.stack(ds.graph.topo.to_coo()[:2])
+  loader = d.DistLinkNeighborLoader(ds, [2], batch_size=8, edge_label_index=ei,
+                                    neg_sampling=NegativeSampling('binary', 1), collect_features=True,
+                                    to_device=torch.device('cpu'), worker_options=opts)
+  n_pos = 0
+  for b in loader:
+    eli, lab = b.edge_label_index, b.edge_label
+    pos = lab == 1
+    src, dst = b.node[eli[1]], b.node[eli[0]]
+    assert torch.all(((dst[pos] - src[pos]) % N == 1) | ((dst[pos] - src[pos]) % N == 2))
+    assert torch.equal(b.x[:, 0].long(), b.node)
+    n_pos += int(pos.sum())
+  assert n_pos == ei.shape[1]
+  sub = d.DistSubGraphLoader(ds, torch.arange(rank, N, 8), num_neighbors=[-1], batch_size=2, with_edge=True,
+                             collect_features=True, to_device=torch.device('cpu'), worker_options=opts)
+  for b in sub:
+    nodes = set(b.node.tolist())
+    src, dst = b.node[b.edge_index[0]], b.node[b.edge_index[1]]
+    got = set(zip(src.tolist(), dst.tolist()))
+    want = {(a, c) for a in nodes for c in nodes if (c - a) % N in (1, 2)}
+    assert got == want                                    # induced edges from *both* partitions
+    assert torch.equal(b.node[b.mapping], b.batch)
+  loader.shutdown(); sub.shutdown()
+  d.barrier()
+  d.shutdown_rpc()
+
+
+def test_dist_link_and_subgraph_loaders():
+  run_workers(_w_link_and_subgraph, timeout=300)
+
+
+def _w_server_client(rank, world, port):
+  """ranks 0,1 = servers (one partition each); ranks 2,3 = clients."""
+  import graphlearn_for_pytorch_b200.distributed as d
+  from graphlearn_for_pytorch_b200.typing import Split
+  if rank < 2:
+    ds = build_partition(rank, 2)
+    own = torch.nonzero(ds.node_pb[torch.arange(N)] == rank).view(-1)
+    ds.init_node_split((own, own[:2], own[:2]))
+    d.init_server(2, rank, ds, '127.0.0.1', port, num_clients=2)
+    d.wait_and_shutdown_server()
+    return
+  crank = rank - 2
+  d.init_client(2, 2, crank, '127.0.0.1', port)
+  n_parts, _, ntypes, etypes = d.request_server(0, d.DistServer.get_dataset_meta)
+  assert n_parts == 2 and ntypes is None
+  feat = d.request_server(1, d.DistServer.get_node_feature, None, torch.tensor([1, 3]))
+  assert feat[:, 0].tolist() == [1.0, 3.0]
+  assert d.request_server(0, d.DistServer.get_node_partition_id, None, torch.tensor([4, 5])).tolist() == [0, 1]
+  opts = d.RemoteDistSamplingWorkerOptions(server_rank=[0, 1], num_workers=1, worker_concurrency=2,
+                                           master_addr='127.0.0.1', master_port=port + 1 + crank,
+                                           buffer_size='16MB', prefetch_size=2)
+  loader = d.DistNeighborLoader(None, [2, 2], Split.train, batch_size=4, with_edge=True, collect_features=True,
+                                to_device=torch.device('cpu'), worker_options=opts)
+  for epoch in range(2):
+    seen = []
+    for b in loader:
+      check_batch(b)
+      seen += b.batch.tolist()
+    assert sorted(seen) == list(range(N)), sorted(seen)
+  loader.shutdown()
+  d.shutdown_client()
+
+
+def test_server_client_mode():
+  run_workers(_w_server_client, world=4, timeout=400)
+
+
+def _w_dist_partitioner(rank, world, port, out):
+  import graphlearn_for_pytorch_b200.distributed as d
+  from graphlearn_for_pytorch_b200.utils.synthetic import id_features, ring_graph
+  d.init_worker_group(world, rank)
+  d.init_rpc('127.0.0.1', port)
+  ei = ring_graph(N)
+  half = ei.shape[1] // 2
+  sl = slice(rank * half, (rank + 1) * half)
+  nsl = slice(rank * N // 2, (rank + 1) * N // 2)
+  d.DistRandomPartitioner(out, N, ei[:, sl], torch.arange(ei.shape[1])[sl], id_features(N, 4)[nsl],
+                          torch.arange(N)[nsl], id_features(ei.shape[1], 2)[sl],
+                          torch.arange(ei.shape[1])[sl]).partition()
+  d.barrier()
+  d.shutdown_rpc()
+
+
+def test_dist_random_partitioner():
+  from graphlearn_for_pytorch_b200.partition import load_partition
+  from graphlearn_for_pytorch_b200.utils.synthetic import ring_graph
+  with tempfile.TemporaryDirectory() as out:
+    run_workers(_w_dist_partitioner, args=(out,))
+    ei = ring_graph(N)
+    nodes, edges = [], []
+    for p in range(2):
+      num, idx, g, nf, ef, npb, epb = load_partition(out, p)
+      assert torch.all(npb[g.edge_index[0]] == p) and torch.all(epb[g.eids] == p)
+      assert torch.equal(ei[0][g.eids], g.edge_index[0]) and torch.equal(ei[1][g.eids], g.edge_index[1])
+      assert torch.equal(nf.feats[:, 0].long(), nf.ids) and torch.all(npb[nf.ids] == p)
+      assert torch.equal(ef.feats[:, 0].long(), ef.ids) and sorted(ef.ids.tolist()) == sorted(g.eids.tolist())
+      nodes += nf.ids.tolist(); edges += g.eids.tolist()
+    assert sorted(nodes) == list(range(N)) and sorted(edges) == list(range(ei.shape[1]))
