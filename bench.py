@@ -48,6 +48,7 @@ def parse_args():
   p.add_argument('--fanout', default='15,10,5')
   p.add_argument('--no-fused', action='store_true')
   p.add_argument('--no-graph', action='store_true')
+  p.add_argument('--no-calibrate', action='store_true', help='size the arena for the worst case')
   p.add_argument('--seed', type=int, default=0)
   p.add_argument('--profile-steps', type=int, default=0,
                  help='run this many eager steps between cudaProfilerStart/Stop (for ncu) and exit')
@@ -183,16 +184,17 @@ def build_ours(args, rank, world, device):
   del topo
   torch.cuda.empty_cache()
   fanouts = [int(x) for x in args.fanout.split(',')]
-  eng = GraphSageEngine(graph, table, labels, in_dim=in_dim, num_nodes=N, fanouts=fanouts,
-                        batch_size=args.batch, hidden=args.hidden, num_classes=args.classes,
-                        lr=3e-3, seed=args.seed, device=device, use_fused=not args.no_fused,
-                        use_cuda_graph=not args.no_graph)
-  eng._keep = keep
   # training seeds: each rank draws from its own slice of a fixed permutation (DDP-style)
   gp = torch.Generator(device='cpu')
   gp.manual_seed(args.seed + 7)
   perm = torch.randperm(N, generator=gp)
   pool = perm[rank::world]
+  eng = GraphSageEngine(graph, table, labels, in_dim=in_dim, num_nodes=N, fanouts=fanouts,
+                        batch_size=args.batch, hidden=args.hidden, num_classes=args.classes,
+                        lr=3e-3, seed=args.seed, device=device, use_fused=not args.no_fused,
+                        use_cuda_graph=not args.no_graph,
+                        calibration_seeds=None if args.no_calibrate else pool)
+  eng._keep = keep
   return eng, pool
 
 
@@ -206,7 +208,7 @@ def run_ours(args):
   eng.warmup_and_capture(n_eager=2)
   if args.profile_steps > 0:
     # ncu --profile-from-start off: only these eager steps are captured
-    eng._graph_fb = eng._graph_opt = None
+    eng._graph_fb = eng._graph_opt = eng._graph_full = None
     sd = pool[:bs].to(device)
     for _ in range(3):
       eng.train_step(sd)
@@ -285,6 +287,8 @@ def run_ours(args):
         'l2_policy': 'inputs larger than L2 (feature table + CSR >> 126 MB, random rows per batch)',
         'baseline_ref': 'BASELINE.md GraphSAGE papers100M epoch 8.56 s / 1,207,179 seeds on 4xA100 (derived)',
         'last_batch_nodes': c[1:5], 'last_batch_edges': c[6:9], 'last_loss': last_loss,
+        'arena': {'calibrated': bool(getattr(eng, 'calibrated', False)), 'cap_rows': [int(x) for x in eng.cap_rows],
+                  'dropped_neighbours_total': int(c[12])},
       },
       'e2e': {'value': e2e, 'unit': 'samples/s', 'ms_per_step': e2e_ms / K,
               'h2d_bytes_per_step': bs * 8, 'd2h_bytes_per_step': 4},

@@ -218,7 +218,7 @@ struct DeviceTable {
     Tensor out = torch::empty({k.numel()}, o32);
     Tensor scratch = torch::empty({std::max<int64_t>(k.numel(), 1)}, o32);
     Tensor counters = torch::zeros({16}, o32);
-    BatchCounters c{counters.data_ptr<int32_t>(), counters.data_ptr<int32_t>() + 6, cursor.data_ptr<int32_t>()};
+    BatchCounters c{counters.data_ptr<int32_t>(), counters.data_ptr<int32_t>() + 6, cursor.data_ptr<int32_t>(), nullptr};
     launch_init_seeds(k.data_ptr<int64_t>(), k.numel(), nullptr, ht, nodes.data_ptr<int64_t>(),
                       out.data_ptr<int32_t>(), scratch.data_ptr<int32_t>(), c, cur_stream());
     check_cuda_err("table init_ordered");
@@ -268,8 +268,10 @@ struct SamplerArena {
   std::vector<Tensor> ell, ell_eids;
   std::unique_ptr<DeviceTable> table;
 
+  // cap_override: optional calibrated frontier capacities per hop (+ one trailing entry for the
+  // number of nodes the last hop may add); empty = worst case (max_seeds * prod(fanouts)).
   SamplerArena(int dev, int64_t max_seeds_, std::vector<int64_t> fanouts_, bool with_edge_,
-               int64_t num_graph_nodes)
+               int64_t num_graph_nodes, std::vector<int64_t> cap_override = {})
       : device(dev), max_seeds(max_seeds_), fanouts(std::move(fanouts_)), with_edge(with_edge_) {
     c10::cuda::CUDAGuard guard(device);
     TORCH_CHECK(fanouts.size() >= 1 && fanouts.size() <= 4, "1..4 hops supported by the arena");
@@ -277,14 +279,19 @@ struct SamplerArena {
     auto o32 = torch::TensorOptions().dtype(torch::kInt32).device(torch::kCUDA, device);
     int64_t rows = max_seeds;
     cap_nodes = max_seeds;
+    TORCH_CHECK(cap_override.empty() || cap_override.size() == fanouts.size() + 1,
+                "cap_override needs len(fanouts)+1 entries");
     for (size_t h = 0; h < fanouts.size(); ++h) {
       TORCH_CHECK(fanouts[h] > 0 && fanouts[h] <= 512, "arena fanouts must be in [1,512]");
+      if (!cap_override.empty()) rows = std::min(rows, std::max<int64_t>(cap_override[h], 1));
       cap_rows.push_back(rows);
       ell.push_back(torch::full({rows * fanouts[h]}, -1, o32));
       ell_eids.push_back(with_edge ? torch::full({rows * fanouts[h]}, -1, o64) : Tensor());
       rows = std::min<int64_t>(rows * fanouts[h], num_graph_nodes > 0 ? num_graph_nodes : INT64_MAX);
+      if (!cap_override.empty()) rows = std::min(rows, std::max<int64_t>(cap_override[h + 1], 1));
       cap_nodes += rows;
     }
+    cap_rows.push_back(rows);  // capacity of the nodes added by the last hop
     if (num_graph_nodes > 0) cap_nodes = std::min(cap_nodes, num_graph_nodes + max_seeds);
     TORCH_CHECK(cap_nodes < (1LL << 30), "sampler arena too large");
     table = std::make_unique<DeviceTable>(device, cap_nodes);
@@ -298,7 +305,7 @@ struct SamplerArena {
 
   BatchCounters bc() {
     int32_t* c = counters.data_ptr<int32_t>();
-    return BatchCounters{c, c + 6, table->cursor.data_ptr<int32_t>()};
+    return BatchCounters{c, c + 6, table->cursor.data_ptr<int32_t>(), c + 12};
   }
 
   void sample(GraphHandle& g, const Tensor& seeds, const c10::optional<Tensor>& n_dev, int64_t seed,
@@ -326,6 +333,7 @@ struct SamplerArena {
       a.k = fanouts[h];
       a.cap_rows = cap_rows[h];
       a.cap_nodes = cap_nodes;
+      a.cap_rows_next = cap_rows[h + 1];
       a.weighted = weighted;
       a.replace = replace;
       a.seed = seed;
@@ -737,7 +745,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def_readonly("cursor", &DeviceTable::cursor)
       .def_readonly("capacity", &DeviceTable::cap_nodes);
   py::class_<SamplerArena>(m, "SamplerArena")
-      .def(py::init<int, int64_t, std::vector<int64_t>, bool, int64_t>())
+      .def(py::init<int, int64_t, std::vector<int64_t>, bool, int64_t, std::vector<int64_t>>(), py::arg("device"),
+           py::arg("max_seeds"), py::arg("fanouts"), py::arg("with_edge"), py::arg("num_graph_nodes"),
+           py::arg("cap_override") = std::vector<int64_t>{})
       .def("sample", &SamplerArena::sample)
       .def("to_coo", &SamplerArena::to_coo)
       .def_readonly("nodes", &SamplerArena::nodes)

@@ -54,6 +54,7 @@ struct BatchCounters {
   int32_t* cum;     // [max_hops + 2]
   int32_t* edges;   // [max_hops]
   int32_t* cursor;  // running number of local nodes
+  int32_t* overflow;  // optional: neighbours dropped by the capacity guard (cumulative)
 };
 
 // ---- sampling.cu -----------------------------------------------------------
@@ -77,6 +78,7 @@ struct HopArgs {
   int k;                // fanout (>0)
   int cap_rows;         // worst-case frontier size
   int cap_nodes;        // node arena capacity (overflow guard)
+  int cap_rows_next;    // capacity of the next hop's frontier
   int weighted;         // 1: exponential-race weighted sampling
   int replace;          // 1: with replacement
   uint64_t seed;

@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(256) k_sample_hop(HopArgs a) {
       if (is_new) {
         const int id = id_base + __popc(nm & lanemask_lt());
         if (id < a.cap_nodes) { a.t.vals[slot] = id; a.nodes[id] = key; }
+        else a.t.vals[slot] = -1;  // arena overflow: the node is dropped (counted by the relabel pass)
       }
       if (valid && j < a.k) {
         const int64_t o = static_cast<int64_t>(r) * a.k + j;
@@ -166,12 +167,26 @@ __global__ void k_relabel_hop(HopArgs a) {
   const int f_begin = a.c.cum[a.hop];
   const int n_rows = min(a.c.cum[a.hop + 1] - f_begin, a.cap_rows);
   const int64_t n = static_cast<int64_t>(n_rows) * a.k;
+  // Capacity guard (arenas may be sized from calibration instead of the worst case): the
+  // next frontier holds at most cap_rows_next rows and the arena cap_nodes nodes.  Nodes past
+  // the bound are dropped: their slot is poisoned (-1) so later hops treat them as absent.
+  // Every thread derives the same bound from stable inputs; the cursor reset is idempotent.
+  const int bound = min(min(*a.c.cursor, a.cap_nodes), a.c.cum[a.hop + 1] + a.cap_rows_next);
+  int dropped = 0;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int32_t s = a.ell[i];
-    if (s >= 0) a.ell[i] = a.t.vals[s];
+    if (s >= 0) {
+      int32_t v = a.t.vals[s];
+      if (v >= bound) { a.t.vals[s] = -1; v = -1; ++dropped; }
+      a.ell[i] = v;
+    }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) a.c.cum[a.hop + 2] = min(*a.c.cursor, a.cap_nodes);
+  if (dropped && a.c.overflow) atomicAdd(a.c.overflow, dropped);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    a.c.cum[a.hop + 2] = bound;
+    *a.c.cursor = bound;
+  }
 }
 
 // Ordered (first-occurrence) seed insertion; single CTA, seeds are few.

@@ -101,7 +101,8 @@ class GraphSageEngine(object):
                fanouts: List[int] = (15, 10, 5), batch_size: int = 1024, hidden: int = 256,
                num_classes: int = 47, lr: float = 3e-3, weight_decay: float = 0.0, seed: int = 0,
                device: Optional[torch.device] = None, group=None, use_fused: bool = True,
-               use_cuda_graph: bool = True):
+               use_cuda_graph: bool = True, calibration_seeds: Optional[torch.Tensor] = None,
+               calibration_margin: float = 1.3, calibration_batches: int = 16):
     self.nat = require_native()
     self.graph = graph
     graph.lazy_init()
@@ -127,8 +128,12 @@ class GraphSageEngine(object):
 
     dev = self.device
     with torch.cuda.device(dev):
-      self.arena = self.nat.SamplerArena(dev.index, self.bs, self.fanouts, False, int(num_nodes))
-      self.cap_rows = list(self.arena.cap_rows)           # frontier capacity per hop
+      cap_override = []
+      if calibration_seeds is not None and calibration_seeds.numel() >= self.bs:
+        cap_override = self._calibrate(calibration_seeds, int(num_nodes), calibration_margin, calibration_batches)
+      self.arena = self.nat.SamplerArena(dev.index, self.bs, self.fanouts, False, int(num_nodes), cap_override)
+      self.calibrated = bool(cap_override)
+      self.cap_rows = list(self.arena.cap_rows)           # frontier capacity per hop (+ last-hop additions)
       # layer l (1-based) targets = nodes of hops 0..L-l
       self.cap_T = [0] + [int(sum(self.cap_rows[:self.L - l + 1])) for l in range(1, self.L + 1)]
       self.cap_T = [min(c, self.arena.cap_nodes) for c in self.cap_T]
@@ -159,6 +164,43 @@ class GraphSageEngine(object):
       self._repack()
     self._graph_fb = None
     self._graph_opt = None
+    self._graph_full = None
+
+  # ------------------------------------------------------------------ capacity calibration
+  def _calibrate(self, pool: torch.Tensor, num_nodes: int, margin: float, n_batches: int):
+    """Size the arena from observed frontier sizes instead of the worst case
+    bs*prod(fanouts): sample a few batches of the seed pool with a worst-case arena, take the
+    per-hop maxima (max over ranks), add a margin.  All buffers and every cap-proportional
+    launch (cuBLAS GEMMs, fills) shrink accordingly.  The kernels stay safe past the caps
+    (excess nodes are dropped and counted in `overflow_count()`)."""
+    dev = self.device
+    tmp = self.nat.SamplerArena(dev.index, self.bs, self.fanouts, False, num_nodes)
+    worst = list(tmp.cap_rows)
+    mx = torch.zeros(self.L + 1, dtype=torch.int64, device=dev)
+    g = torch.Generator(device='cpu')
+    g.manual_seed(self.seed + 991)
+    for i in range(n_batches):
+      idx = torch.randint(0, pool.numel(), (self.bs,), generator=g)
+      seeds = pool[idx].to(dev)
+      tmp.sample(self.gh, seeds.contiguous(), None, self.seed + 17, i * 8, False, False, False)
+      c = tmp.counters[:self.L + 2].to(torch.int64)
+      mx = torch.maximum(mx, c[1:] - c[:-1])
+    if self.world > 1:
+      import torch.distributed as dist
+      dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=self.group)
+    mx = mx.cpu().tolist()
+    caps = []
+    for h in range(self.L + 1):
+      c = int(mx[h] * margin) + 128
+      c = (c + 127) // 128 * 128
+      caps.append(min(c, worst[h]) if h > 0 else self.bs)
+    del tmp
+    torch.cuda.empty_cache()
+    return caps
+
+  def overflow_count(self) -> int:
+    """Neighbours dropped by the capacity guard since construction (0 in normal operation)."""
+    return int(self.arena.counters[12].item())
 
   # ------------------------------------------------------------------ parameters
   def _init_params(self):
@@ -332,12 +374,30 @@ class GraphSageEngine(object):
       self.load_state_dict(saved)
       if not self.use_cuda_graph:
         return
-      self._graph_fb = torch.cuda.CUDAGraph()
-      with torch.cuda.graph(self._graph_fb):
-        self._forward_backward_for_capture()
-      self._graph_opt = torch.cuda.CUDAGraph()
-      with torch.cuda.graph(self._graph_opt):
-        self._optimizer()
+      import os
+      capture_nccl = os.environ.get('GLT_B200_CAPTURE_NCCL', '1') != '0'
+      self._graph_full = None
+      if self.world == 1 or capture_nccl:
+        # one graph for the whole step; NCCL's all-reduce is captured as a graph node too
+        try:
+          g = torch.cuda.CUDAGraph()
+          with torch.cuda.graph(g):
+            self._forward_backward_for_capture()
+            self._allreduce()
+            self._optimizer()
+          self._graph_full = g
+          self._graph_fb = g
+        except Exception as e:  # pragma: no cover - depends on the NCCL build
+          import warnings
+          warnings.warn(f'single-graph capture failed ({e!r}); falling back to two graphs')
+          self._graph_full = None
+      if self._graph_full is None:
+        self._graph_fb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph_fb):
+          self._forward_backward_for_capture()
+        self._graph_opt = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph_opt):
+          self._optimizer()
       torch.cuda.synchronize()
       self.load_state_dict(saved)
 
@@ -355,7 +415,9 @@ class GraphSageEngine(object):
     if n < self.bs:
       self.seeds_dev.fill_(-1)
     self.seeds_dev[:n].copy_(seeds, non_blocking=True)
-    if self._graph_fb is not None:
+    if getattr(self, '_graph_full', None) is not None:
+      self._graph_full.replay()
+    elif self._graph_fb is not None:
       self._graph_fb.replay()
       self._allreduce()
       self._graph_opt.replay()
