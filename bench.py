@@ -49,6 +49,7 @@ def parse_args():
   p.add_argument('--no-fused', action='store_true')
   p.add_argument('--no-graph', action='store_true')
   p.add_argument('--no-calibrate', action='store_true', help='size the arena for the worst case')
+  p.add_argument('--no-pipeline', action='store_true', help='do not overlap sample(b+1) with train(b)')
   p.add_argument('--seed', type=int, default=0)
   p.add_argument('--profile-steps', type=int, default=0,
                  help='run this many eager steps between cudaProfilerStart/Stop (for ncu) and exit')
@@ -193,7 +194,8 @@ def build_ours(args, rank, world, device):
                         batch_size=args.batch, hidden=args.hidden, num_classes=args.classes,
                         lr=3e-3, seed=args.seed, device=device, use_fused=not args.no_fused,
                         use_cuda_graph=not args.no_graph,
-                        calibration_seeds=None if args.no_calibrate else pool)
+                        calibration_seeds=None if args.no_calibrate else pool,
+                        pipeline=not args.no_pipeline)
   eng._keep = keep
   return eng, pool
 
@@ -209,6 +211,7 @@ def run_ours(args):
   if args.profile_steps > 0:
     # ncu --profile-from-start off: only these eager steps are captured
     eng._graph_fb = eng._graph_opt = eng._graph_full = None
+    eng._graphs = []
     sd = pool[:bs].to(device)
     for _ in range(3):
       eng.train_step(sd)
@@ -283,7 +286,7 @@ def run_ours(args):
         'feat_dim': args.feat_dim, 'feat_dim_padded': eng.in_dim, 'classes': args.classes,
         'parallelism': f'dp{world}+graph/feature range-partition over {world} GPU(s), in-kernel P2P',
         'optimizer': 'Adam(fused)', 'fused_tcgen05_layer1': bool(eng.fused_ok[1]),
-        'cuda_graph': eng._graph_fb is not None,
+        'cuda_graph': eng._graph_fb is not None, 'pipelined_sample_train_overlap': bool(eng.pipeline),
         'l2_policy': 'inputs larger than L2 (feature table + CSR >> 126 MB, random rows per batch)',
         'baseline_ref': 'BASELINE.md GraphSAGE papers100M epoch 8.56 s / 1,207,179 seeds on 4xA100 (derived)',
         'last_batch_nodes': c[1:5], 'last_batch_edges': c[6:9], 'last_loss': last_loss,
@@ -298,7 +301,17 @@ def run_ours(args):
     }
     print(json.dumps(out), flush=True)
   if world > 1:
+    # orderly teardown, but never let a stuck NCCL/IPC teardown hold the box: every rank has
+    # reported, so after a final barrier a hard exit is safe
+    eng.close()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    watchdog = threading.Timer(20.0, lambda: os._exit(0))
+    watchdog.daemon = True
+    watchdog.start()
     dist.destroy_process_group()
+    watchdog.cancel()
 
 
 def run_reference(args):

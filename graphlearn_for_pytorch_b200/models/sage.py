@@ -102,8 +102,9 @@ class GraphSageEngine(object):
                num_classes: int = 47, lr: float = 3e-3, weight_decay: float = 0.0, seed: int = 0,
                device: Optional[torch.device] = None, group=None, use_fused: bool = True,
                use_cuda_graph: bool = True, calibration_seeds: Optional[torch.Tensor] = None,
-               calibration_margin: float = 1.3, calibration_batches: int = 16):
+               calibration_margin: float = 1.3, calibration_batches: int = 16, pipeline: bool = False):
     self.nat = require_native()
+    self.pipeline = bool(pipeline)
     self.graph = graph
     graph.lazy_init()
     self.gh = graph.graph_handler
@@ -131,7 +132,15 @@ class GraphSageEngine(object):
       cap_override = []
       if calibration_seeds is not None and calibration_seeds.numel() >= self.bs:
         cap_override = self._calibrate(calibration_seeds, int(num_nodes), calibration_margin, calibration_batches)
-      self.arena = self.nat.SamplerArena(dev.index, self.bs, self.fanouts, False, int(num_nodes), cap_override)
+      # pipelined mode double-buffers the sampler state: batch i+1 is sampled on a side stream
+      # while batch i trains (the reference's sampler<->trainer producer/consumer pipeline,
+      # distributed/dist_sampling_producer.py:54-163, collapsed onto CUDA streams of one GPU)
+      n_arenas = 2 if self.pipeline else 1
+      self._arenas = [self.nat.SamplerArena(dev.index, self.bs, self.fanouts, False, int(num_nodes), cap_override)
+                      for _ in range(n_arenas)]
+      self._cur = 0
+      for p_, ar_ in enumerate(self._arenas):
+        ar_.step.fill_(p_ - n_arenas)          # disjoint Philox stream ids per arena
       self.calibrated = bool(cap_override)
       self.cap_rows = list(self.arena.cap_rows)           # frontier capacity per hop (+ last-hop additions)
       # layer l (1-based) targets = nodes of hops 0..L-l
@@ -151,7 +160,9 @@ class GraphSageEngine(object):
                                 for l in range(2, self.L + 1)]
       self.dH = [None] + [torch.zeros(self.cap_T[l], self.dims_out[l - 1], dtype=f32, device=dev)
                           for l in range(1, self.L)]
-      self.seeds_dev = torch.zeros(self.bs, dtype=torch.int64, device=dev)
+      self._seeds = [torch.zeros(self.bs, dtype=torch.int64, device=dev) for _ in range(n_arenas)]
+      self._side = torch.cuda.Stream(device=dev) if self.pipeline else None
+      self._primed = False
       self.y = torch.zeros(self.bs, dtype=torch.int64, device=dev)
       self.loss = torch.zeros(1, dtype=f32, device=dev)
       self.correct = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -165,6 +176,14 @@ class GraphSageEngine(object):
     self._graph_fb = None
     self._graph_opt = None
     self._graph_full = None
+
+  @property
+  def arena(self):
+    return self._arenas[self._cur]
+
+  @property
+  def seeds_dev(self):
+    return self._seeds[self._cur]
 
   # ------------------------------------------------------------------ capacity calibration
   def _calibrate(self, pool: torch.Tensor, num_nodes: int, margin: float, n_batches: int):
@@ -200,7 +219,7 @@ class GraphSageEngine(object):
 
   def overflow_count(self) -> int:
     """Neighbours dropped by the capacity guard since construction (0 in normal operation)."""
-    return int(self.arena.counters[12].item())
+    return int(sum(int(a.counters[12].item()) for a in self._arenas))
 
   # ------------------------------------------------------------------ parameters
   def _init_params(self):
@@ -245,14 +264,17 @@ class GraphSageEngine(object):
 
   def state_dict(self):
     return {'p32': self.p32.clone(), 'm': self.m.clone(), 'v': self.v.clone(),
-            'step': int(self.step_dev.item()), 'sample_step': int(self.arena.step.item()),
+            'step': int(self.step_dev.item()), 'sample_step': [int(a.step.item()) for a in self._arenas],
             'step_idx': self.step_idx, 'seed': self.seed}
 
   def load_state_dict(self, s):
     self.p32.copy_(s['p32']); self.m.copy_(s['m']); self.v.copy_(s['v'])
     self.p16.copy_(self.p32)
     self.step_dev.fill_(s['step'])
-    self.arena.step.fill_(s.get('sample_step', 0))
+    ss = s.get('sample_step', None)
+    if ss is not None:
+      for a, v in zip(self._arenas, ss if isinstance(ss, (list, tuple)) else [ss]):
+        a.step.fill_(v)
     self.step_idx, self.seed = s['step_idx'], s['seed']
     self._repack()
 
@@ -267,11 +289,13 @@ class GraphSageEngine(object):
     nh = self.L - l + 1
     return list(self.arena.ell[:nh]), self.fanouts[:nh], nh
 
-  def _sample(self):
+  def _sample(self, which: Optional[int] = None):
     # the Philox stream advances from a device-side step counter (arena.step) so that a
     # CUDA-graph replay draws fresh samples every step
-    self.arena.step.add_(1)
-    self.arena.sample(self.gh, self.seeds_dev, None, self.seed, 0, False, False, True)
+    which = self._cur if which is None else which
+    ar = self._arenas[which]
+    ar.step.add_(len(self._arenas))
+    ar.sample(self.gh, self._seeds[which], None, self.seed, 0, False, False, True)
     self._k(2 + 2 * self.L)  # memset + init_seeds + (sample, relabel) per hop
 
   def _forward(self):
@@ -350,85 +374,144 @@ class GraphSageEngine(object):
       import torch.distributed as dist
       dist.all_reduce(self.g32, group=self.group)
 
-  def _step_eager(self):
-    self._sample()
+  def _pipelined_body(self, cur: int):
+    """train(batch in arena[cur])  ||  sample(next batch into arena[1-cur])."""
+    self._cur = cur
+    main = torch.cuda.current_stream()
+    self._side.wait_stream(main)                       # fork
+    with torch.cuda.stream(self._side):
+      self._sample(1 - cur)
     self._forward()
     self._backward()
+    main.wait_stream(self._side)                        # join
+
+  def _step_eager(self):
+    if self.pipeline:
+      self._pipelined_body(self._cur)
+    else:
+      self._sample()
+      self._forward()
+      self._backward()
     self._allreduce()
     self._optimizer()
 
   # ------------------------------------------------------------------ public API
   def warmup_and_capture(self, n_eager: int = 2):
-    """Run a few eager steps (lazy inits, cuBLAS workspaces), then capture the CUDA graphs."""
+    """Run a few eager steps (lazy inits, cuBLAS workspaces), then capture the CUDA graphs.
+    Pipelined engines capture one graph per buffer parity."""
+    import os
     with torch.cuda.device(self.device):
       saved = self.state_dict()
       side = torch.cuda.Stream()
       side.wait_stream(torch.cuda.current_stream())
       with torch.cuda.stream(side):
+        if self.pipeline:
+          self._sample(0)
         for _ in range(n_eager):
           self._tally = 0
           self._step_eager()
           self.kernels_per_step = self._tally
+          if self.pipeline:
+            self._cur ^= 1
       torch.cuda.current_stream().wait_stream(side)
       torch.cuda.synchronize()
       self.load_state_dict(saved)
+      self._cur, self._primed = 0, False
+      self._graphs = []
       if not self.use_cuda_graph:
         return
-      import os
-      capture_nccl = os.environ.get('GLT_B200_CAPTURE_NCCL', '1') != '0'
-      self._graph_full = None
-      if self.world == 1 or capture_nccl:
-        # one graph for the whole step; NCCL's all-reduce is captured as a graph node too
-        try:
-          g = torch.cuda.CUDAGraph()
-          with torch.cuda.graph(g):
-            self._forward_backward_for_capture()
+      # capturing NCCL collectives works but makes process-group teardown hang on this stack
+      # (measured: bench exit blocked until the timeout), so it is opt-in for world > 1
+      single = self.world == 1 or os.environ.get('GLT_B200_CAPTURE_NCCL', '0') == '1'
+      g_opt = None
+      for parity in range(2 if self.pipeline else 1):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+          if self.pipeline:
+            self._pipelined_body(parity)
+          else:
+            self._sample()
+            self._forward()
+            self._backward()
+          if single:
             self._allreduce()
             self._optimizer()
-          self._graph_full = g
-          self._graph_fb = g
-        except Exception as e:  # pragma: no cover - depends on the NCCL build
-          import warnings
-          warnings.warn(f'single-graph capture failed ({e!r}); falling back to two graphs')
-          self._graph_full = None
-      if self._graph_full is None:
-        self._graph_fb = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph_fb):
-          self._forward_backward_for_capture()
-        self._graph_opt = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph_opt):
-          self._optimizer()
+        if not single and g_opt is None:
+          g_opt = torch.cuda.CUDAGraph()
+          with torch.cuda.graph(g_opt):
+            self._optimizer()
+        self._graphs.append((g, None if single else g_opt))
       torch.cuda.synchronize()
       self.load_state_dict(saved)
+      self._cur, self._primed = 0, False
+      self._graph_fb = self._graphs[0][0]
 
-  def _forward_backward_for_capture(self):
-    self._sample()
-    self._forward()
-    self._backward()
+  def close(self):
+    """Drop the captured graphs (call before destroying the process group)."""
+    torch.cuda.synchronize(self.device)
+    self._graphs = []
+    self._graph_full = self._graph_fb = self._graph_opt = None
 
-  def train_step(self, seeds: torch.Tensor) -> torch.Tensor:
-    """One training step on a batch of seed node ids.  `seeds` may be a (pinned) host
-    tensor -- it is copied H2D asynchronously -- or a device tensor.  Returns the device
-    scalar holding the mean NLL loss of the batch (read it with .item() / a D2H copy)."""
+  def _run_captured_or_eager(self, parity: int):
+    if getattr(self, '_graphs', None):
+      g, g_opt = self._graphs[parity]
+      g.replay()
+      if g_opt is not None:
+        self._allreduce()
+        g_opt.replay()
+    else:
+      self._cur = parity
+      self._step_eager()
+
+  def _stage_seeds(self, buf: torch.Tensor, seeds: torch.Tensor):
     n = seeds.numel()
     assert n <= self.bs
     if n < self.bs:
-      self.seeds_dev.fill_(-1)
-    self.seeds_dev[:n].copy_(seeds, non_blocking=True)
-    if getattr(self, '_graph_full', None) is not None:
-      self._graph_full.replay()
-    elif self._graph_fb is not None:
-      self._graph_fb.replay()
-      self._allreduce()
-      self._graph_opt.replay()
-    else:
-      self._step_eager()
+      buf.fill_(-1)
+    buf[:n].copy_(seeds, non_blocking=True)
+
+  def train_step(self, seeds: torch.Tensor) -> Optional[torch.Tensor]:
+    """One training step on a batch of seed node ids.  `seeds` may be a (pinned) host
+    tensor -- it is copied H2D asynchronously -- or a device tensor.  Returns the device
+    scalar holding the mean NLL loss (read it with .item() / a D2H copy).
+
+    Pipelined engines run *sample(this batch) || train(previous batch)*: the first call only
+    samples (returns None), later calls return the loss of the batch passed one call earlier;
+    `flush()` trains the last pending batch."""
+    if not self.pipeline:
+      self._stage_seeds(self._seeds[0], seeds)
+      self._run_captured_or_eager(0)
+      self.step_idx += 1
+      return self.loss
+    if not self._primed:
+      self._cur = 0
+      self._stage_seeds(self._seeds[0], seeds)
+      self._sample(0)
+      self._primed = True
+      return None
+    cur = self._cur
+    self._stage_seeds(self._seeds[1 - cur], seeds)
+    self._run_captured_or_eager(cur)
+    self._cur = 1 - cur
+    self.step_idx += 1
+    return self.loss
+
+  def flush(self) -> Optional[torch.Tensor]:
+    """Pipelined mode: train the batch that was sampled by the last train_step() call."""
+    if not self.pipeline or not self._primed:
+      return None
+    self._forward()
+    self._backward()
+    self._allreduce()
+    self._optimizer()
+    self._primed = False
     self.step_idx += 1
     return self.loss
 
   @torch.no_grad()
   def evaluate_batch(self, seeds: torch.Tensor):
     """(loss, #correct, #seeds) for a batch without updating parameters."""
+    assert not (self.pipeline and self._primed), 'call flush() before evaluate_batch()'
     n = seeds.numel()
     self.seeds_dev.fill_(-1)
     self.seeds_dev[:n].copy_(seeds)

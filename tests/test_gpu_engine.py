@@ -174,3 +174,28 @@ def test_graph_replay_resamples(native):
   eng.train_step(seeds); a = eng.arena.nodes[:eng.arena.counters[3].item()].clone()
   eng.train_step(seeds); b = eng.arena.nodes[:eng.arena.counters[3].item()].clone()
   assert a.numel() != b.numel() or not torch.equal(a.sort().values, b.sort().values)
+
+
+def test_pipelined_engine_matches_sequential_semantics(native):
+  """sample(b+1) || train(b): same learning behaviour, loss lags one call, flush trains the tail."""
+  torch.manual_seed(0)
+  ei, topo = rmat_csr(8000, 100000, seed=3)
+  g = glt.data.Graph(topo, 'CUDA', 0)
+  feats = torch.randn(8000, 128, device=DEV).to(torch.bfloat16)
+  w = torch.randn(128, 8, device=DEV)
+  labels = (feats.float() @ w).argmax(1)
+  ut = glt.data.UnifiedTensor(0, torch.bfloat16); ut.append_shared_tensor(feats)
+  for use_graph in (False, True):
+    eng = GraphSageEngine(g, ut._table(), labels, in_dim=128, num_nodes=8000, fanouts=[4, 3], batch_size=512,
+                          hidden=256, num_classes=8, device=DEV, use_cuda_graph=use_graph, seed=5, pipeline=True)
+    eng.warmup_and_capture(n_eager=1)
+    assert eng.train_step(torch.randperm(8000, device=DEV)[:512]) is None      # priming call
+    losses = []
+    for i in range(60):
+      losses.append(float(eng.train_step(torch.randperm(8000, device=DEV)[:512]).item()))
+    tail = eng.flush()
+    assert tail is not None and eng.flush() is None
+    assert losses[-1] < 0.6 * losses[0], (losses[0], losses[-1])
+    assert eng.overflow_count() == 0
+    loss, correct, n = eng.evaluate_batch(torch.randperm(8000, device=DEV)[:512])
+    assert n == 512 and correct / n > 0.5
