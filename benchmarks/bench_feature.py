@@ -1,0 +1,42 @@
+"""Feature-lookup bandwidth (GB/s = numel*bytes / time / 2^30), device-timed.
+
+Counterpart of the reference's benchmarks/api/bench_feature.py:27-61 (`split_ratio` of the rows in
+HBM, the rest in pinned host memory).  Sweeps the split ratio and the row dtype.
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import graphlearn_for_pytorch_b200 as glt  # noqa: E402
+
+p = argparse.ArgumentParser()
+p.add_argument('--rows', type=int, default=2_449_029)
+p.add_argument('--dim', type=int, default=128)
+p.add_argument('--ids', type=int, default=400_000, help='rows gathered per lookup (~unique nodes of one batch)')
+p.add_argument('--iters', type=int, default=50)
+args = p.parse_args()
+dev = torch.device('cuda', 0)
+results = []
+for dtype in (torch.float32, torch.bfloat16):
+  full = torch.randn(args.rows, args.dim).to(dtype)
+  for ratio in (1.0, 0.2, 0.0):
+    feat = glt.data.Feature(full, split_ratio=ratio, device=0, dtype=dtype)
+    ids = [torch.randint(0, args.rows, (args.ids,), device=dev) for _ in range(args.iters + 3)]
+    for i in ids[:3]:
+      feat[i]
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in ids[3:]:
+      out = feat[i]
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.iters
+    gbs = out.numel() * out.element_size() / (ms / 1e3) / 2 ** 30
+    results.append({'dtype': str(dtype), 'split_ratio': ratio, 'ms': ms, 'GB_per_s': gbs})
+    del feat
+print(json.dumps({'metric': 'feature lookup GB/s', 'rows_per_lookup': args.ids, 'dim': args.dim,
+                  'results': results, 'reference_published_A100_GB_per_s_derived': 11.1}))

@@ -1,0 +1,75 @@
+"""GraphSAGE on an ogbn-products-shaped graph, single GPU (or CPU).
+
+Counterpart of the reference's examples/train_sage_ogbn_products.py and
+train_sage_prod_with_trim.py.  Two paths:
+  --mode loader   PyG-style: NeighborLoader -> eager GraphSAGE with per-layer trimming
+  --mode engine   fused CUDA-graph engine (tcgen05 layer 1, hand-written backward)
+"""
+import argparse
+import time
+
+import torch
+import torch.nn.functional as F
+
+from common import glt, synthetic_homo
+from graphlearn_for_pytorch_b200.models import GraphSAGE, GraphSageEngine
+
+p = argparse.ArgumentParser()
+p.add_argument('--mode', default='loader', choices=['loader', 'engine'])
+p.add_argument('--nodes', type=int, default=100_000)
+p.add_argument('--edges', type=int, default=2_000_000)
+p.add_argument('--epochs', type=int, default=2)
+p.add_argument('--batch', type=int, default=1024)
+p.add_argument('--split-ratio', type=float, default=0.2, help='fraction of (hot) feature rows kept in HBM')
+args = p.parse_args()
+
+cuda = torch.cuda.is_available()
+device = torch.device('cuda', 0) if cuda else torch.device('cpu')
+ei, x, y = synthetic_homo(args.nodes, args.edges)     # <- replace with the real ogbn-products tensors
+n_cls = int(y.max()) + 1
+train_idx = torch.randperm(args.nodes)[: args.nodes // 10]
+
+if args.mode == 'loader':
+  ds = glt.data.Dataset()
+  ds.init_graph(ei, graph_mode='CUDA' if cuda else 'CPU', directed=False)
+  ds.init_node_features(x, sort_func=glt.data.sort_by_in_degree, split_ratio=args.split_ratio, with_gpu=cuda)
+  ds.init_node_labels(y)
+  loader = glt.loader.NeighborLoader(ds, [15, 10, 5], train_idx, batch_size=args.batch, shuffle=True,
+                                     drop_last=True, device=device)
+  model = GraphSAGE(x.shape[1], 256, n_cls, num_layers=3).to(device)
+  opt = torch.optim.Adam(model.parameters(), lr=3e-3)
+  for epoch in range(args.epochs):
+    t0, tot, correct, seen = time.time(), 0.0, 0, 0
+    for b in loader:
+      out = model(b.x, b.edge_index, b.num_sampled_nodes, b.num_sampled_edges)[:b.batch_size]
+      tgt = b.y[:b.batch_size].to(device)
+      loss = F.cross_entropy(out, tgt)
+      opt.zero_grad(); loss.backward(); opt.step()
+      tot += float(loss); correct += int((out.argmax(1) == tgt).sum()); seen += b.batch_size
+    print(f'epoch {epoch}: loss {tot / len(loader):.4f} acc {correct / seen:.4f} time {time.time() - t0:.2f}s')
+else:
+  assert cuda, 'the engine needs a GPU'
+  in_dim = (x.shape[1] + 63) // 64 * 64
+  feats = torch.zeros(args.nodes, in_dim, dtype=torch.bfloat16, device=device)
+  feats[:, :x.shape[1]] = x.to(device).to(torch.bfloat16)
+  topo = glt.data.Topology(ei.to(device), layout='CSR', num_nodes=args.nodes)
+  graph = glt.data.Graph(topo, 'CUDA', 0)
+  ut = glt.data.UnifiedTensor(0, torch.bfloat16); ut.append_shared_tensor(feats)
+  eng = GraphSageEngine(graph, ut._table(), y.to(device), in_dim=in_dim, num_nodes=args.nodes, fanouts=[15, 10, 5],
+                        batch_size=args.batch, hidden=256, num_classes=n_cls, device=device,
+                        calibration_seeds=train_idx, pipeline=True)
+  eng.warmup_and_capture()
+  pinned = train_idx.pin_memory()
+  for epoch in range(args.epochs):
+    t0 = time.time()
+    perm = torch.randperm(train_idx.numel())
+    losses = []
+    for i in range(0, perm.numel() - args.batch + 1, args.batch):
+      loss = eng.train_step(pinned[perm[i:i + args.batch]])
+      if loss is not None and (i // args.batch) % 20 == 0:
+        losses.append(float(loss.item()))
+    eng.flush()
+    torch.cuda.synchronize()
+    l, c, n = eng.evaluate_batch(train_idx[:args.batch].to(device))
+    print(f'epoch {epoch}: loss {sum(losses) / max(len(losses), 1):.4f} eval-acc {c / n:.4f} '
+          f'time {time.time() - t0:.2f}s ({perm.numel() / (time.time() - t0):.0f} seeds/s)')

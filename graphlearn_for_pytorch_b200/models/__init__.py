@@ -1,1 +1,3 @@
 from .sage import SAGEConv, GraphSAGE, GraphSageEngine
+from .rgnn import RGNN, RelSAGEConv, RelGCNConv, RelGATConv
+from .seal import drnl_node_labeling, DGCNN

@@ -1,0 +1,69 @@
+import torch
+
+import graphlearn_for_pytorch_b200 as glt
+from graphlearn_for_pytorch_b200.loader import NeighborLoader
+from graphlearn_for_pytorch_b200.models import DGCNN, RGNN, GraphSAGE, drnl_node_labeling
+from helpers import ring_dataset
+
+
+def test_graphsage_eager_trains_on_loader_batches():
+  torch.manual_seed(0)
+  ds = ring_dataset(40, dim=8)
+  ds.init_node_labels((torch.arange(40) >= 20).long())
+  loader = NeighborLoader(ds, [2, 2], torch.arange(40), batch_size=20, shuffle=True, seed=1)
+  model = GraphSAGE(8, 16, 2, num_layers=2)
+  opt = torch.optim.Adam(model.parameters(), lr=0.01)
+  first = last = None
+  for epoch in range(30):
+    for b in loader:
+      x = b.x / 40.0
+      out = model(x, b.edge_index, b.num_sampled_nodes, b.num_sampled_edges)
+      assert out.shape[0] == b.batch_size
+      loss = torch.nn.functional.cross_entropy(out, b.y[:b.batch_size])
+      opt.zero_grad(); loss.backward(); opt.step()
+      first = first if first is not None else loss.item()
+      last = loss.item()
+  assert last < first
+
+
+def test_trimmed_equals_untrimmed_for_seeds():
+  ds = ring_dataset(40, dim=8)
+  loader = NeighborLoader(ds, [2, 2], torch.arange(8), batch_size=8)
+  b = next(iter(loader))
+  model = GraphSAGE(8, 16, 3, num_layers=2).eval()
+  full = model(b.x, b.edge_index)[:b.batch_size]
+  trimmed = model(b.x, b.edge_index, b.num_sampled_nodes, b.num_sampled_edges)
+  assert torch.allclose(full, trimmed, atol=1e-5)
+
+
+def test_rgnn_variants_on_hetero_batches():
+  u2i = torch.tensor([[0, 0, 1, 2, 3, 3], [0, 1, 1, 2, 3, 0]])
+  i2i = torch.tensor([[0, 1, 2, 3], [1, 2, 3, 0]])
+  ds = glt.data.Dataset(edge_dir='out')
+  ds.init_graph({('user', 'u2i', 'item'): u2i, ('item', 'i2i', 'item'): i2i}, graph_mode='CPU')
+  ds.init_node_features({'user': torch.randn(4, 8), 'item': torch.randn(4, 8)}, with_gpu=False)
+  ds.init_node_labels({'user': torch.tensor([0, 1, 0, 1])})
+  loader = NeighborLoader(ds, [2, 2], ('user', torch.arange(4)), batch_size=4)
+  b = next(iter(loader))
+  etypes = list(b.edge_index_dict.keys())
+  for kind in ('rsage', 'rgcn', 'rgat'):
+    model = RGNN(etypes, 8, 16, 2, num_layers=2, node_type='user', model=kind)
+    out = model(b.x_dict, b.edge_index_dict)
+    assert out.shape == (b['user'].node.numel(), 2)
+    out.sum().backward()
+    out_t = model(b.x_dict, b.edge_index_dict, b.num_sampled_nodes, b.num_sampled_edges)
+    assert out_t.shape[1] == 2 and out_t.shape[0] >= b['user'].batch_size
+
+
+def test_drnl_and_dgcnn():
+  # path 0-1-2-3, link (0, 3)
+  ei = torch.tensor([[0, 1, 2], [1, 2, 3]])
+  z = drnl_node_labeling(ei, 0, 3, 4)
+  assert z[0] == 1 and z[3] == 1 and z[1] == z[2] and z[1] > 1
+  model = DGCNN(num_labels=50, hidden=8, num_layers=2, k=10)
+  zz = torch.cat([z, z])
+  e2 = torch.cat([ei, ei + 4], 1)
+  batch = torch.tensor([0, 0, 0, 0, 1, 1, 1, 1])
+  out = model(zz, e2, batch, 2)
+  assert out.shape == (2,)
+  out.sum().backward()
