@@ -500,11 +500,12 @@ static void sage_scatter_bwd(const Tensor& dA, int64_t d, const Tensor& counters
 }
 
 static void relu_bwd_cast(const Tensor& dH, const Tensor& Z, const Tensor& counters, int64_t n_hops,
-                          Tensor dPre) {
+                          Tensor dPre, const c10::optional<Tensor>& colsum) {
   c10::cuda::CUDAGuard guard(dH.device());
   TORCH_CHECK(dPre.size(0) <= dH.size(0) && dPre.size(0) <= Z.size(0) && dPre.size(1) % 8 == 0);
   launch_relu_bwd_cast(dH.data_ptr<float>(), Z.data_ptr(), counters.data_ptr<int32_t>(), n_hops,
-                       dPre.size(0), dPre.size(1), dPre.data_ptr(), cur_stream());
+                       dPre.size(0), dPre.size(1), dPre.data_ptr(),
+                       (colsum.has_value() && colsum->defined()) ? colsum->data_ptr<float>() : nullptr, cur_stream());
   check_cuda_err("relu_bwd_cast");
 }
 
@@ -520,7 +521,7 @@ static void bias_relu(Tensor Z, const Tensor& bias, const Tensor& counters, int6
 static void softmax_nll(const Tensor& logits, int64_t C, const c10::optional<Tensor>& y,
                         const c10::optional<Tensor>& labels_all, const c10::optional<Tensor>& nodes,
                         const Tensor& counters, Tensor loss, Tensor dlogits,
-                        const c10::optional<Tensor>& correct) {
+                        const c10::optional<Tensor>& correct, const c10::optional<Tensor>& colsum) {
   c10::cuda::CUDAGuard guard(logits.device());
   TORCH_CHECK(logits.scalar_type() == torch::kBFloat16 && logits.is_contiguous());
   TORCH_CHECK(dlogits.sizes() == logits.sizes() && dlogits.is_contiguous());
@@ -532,6 +533,7 @@ static void softmax_nll(const Tensor& logits, int64_t C, const c10::optional<Ten
                      counters.data_ptr<int32_t>(), logits.size(0), loss.data_ptr<float>(),
                      dlogits.data_ptr(),
                      (correct.has_value() && correct->defined()) ? correct->data_ptr<int32_t>() : nullptr,
+                     (colsum.has_value() && colsum->defined()) ? colsum->data_ptr<float>() : nullptr,
                      cur_stream());
   check_cuda_err("softmax_nll");
 }
@@ -664,6 +666,57 @@ struct PeerBuffer : public std::enable_shared_from_this<PeerBuffer> {
   }
 };
 
+// PeerGroup: the per-rank view of all ranks' gradient buffers + barrier flags.
+struct PeerGroup {
+  PeerPtrs p{};
+  std::vector<Tensor> keep;
+  Tensor epoch, err;
+  int device;
+
+  PeerGroup(int dev, int rank, std::vector<Tensor> grads, std::vector<Tensor> flags) : device(dev) {
+    c10::cuda::CUDAGuard guard(dev);
+    TORCH_CHECK(grads.size() == flags.size() && grads.size() <= kMaxParts);
+    p.world = grads.size();
+    p.rank = rank;
+    for (size_t r = 0; r < grads.size(); ++r) {
+      TORCH_CHECK(grads[r].scalar_type() == torch::kFloat32 && flags[r].scalar_type() == torch::kInt32);
+      TORCH_CHECK(flags[r].numel() >= 2 * p.world);
+      p.g[r] = grads[r].data_ptr<float>();
+      p.flags[r] = flags[r].data_ptr<int32_t>();
+      keep.push_back(grads[r]);
+      keep.push_back(flags[r]);
+    }
+    auto o32 = torch::TensorOptions().dtype(torch::kInt32).device(torch::kCUDA, dev);
+    epoch = torch::zeros({2}, o32);
+    err = torch::zeros({1}, o32);
+  }
+
+  void barrier(int64_t which) {
+    c10::cuda::CUDAGuard guard(device);
+    launch_peer_barrier(p, which, epoch.data_ptr<int32_t>(), err.data_ptr<int32_t>(), cur_stream());
+    check_cuda_err("peer_barrier");
+  }
+
+  void adam(Tensor param, Tensor m, Tensor v, const c10::optional<Tensor>& p_bf16, double lr, double b1, double b2,
+            double eps, double wd, const Tensor& step_dev, double gscale) {
+    c10::cuda::CUDAGuard guard(device);
+    TORCH_CHECK(param.numel() % 4 == 0, "flat parameter buffer must be padded to a multiple of 4");
+    launch_adam_peer(p, param.data_ptr<float>(), m.data_ptr<float>(), v.data_ptr<float>(),
+                     (p_bf16.has_value() && p_bf16->defined()) ? p_bf16->data_ptr() : nullptr, param.numel(), lr,
+                     b1, b2, eps, wd, step_dev.data_ptr<int32_t>(), gscale, cur_stream());
+    check_cuda_err("adam_peer");
+  }
+};
+
+static void multimem_copy(const Tensor& src, int64_t mc_ptr, int64_t dst_byte_offset) {
+  c10::cuda::CUDAGuard guard(src.device());
+  TORCH_CHECK(src.is_cuda() && src.is_contiguous());
+  const int64_t nbytes = src.numel() * src.element_size();
+  TORCH_CHECK(nbytes % 16 == 0 && dst_byte_offset % 16 == 0 && mc_ptr != 0);
+  launch_multimem_copy(src.data_ptr(), reinterpret_cast<void*>(mc_ptr + dst_byte_offset), nbytes, cur_stream());
+  check_cuda_err("multimem_copy");
+}
+
 static Tensor pack_weight(const Tensor& w) {
   c10::cuda::CUDAGuard guard(w.device());
   TORCH_CHECK(w.scalar_type() == torch::kBFloat16 && w.is_contiguous() && w.dim() == 2);
@@ -789,7 +842,14 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def_readonly("bytes", &PeerBuffer::bytes)
       .def_readonly("device", &PeerBuffer::device)
       .def_readonly("imported", &PeerBuffer::imported);
+  py::class_<PeerGroup>(m, "PeerGroup")
+      .def(py::init<int, int, std::vector<Tensor>, std::vector<Tensor>>())
+      .def("barrier", &PeerGroup::barrier)
+      .def("adam", &PeerGroup::adam)
+      .def_readonly("err", &PeerGroup::err)
+      .def_readonly("epoch", &PeerGroup::epoch);
   m.def("enable_peer_access", &enable_peer_access);
+  m.def("multimem_copy", &multimem_copy);
   m.def("pack_weight", &pack_weight);
   m.def("pack_weight_into", &pack_weight_into);
 }

@@ -127,6 +127,28 @@ void launch_gather_rows(RowTable t, const int64_t* idx, const int64_t* id2index,
     k_gather_scalar<uint8_t><<<g, 256, 0, s>>>(t, idx, id2index, n, n_dev, o, out_row_bytes);
 }
 
+// NVSwitch multicast store: one write lands in the replica of every GPU bound to the
+// multicast object (hot-cache fill).  `mc_dst` is a multicast virtual address.
+__global__ void k_multimem_copy(const uint4* __restrict__ src, uint4* mc_dst, int64_t n16) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n16;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const uint4 v = src[i];
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_dst + i),
+                 "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)),
+                 "f"(__uint_as_float(v.w))
+                 : "memory");
+  }
+}
+
+void launch_multimem_copy(const void* src, void* mc_dst, int64_t nbytes, cudaStream_t s) {
+  const int64_t n16 = nbytes / 16;
+  if (n16 <= 0) return;
+  int64_t blocks = (n16 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_multimem_copy<<<static_cast<int>(blocks), 256, 0, s>>>(reinterpret_cast<const uint4*>(src),
+                                                           reinterpret_cast<uint4*>(mc_dst), n16);
+}
+
 void launch_gather_i64(RowTable t, const int64_t* idx, int64_t n, const int32_t* n_dev,
                        int64_t* out, cudaStream_t s) {
   if (n <= 0) return;

@@ -130,6 +130,8 @@ void launch_gather_rows(RowTable t, const int64_t* idx, const int64_t* id2index,
                         const int32_t* n_dev, void* out, int64_t out_row_bytes, cudaStream_t s);
 void launch_gather_i64(RowTable t, const int64_t* idx, int64_t n, const int32_t* n_dev,
                        int64_t* out, cudaStream_t s);
+// copy `nbytes` (multiple of 16) from local memory to an NVSwitch multicast address
+void launch_multimem_copy(const void* src, void* mc_dst, int64_t nbytes, cudaStream_t s);
 
 // ---- sage.cu (GraphSAGE engine kernels) ---------------------------------------
 struct SageAggArgs {
@@ -164,8 +166,9 @@ struct SageScatterArgs {
 void launch_sage_scatter_bwd(const SageScatterArgs& a, cudaStream_t s);
 
 // dPre = (Z > 0) ? bf16(dH) : 0 for rows < cum[n_hops]; 0 beyond.
+// colsum (optional, fp32 [d]): fused bias gradient = column sums of dPre.
 void launch_relu_bwd_cast(const float* dH, const void* Z, const int32_t* cum, int n_hops, int cap,
-                          int d, void* dPre, cudaStream_t s);
+                          int d, void* dPre, float* colsum, cudaStream_t s);
 // bias + relu epilogue over valid rows (zero beyond): Z = relu(Z + b)
 void launch_bias_relu(void* Z, const void* bias, const int32_t* cum, int n_hops, int cap, int d,
                       int relu, cudaStream_t s);
@@ -173,7 +176,7 @@ void launch_bias_relu(void* Z, const void* bias, const int32_t* cum, int n_hops,
 // labels come from y[r], or (labels_all != nullptr) from labels_all[nodes[r]].
 void launch_softmax_nll(const void* logits, int ld, int C, const int64_t* y, const int64_t* labels_all,
                         const int64_t* nodes, const int32_t* cum, int cap, float* loss, void* dlogits,
-                        int32_t* correct, cudaStream_t s);
+                        int32_t* correct, float* colsum, cudaStream_t s);
 // out[c] = sum over valid rows of X[:, c]  (d multiple of 8, d <= 2048)
 void launch_colsum_bf16(const void* X, const int32_t* cum, int n_hops, int cap, int d, float* out,
                         cudaStream_t s);
@@ -183,6 +186,17 @@ void launch_adam(float* p, const float* g, float* m, float* v, void* p_bf16, int
                  float b1, float b2, float eps, float wd, const int32_t* step_dev, float gscale,
                  cudaStream_t s);
 void launch_bf16_to_f32(const void* src, float* dst, int64_t n, cudaStream_t s);
+
+// ---- peer.cu (collectives over NVLink peer memory, CUDA-graph capturable) ------
+struct PeerPtrs {
+  int world, rank;
+  const float* g[kMaxParts];   // gradient buffer of every rank, mapped on this device
+  int32_t* flags[kMaxParts];   // barrier flag array [2 * world] of every rank, mapped on this device
+};
+void launch_peer_barrier(const PeerPtrs& p, int which, int32_t* epoch_dev, int32_t* err, cudaStream_t s);
+void launch_adam_peer(const PeerPtrs& p, float* param, float* m, float* v, void* p_bf16, int64_t n, float lr,
+                      float b1, float b2, float eps, float wd, const int32_t* step_dev, float gscale,
+                      cudaStream_t s);
 
 // ---- sage_tc.cu (tcgen05 fused gather+aggregate+GEMM) -------------------------
 struct SageFusedArgs {

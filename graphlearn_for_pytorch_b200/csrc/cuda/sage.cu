@@ -135,10 +135,17 @@ __global__ void __launch_bounds__(256) k_sage_scatter_bwd(SageScatterArgs a) {
   }
 }
 
-__global__ void k_relu_bwd_cast(const float* dH, const __nv_bfloat16* Z, const int32_t* cum,
-                                int n_hops, int cap, int d, __nv_bfloat16* dPre) {
+__global__ void __launch_bounds__(256) k_relu_bwd_cast(const float* dH, const __nv_bfloat16* Z, const int32_t* cum,
+                                                       int n_hops, int cap, int d, __nv_bfloat16* dPre,
+                                                       float* colsum) {
+  // colsum != nullptr: also accumulate the bias gradient (column sums of dPre).  Requires
+  // d | 2048 so that a thread keeps the same 8 columns across grid-stride iterations.
+  __shared__ float s_acc[256][8];
   const int T = min(cum[n_hops], cap);
   const int64_t n8 = static_cast<int64_t>(cap) * d / 8;
+  float acc[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) acc[q] = 0.f;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n8;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int64_t e = i * 8;
@@ -155,8 +162,26 @@ __global__ void k_relu_bwd_cast(const float* dH, const __nv_bfloat16* Z, const i
 #pragma unroll
       for (int q = 0; q < 8; ++q) g[q] = z[q] > 0.f ? g[q] : 0.f;
       o = pack_bf16x8(g, 1.f);
+      if (colsum) {
+        float r[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) r[q] = 0.f;
+        bf16x8_accum(o, r);  // sum exactly what the GEMMs will see (bf16-rounded)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] += r[q];
+      }
     }
     *reinterpret_cast<uint4*>(dPre + e) = o;
+  }
+  if (colsum == nullptr) return;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) s_acc[threadIdx.x][q] = acc[q];
+  __syncthreads();
+  const int groups = d >> 3;                 // threads t, t + groups, ... share a column group
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    float v = 0.f;
+    for (int t = c >> 3; t < static_cast<int>(blockDim.x); t += groups) v += s_acc[t][c & 7];
+    if (v != 0.f) atomicAdd(colsum + c, v);
   }
 }
 
@@ -183,8 +208,11 @@ __global__ void k_bias_relu(__nv_bfloat16* Z, const __nv_bfloat16* bias, const i
 __global__ void k_softmax_nll(const __nv_bfloat16* logits, int ld, int C, const int64_t* y,
                               const int64_t* labels_all, const int64_t* nodes,
                               const int32_t* cum, int cap, float* loss, __nv_bfloat16* dlogits,
-                              int32_t* correct) {
+                              int32_t* correct, float* colsum) {
   const int lane = threadIdx.x & 31;
+  float csum[8];  // bias gradient: columns lane, lane+32, ... (ld <= 256)
+#pragma unroll
+  for (int q = 0; q < 8; ++q) csum[q] = 0.f;
   const int wpb = blockDim.x >> 5;
   const int n0 = min(cum[1], cap);
   const float invn = n0 > 0 ? 1.f / static_cast<float>(n0) : 0.f;
@@ -220,13 +248,19 @@ __global__ void k_softmax_nll(const __nv_bfloat16* logits, int ld, int C, const 
         const float p = __expf(__bfloat162float(x[c]) - lse);
         g = (p - (c == label ? 1.f : 0.f)) * invn;
       }
-      dl[c] = __float2bfloat16(g);
+      const __nv_bfloat16 gb = __float2bfloat16(g);
+      dl[c] = gb;
+      if (colsum) csum[(c >> 5) & 7] += __bfloat162float(gb);
     }
     if (lane == 0) {
       const float xl = (label >= 0 && label < C) ? __bfloat162float(x[label]) : lse;
       atomicAdd(loss, (lse - xl) * invn);
       if (correct && arg == label) atomicAdd(correct, 1);
     }
+  }
+  if (colsum) {
+    for (int c = lane, q = 0; c < ld && q < 8; c += 32, ++q)
+      if (csum[q] != 0.f) atomicAdd(colsum + c, csum[q]);
   }
 }
 
@@ -321,10 +355,12 @@ void launch_sage_scatter_bwd(const SageScatterArgs& a, cudaStream_t s) {
 }
 
 void launch_relu_bwd_cast(const float* dH, const void* Z, const int32_t* cum, int n_hops, int cap,
-                          int d, void* dPre, cudaStream_t s) {
-  k_relu_bwd_cast<<<grid_for(static_cast<int64_t>(cap) * d / 8, 256), 256, 0, s>>>(
+                          int d, void* dPre, float* colsum, cudaStream_t s) {
+  if (colsum && (2048 % d != 0)) colsum = nullptr;  // caller falls back to launch_colsum_bf16
+  if (colsum) cudaMemsetAsync(colsum, 0, sizeof(float) * d, s);
+  k_relu_bwd_cast<<<grid_for(static_cast<int64_t>(cap) * d / 8, 256 * 2, 148 * 4), 256, 0, s>>>(
       dH, reinterpret_cast<const __nv_bfloat16*>(Z), cum, n_hops, cap, d,
-      reinterpret_cast<__nv_bfloat16*>(dPre));
+      reinterpret_cast<__nv_bfloat16*>(dPre), colsum);
 }
 
 void launch_bias_relu(void* Z, const void* bias, const int32_t* cum, int n_hops, int cap, int d,
@@ -336,12 +372,14 @@ void launch_bias_relu(void* Z, const void* bias, const int32_t* cum, int n_hops,
 
 void launch_softmax_nll(const void* logits, int ld, int C, const int64_t* y, const int64_t* labels_all,
                         const int64_t* nodes, const int32_t* cum, int cap, float* loss, void* dlogits,
-                        int32_t* correct, cudaStream_t s) {
+                        int32_t* correct, float* colsum, cudaStream_t s) {
+  if (ld > 256) colsum = nullptr;
+  if (colsum) cudaMemsetAsync(colsum, 0, sizeof(float) * ld, s);
   cudaMemsetAsync(loss, 0, sizeof(float), s);
   if (correct) cudaMemsetAsync(correct, 0, sizeof(int32_t), s);
   k_softmax_nll<<<grid_for(cap, 8), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(logits), ld,
                                                   C, y, labels_all, nodes, cum, cap, loss,
-                                                  reinterpret_cast<__nv_bfloat16*>(dlogits), correct);
+                                                  reinterpret_cast<__nv_bfloat16*>(dlogits), correct, colsum);
 }
 
 void launch_adam(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr,

@@ -102,9 +102,12 @@ class GraphSageEngine(object):
                num_classes: int = 47, lr: float = 3e-3, weight_decay: float = 0.0, seed: int = 0,
                device: Optional[torch.device] = None, group=None, use_fused: bool = True,
                use_cuda_graph: bool = True, calibration_seeds: Optional[torch.Tensor] = None,
-               calibration_margin: float = 1.3, calibration_batches: int = 16, pipeline: bool = False):
+               calibration_margin: float = 1.3, calibration_batches: int = 16, pipeline: bool = False,
+               use_peer_allreduce: bool = True):
     self.nat = require_native()
     self.pipeline = bool(pipeline)
+    self.use_peer_allreduce = bool(use_peer_allreduce)
+    self.peer_group = None
     self.graph = graph
     graph.lazy_init()
     self.gh = graph.graph_handler
@@ -245,6 +248,16 @@ class GraphSageEngine(object):
       self._b_off.append((off, n)); off += n
     self.p16 = self.p32.to(torch.bfloat16)
     self.g32 = torch.zeros_like(self.p32)
+    if self.world > 1 and self.use_peer_allreduce:
+      # gradients live in a symmetric-heap segment: the optimizer kernel of every rank reads
+      # all peers' gradients over NVLink (all-reduce fused into Adam, no NCCL in the step)
+      import torch.distributed as dist
+      from ..parallel.peer import exchange_peer_tensors
+      rank = dist.get_rank(self.group)
+      peers_g = exchange_peer_tensors(self.g32, self.group)
+      flags = exchange_peer_tensors(torch.zeros(2 * self.world, dtype=torch.int32, device=dev), self.group)
+      self.g32 = peers_g[rank]
+      self.peer_group = self.nat.PeerGroup(dev.index, rank, peers_g, flags)
     self.m = torch.zeros_like(self.p32)
     self.v = torch.zeros_like(self.p32)
 
@@ -317,12 +330,17 @@ class GraphSageEngine(object):
         nat.bias_relu(self.Z[l], self.b(l), ar.counters, nh, relu)
         self._k(2)
     # labels[nodes[r]] is looked up inside the loss kernel (no gather launch)
+    boff, n = self._b_off[self.L - 1]
+    # the bias gradient of the last layer (column sums of dlogits) is produced by the loss kernel
     nat.softmax_nll(self.Z[self.L], self.C, None, self.labels, ar.nodes, ar.counters, self.loss,
-                    self.dPre[self.L], self.correct)
+                    self.dPre[self.L], self.correct, self.g32[boff:boff + n])
     self._k(1)
 
   def _backward(self):
     nat, ar = self.nat, self.arena
+    if self.peer_group is not None:
+      self.peer_group.barrier(1)          # peers finished reading last step's gradients
+      self._k(1)
     for l in range(self.L, 0, -1):
       ell, ks, nh = self._ell(l)
       off, n, k = self._w_off[l - 1]
@@ -330,13 +348,14 @@ class GraphSageEngine(object):
       gW = self.g32[off:off + n * k].view(n, k)
       # dW = dPre^T A accumulated in fp32 straight into the flat gradient buffer
       self._mm_f32(self.dPre[l].t(), self.A[l], gW)
-      nat.colsum_bf16(self.dPre[l], ar.counters, nh, self.g32[boff:boff + n])
-      self._k(1)
+      # bias gradients are fused into the kernels that produce dPre (loss / relu_bwd_cast)
       if l > 1:
         torch.mm(self.dPre[l], self.W(l), out=self.dA[l])
         nat.zero_rows(self.dH[l - 1], ar.counters, nh + 1)
         nat.sage_scatter_bwd(self.dA[l], self.dims_in[l - 1], ar.counters, nh, ell, ks, ar.deg, self.dH[l - 1])
-        nat.relu_bwd_cast(self.dH[l - 1], self.Z[l - 1], ar.counters, nh + 1, self.dPre[l - 1])
+        pboff, pn = self._b_off[l - 2]
+        nat.relu_bwd_cast(self.dH[l - 1], self.Z[l - 1], ar.counters, nh + 1, self.dPre[l - 1],
+                          self.g32[pboff:pboff + pn])
         self._k(3)
 
   _f32_mode = None
@@ -364,13 +383,19 @@ class GraphSageEngine(object):
 
   def _optimizer(self):
     self.step_dev.add_(1)
-    self.nat.adam_step(self.p32, self.g32, self.m, self.v, self.p16, self.lr, 0.9, 0.999, 1e-8, self.wd,
-                       self.step_dev, 1.0 / self.world)
-    self._k(1)
+    if self.peer_group is not None:
+      self.peer_group.barrier(0)          # every rank finished writing its gradients
+      self.peer_group.adam(self.p32, self.m, self.v, self.p16, self.lr, 0.9, 0.999, 1e-8, self.wd,
+                           self.step_dev, 1.0 / self.world)
+      self._k(2)
+    else:
+      self.nat.adam_step(self.p32, self.g32, self.m, self.v, self.p16, self.lr, 0.9, 0.999, 1e-8, self.wd,
+                         self.step_dev, 1.0 / self.world)
+      self._k(1)
     self._repack()
 
   def _allreduce(self):
-    if self.world > 1:
+    if self.world > 1 and self.peer_group is None:
       import torch.distributed as dist
       dist.all_reduce(self.g32, group=self.group)
 
@@ -422,7 +447,8 @@ class GraphSageEngine(object):
         return
       # capturing NCCL collectives works but makes process-group teardown hang on this stack
       # (measured: bench exit blocked until the timeout), so it is opt-in for world > 1
-      single = self.world == 1 or os.environ.get('GLT_B200_CAPTURE_NCCL', '0') == '1'
+      single = self.world == 1 or self.peer_group is not None or \
+          os.environ.get('GLT_B200_CAPTURE_NCCL', '0') == '1'
       g_opt = None
       for parity in range(2 if self.pipeline else 1):
         g = torch.cuda.CUDAGraph()

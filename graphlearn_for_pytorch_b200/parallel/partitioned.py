@@ -61,18 +61,72 @@ class PartitionedGraph(object):
 
 
 class PartitionedFeature(object):
-  """Row-range partitioned feature table readable from every rank (peer HBM loads)."""
+  """Row-range partitioned feature table readable from every rank (peer HBM loads), with an
+  optional **replicated hot cache**: when ids are hotness-ordered (data.sort_by_in_degree puts
+  the hottest rows first) the first `hot_rows` rows are replicated into every rank's local HBM,
+  so the most frequently gathered rows never cross NVLink.
 
-  def __init__(self, local_rows: torch.Tensor, bounds: List[int], device: torch.device, group=None):
+  The replica is filled either through an NVSwitch multicast object (`multimem.st`: the owner
+  writes each hot row once and the switch delivers it to all replicas; needs
+  torch.distributed._symmetric_memory with multicast support) or, as a fallback, by pulling the
+  hot slices from the owners' peer-mapped shards.  This replaces the reference's per-DeviceGroup
+  host->device replication of the hot part (data/feature.py:185-199).
+  """
+
+  def __init__(self, local_rows: torch.Tensor, bounds: List[int], device: torch.device, group=None,
+               hot_rows: int = 0, use_multicast: bool = True):
     rank, world = world_info(group)
     assert local_rows.shape[0] == bounds[rank + 1] - bounds[rank]
     self.bounds, self.rank, self.world = bounds, rank, world
     self.device = torch.device(device)
     self.local = local_rows.to(self.device).contiguous()
     self.peers = exchange_peer_tensors(self.local, group)
+    self.local = self.peers[rank]
+    self.hot_rows = int(min(max(hot_rows, 0), bounds[-1])) if world > 1 else 0
+    self.replica = None
+    self.fill_mode = None
     self.unified = UnifiedTensor(self.device.index, self.local.dtype)
-    for p in self.peers:
-      self.unified.append_shared_tensor(p)
+    if self.hot_rows > 0:
+      self.replica = self._build_replica(group, use_multicast)
+      self.unified.append_shared_tensor(self.replica)                  # rows [0, H): local replica
+    H = self.hot_rows
+    for r, p in enumerate(self.peers):
+      lo = max(bounds[r], H)
+      if lo >= bounds[r + 1]:
+        continue
+      self.unified.append_shared_tensor(p[lo - bounds[r]:])             # cold rows stay partitioned
+
+  def _build_replica(self, group, use_multicast: bool) -> torch.Tensor:
+    import torch.distributed as dist
+    H, F = self.hot_rows, self.local.shape[1:]
+    b, e = self.bounds[self.rank], self.bounds[self.rank + 1]
+    lo, hi = min(max(b, 0), H), min(e, H)            # hot rows owned by this rank
+    if use_multicast:
+      try:
+        import torch.distributed._symmetric_memory as symm_mem
+        rep = symm_mem.empty((H, *F), dtype=self.local.dtype, device=self.device)
+        hdl = symm_mem.rendezvous(rep, group=group if group is not None else dist.group.WORLD)
+        mc = int(getattr(hdl, 'multicast_ptr', 0) or 0)
+        row_bytes = rep[0].numel() * rep.element_size()
+        if mc != 0 and row_bytes % 16 == 0:
+          if hi > lo:
+            require_native().multimem_copy(self.local[lo - b:hi - b].contiguous(), mc, lo * row_bytes)
+          torch.cuda.synchronize(self.device)
+          dist.barrier(group=group)
+          self.fill_mode = 'nvswitch-multicast'
+          self._symm_handle = hdl
+          return rep
+      except Exception as ex:  # noqa: BLE001 - multicast is optional
+        self._multicast_error = repr(ex)
+    rep = torch.empty((H, *F), dtype=self.local.dtype, device=self.device)
+    for r, p in enumerate(self.peers):
+      plo, phi = min(self.bounds[r], H), min(self.bounds[r + 1], H)
+      if phi > plo:
+        rep[plo:phi].copy_(p[plo - self.bounds[r]:phi - self.bounds[r]])   # NVLink pull
+    torch.cuda.synchronize(self.device)
+    dist.barrier(group=group)
+    self.fill_mode = 'peer-pull'
+    return rep
 
   @property
   def table(self):

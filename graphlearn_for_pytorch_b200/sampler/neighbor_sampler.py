@@ -59,7 +59,8 @@ class NeighborSampler(BaseSampler):
     self._arena_key = None
     self._neg_sampler = None
     self._batch = 0
-    self.seed = int(seed) if seed is not None else int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
+    from ..utils.common import RandomSeedManager
+    self.seed = int(seed) if seed is not None else RandomSeedManager.next_seed()
 
     if isinstance(graph, Graph):
       self._g_cls = 'homo'

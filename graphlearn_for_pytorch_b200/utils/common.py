@@ -154,3 +154,28 @@ def load_ckpt(ckpt_seq: int, ckpt_dir: str, model, optimizer=None, return_extra:
   if return_extra:
     return state.get('epoch', -1), state.get('extra')
   return state.get('epoch', -1)
+
+
+class RandomSeedManager(object):
+  """Process-wide optional seed for samplers created without an explicit `seed`
+  (parity: reference include/common.h:36-65).  With a seed set, every sampler draws from
+  Philox streams derived from it, so whole runs are reproducible."""
+  _seed = None
+  _count = 0
+
+  @classmethod
+  def set_seed(cls, seed: int):
+    cls._seed = int(seed)
+    cls._count = 0
+
+  @classmethod
+  def get_seed(cls):
+    return cls._seed
+
+  @classmethod
+  def next_seed(cls):
+    """A fresh per-object seed: deterministic when a global seed is set, random otherwise."""
+    if cls._seed is None:
+      return int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
+    cls._count += 1
+    return (cls._seed * 1000003 + cls._count * 7919) % (2 ** 31 - 1)

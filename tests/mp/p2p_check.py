@@ -47,6 +47,12 @@ def main():
   assert torch.equal(got, full[ids]), 'peer gather mismatch'
   ok('gather kernel across peer HBM')
 
+  # 2b. replicated hot cache (multicast fill when available, NVLink pull otherwise)
+  pfh = PartitionedFeature(full[bounds[rank]:bounds[rank + 1]].clone(), bounds, dev, hot_rows=3000)
+  assert torch.equal(pfh[ids], full[ids]), 'hot-replica gather mismatch'
+  assert torch.equal(pfh.replica, full[:3000])
+  ok(f'hot-cache replica ({pfh.fill_mode}; parts={pfh.unified._table().num_parts})')
+
   # 3. one-hop + multi-hop sampling on the partitioned CSR == sampling on the full CSR
   ei = rmat_edges(N, 100000, seed=1, device=dev)
   topo = glt.data.Topology(ei, layout='CSR', num_nodes=N)

@@ -119,7 +119,7 @@ def test_softmax_nll_and_adam(native):
   y = torch.randint(0, 47, (128,), device=DEV)
   counters = torch.zeros(16, dtype=torch.int32, device=DEV); counters[1] = 100
   loss = torch.zeros(1, device=DEV); dl = torch.zeros_like(logits); corr = torch.zeros(1, dtype=torch.int32, device=DEV)
-  native.softmax_nll(logits, 47, y, None, None, counters, loss, dl, corr)
+  native.softmax_nll(logits, 47, y, None, None, counters, loss, dl, corr, None)
   x = logits[:100, :47].float().requires_grad_(True)
   ref = F.cross_entropy(x, y[:100]); ref.backward()
   assert abs(loss.item() - ref.item()) < 1e-3
@@ -129,7 +129,9 @@ def test_softmax_nll_and_adam(native):
   # fused label lookup through the node list
   nodes = torch.randperm(500, device=DEV)[:128]; labels_all = torch.randint(0, 47, (500,), device=DEV)
   loss2 = torch.zeros(1, device=DEV)
-  native.softmax_nll(logits, 47, None, labels_all, nodes, counters, loss2, dl, None)
+  bsum = torch.zeros(64, device=DEV)
+  native.softmax_nll(logits, 47, None, labels_all, nodes, counters, loss2, dl, None, bsum)
+  assert torch.allclose(bsum, dl[:100].float().sum(0), atol=1e-3)
   assert abs(loss2.item() - F.cross_entropy(logits[:100, :47].float(), labels_all[nodes[:100]]).item()) < 1e-3
   # column sums / row zeroing with device-side extents
   X = torch.randn(300, 256, device=DEV).to(torch.bfloat16); out = torch.zeros(256, device=DEV)
