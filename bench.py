@@ -47,6 +47,8 @@ def parse_args():
   p.add_argument('--hidden', type=int, default=256)
   p.add_argument('--fanout', default='15,10,5')
   p.add_argument('--no-fused', action='store_true')
+  p.add_argument('--fused', default='auto', choices=['auto', 'on'],
+                 help="'auto': time fused vs unfused layer 1 at warm-up and keep the faster")
   p.add_argument('--no-graph', action='store_true')
   p.add_argument('--no-calibrate', action='store_true', help='size the arena for the worst case')
   p.add_argument('--no-pipeline', action='store_true', help='do not overlap sample(b+1) with train(b)')
@@ -192,7 +194,7 @@ def build_ours(args, rank, world, device):
   pool = perm[rank::world]
   eng = GraphSageEngine(graph, table, labels, in_dim=in_dim, num_nodes=N, fanouts=fanouts,
                         batch_size=args.batch, hidden=args.hidden, num_classes=args.classes,
-                        lr=3e-3, seed=args.seed, device=device, use_fused=not args.no_fused,
+                        lr=3e-3, seed=args.seed, device=device, use_fused=False if args.no_fused else (True if args.fused == 'on' else 'auto'),
                         use_cuda_graph=not args.no_graph,
                         calibration_seeds=None if args.no_calibrate else pool,
                         pipeline=not args.no_pipeline)
@@ -286,6 +288,8 @@ def run_ours(args):
         'feat_dim': args.feat_dim, 'feat_dim_padded': eng.in_dim, 'classes': args.classes,
         'parallelism': f'dp{world}+graph/feature range-partition over {world} GPU(s), in-kernel P2P',
         'optimizer': 'Adam(fused)', 'fused_tcgen05_layer1': bool(eng.fused_ok[1]),
+        'layer1_autotune_ms': getattr(eng, 'autotune_ms', {}).get(1),
+        'grad_allreduce': 'peer-HBM all-reduce fused into Adam (NVLink, in-graph)' if eng.peer_group is not None else ('nccl' if world > 1 else 'none'),
         'cuda_graph': eng._graph_fb is not None, 'pipelined_sample_train_overlap': bool(eng.pipeline),
         'l2_policy': 'inputs larger than L2 (feature table + CSR >> 126 MB, random rows per batch)',
         'baseline_ref': 'BASELINE.md GraphSAGE papers100M epoch 8.56 s / 1,207,179 seeds on 4xA100 (derived)',

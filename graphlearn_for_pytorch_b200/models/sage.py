@@ -93,7 +93,9 @@ class GraphSageEngine(object):
     num_nodes: number of graph nodes (arena sizing).
     fanouts / batch_size / hidden / num_classes: model + sampling config.
     group: torch.distributed group for the gradient all-reduce (None = single process).
-    use_fused: use the tcgen05 gather+GEMM kernel where the shape allows.
+    use_fused: True = use the tcgen05 gather+GEMM kernel where the shape allows; 'auto' = time the
+      fused and the unfused (aggregate kernel + cuBLAS) layer on real batches during warm-up and
+      keep the faster one (remote-heavy multi-GPU runs can favour the unfused pair).
     use_cuda_graph: capture sample+forward+backward(+adam) into CUDA graphs.
   """
 
@@ -170,6 +172,7 @@ class GraphSageEngine(object):
       self.loss = torch.zeros(1, dtype=f32, device=dev)
       self.correct = torch.zeros(1, dtype=torch.int32, device=dev)
       self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+      self._autotune_fused = (use_fused == 'auto')
       self.fused_ok = [False] + [bool(use_fused and self.nat.sage_fused_supported(self.dims_in[l - 1],
                                                                                     self.dims_out[l - 1]))
                                  for l in range(1, self.L + 1)]
@@ -314,6 +317,12 @@ class GraphSageEngine(object):
   def _forward(self):
     nat, ar = self.nat, self.arena
     for l in range(1, self.L + 1):
+      self._forward_layer(l)
+    self._forward_loss()
+
+  def _forward_layer(self, l: int):
+    nat, ar = self.nat, self.arena
+    if True:
       ell, ks, nh = self._ell(l)
       d = self.dims_in[l - 1]
       relu = l < self.L
@@ -330,6 +339,8 @@ class GraphSageEngine(object):
         nat.bias_relu(self.Z[l], self.b(l), ar.counters, nh, relu)
         self._k(2)
     # labels[nodes[r]] is looked up inside the loss kernel (no gather launch)
+  def _forward_loss(self):
+    nat, ar = self.nat, self.arena
     boff, n = self._b_off[self.L - 1]
     # the bias gradient of the last layer (column sums of dlogits) is produced by the loss kernel
     nat.softmax_nll(self.Z[self.L], self.C, None, self.labels, ar.nodes, ar.counters, self.loss,
@@ -420,6 +431,31 @@ class GraphSageEngine(object):
     self._allreduce()
     self._optimizer()
 
+  def _autotune(self, iters: int = 5):
+    """Pick fused vs unfused per layer from device timings on the current batch."""
+    self.autotune_ms = {}
+    ar = self.arena
+    for l in range(1, self.L + 1):
+      if not self.fused_ok[l]:
+        continue
+      res = {}
+      for mode in (True, False):
+        self.fused_ok[l] = mode
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self._forward_layer(l)
+        e0.record()
+        for _ in range(iters):
+          self._forward_layer(l)
+        e1.record()
+        e1.synchronize()
+        res[mode] = e0.elapsed_time(e1) / iters
+      t = torch.tensor([res[True], res[False]], device=self.device)
+      if self.world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)   # same choice on every rank
+      self.fused_ok[l] = bool(t[0] <= t[1])
+      self.autotune_ms[l] = {'fused': float(t[0]), 'unfused': float(t[1])}
+
   # ------------------------------------------------------------------ public API
   def warmup_and_capture(self, n_eager: int = 2):
     """Run a few eager steps (lazy inits, cuBLAS workspaces), then capture the CUDA graphs.
@@ -440,6 +476,17 @@ class GraphSageEngine(object):
             self._cur ^= 1
       torch.cuda.current_stream().wait_stream(side)
       torch.cuda.synchronize()
+      if self._autotune_fused:
+        self._cur = 0
+        self._autotune()
+        self._autotune_fused = False
+        if self.pipeline:
+          self._sample(0)
+        self._tally = 0
+        self._step_eager()                      # re-count kernels with the chosen variants
+        self.kernels_per_step = self._tally
+        torch.cuda.synchronize()
+        self._cur = 0
       self.load_state_dict(saved)
       self._cur, self._primed = 0, False
       self._graphs = []

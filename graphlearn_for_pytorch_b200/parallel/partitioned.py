@@ -38,7 +38,11 @@ def shard_topology(topo: Topology, bounds: List[int], rank: int, device: torch.d
 class PartitionedGraph(object):
   """Collectively build a multi-shard `Graph` from each rank's local shard."""
 
-  def __init__(self, local_shard: dict, bounds: List[int], device: torch.device, group=None):
+  def __init__(self, local_shard: dict, bounds: List[int], device: torch.device, group=None,
+               replicate_indptr: bool = True):
+    """replicate_indptr: keep a local copy of every shard's row-pointer array (8 B per node in
+    total) so that degree / row-extent lookups never cross NVLink; only the sampled column
+    ids (and edge ids / weights) are read from the owner."""
     rank, world = world_info(group)
     self.bounds, self.rank, self.world = bounds, rank, world
     self.device = torch.device(device)
@@ -51,7 +55,10 @@ class PartitionedGraph(object):
         continue
       peers = exchange_peer_tensors(t, group)
       for r in range(world):
-        shards[r][key] = peers[r]
+        if key == 'indptr' and replicate_indptr and r != rank:
+          shards[r][key] = peers[r].clone()      # one NVLink pull at setup, local reads afterwards
+        else:
+          shards[r][key] = peers[r]
     self._peer_shards = shards
     self.graph = Graph.from_shards(shards, self.device.index)
 
@@ -138,3 +145,18 @@ class PartitionedFeature(object):
   @property
   def shape(self):
     return self.unified.shape
+
+
+def partition_hetero_graph(topo_dict: dict, num_nodes: dict, rank: int, world: int, device: torch.device,
+                           edge_dir: str = 'out', group=None):
+  """Range-partition every relation of a heterogeneous graph by the node type its CSR/CSC rows
+  belong to and map all shards on every rank.  -> ({etype: Graph}, {ntype: bounds})."""
+  bounds = {nt: range_bounds(n, world) for nt, n in num_nodes.items()}
+  graphs, keep = {}, []
+  for et, topo in topo_dict.items():
+    row_type = et[0] if edge_dir == 'out' else et[2]
+    shard = shard_topology(topo, bounds[row_type], rank, device)
+    pg = PartitionedGraph(shard, bounds[row_type], device, group)
+    keep.append(pg)
+    graphs[et] = pg.graph
+  return graphs, bounds, keep
