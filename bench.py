@@ -52,7 +52,10 @@ def parse_args():
   p.add_argument('--no-graph', action='store_true')
   p.add_argument('--no-calibrate', action='store_true', help='size the arena for the worst case')
   p.add_argument('--no-pipeline', action='store_true', help='do not overlap sample(b+1) with train(b)')
+  p.add_argument('--hot-fraction', type=float, default=0.25,
+                 help='multi-GPU: fraction of every rank\'s (hotness-ordered) feature rows replicated on all GPUs')
   p.add_argument('--seed', type=int, default=0)
+  p.add_argument('--sections', action='store_true', help='print per-stage device times (eager) and exit')
   p.add_argument('--profile-steps', type=int, default=0,
                  help='run this many eager steps between cudaProfilerStart/Stop (for ncu) and exit')
   return p.parse_args()
@@ -155,12 +158,21 @@ def build_ours(args, rank, world, device):
   half = E // 2
   ei = rmat_edges(N, half, seed=args.seed, device=device)
   ei = torch.cat([ei, ei.flip(0)], dim=1)         # undirected, like ogbn-products
+  bounds = range_bounds(N, world)
+  if world > 1 and args.hot_fraction > 0:
+    # hotness reordering (the reference's example does sort_by_in_degree + split_ratio): nodes are
+    # sorted by degree and dealt round-robin to the ranks, so every rank's id range is balanced and
+    # starts with its hottest rows, which are replicated on all GPUs through NVSwitch multicast
+    from graphlearn_for_pytorch_b200.parallel import hotness_balanced_order
+    deg = torch.bincount(ei[0], minlength=N)
+    old2new, bounds = hotness_balanced_order(deg, world)
+    ei = old2new[ei]
+    del deg, old2new
   topo = glt.data.Topology(ei, layout='CSR', num_nodes=N)
   del ei
   g = torch.Generator(device=device)
   g.manual_seed(args.seed + 1)
   labels = torch.randint(0, args.classes, (N,), device=device, generator=g)
-  bounds = range_bounds(N, world)
   if world == 1:
     graph = glt.data.Graph(topo, 'CUDA', device.index)
     graph.lazy_init()
@@ -181,7 +193,8 @@ def build_ours(args, rank, world, device):
     gl.manual_seed(args.seed + 100 + rank)
     local = torch.zeros(e - b, in_dim, dtype=torch.bfloat16, device=device)
     local[:, :args.feat_dim] = torch.randn(e - b, args.feat_dim, device=device, generator=gl).to(torch.bfloat16)
-    pf = PartitionedFeature(local, bounds, device)
+    pf = PartitionedFeature(local, bounds, device,
+                            hot_per_rank=int(args.hot_fraction * (bounds[1] - bounds[0])))
     table = pf.table
     keep = (pg, pf)
   del topo
@@ -210,6 +223,19 @@ def run_ours(args):
   eng, pool = build_ours(args, rank, world, device)
   bs, K, W = args.batch, args.steps, args.warmup
   eng.warmup_and_capture(n_eager=2)
+  if args.sections:
+    eng._graphs = []
+    sec = eng.profile_sections(pool[:bs].to(device), iters=10)
+    t = torch.tensor([sec[k] for k in sorted(sec)], device=device)
+    if world > 1:
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+      print(json.dumps({'sections_ms_max_over_ranks': dict(zip(sorted(sec), [round(float(x), 4) for x in t])),
+                        'n_gpus': world}), flush=True)
+    if world > 1:
+      dist.barrier()
+      os._exit(0)
+    return
   if args.profile_steps > 0:
     # ncu --profile-from-start off: only these eager steps are captured
     eng._graph_fb = eng._graph_opt = eng._graph_full = None
@@ -289,6 +315,7 @@ def run_ours(args):
         'parallelism': f'dp{world}+graph/feature range-partition over {world} GPU(s), in-kernel P2P',
         'optimizer': 'Adam(fused)', 'fused_tcgen05_layer1': bool(eng.fused_ok[1]),
         'layer1_autotune_ms': getattr(eng, 'autotune_ms', {}).get(1),
+        'hot_feature_replica': (None if world == 1 else {'fraction': args.hot_fraction, 'fill': getattr(eng._keep[1], 'fill_mode', None)}),
         'grad_allreduce': 'peer-HBM all-reduce fused into Adam (NVLink, in-graph)' if eng.peer_group is not None else ('nccl' if world > 1 else 'none'),
         'cuda_graph': eng._graph_fb is not None, 'pipelined_sample_train_overlap': bool(eng.pipeline),
         'l2_policy': 'inputs larger than L2 (feature table + CSR >> 126 MB, random rows per batch)',

@@ -396,7 +396,7 @@ struct RowTableHandle {
     }
     TORCH_CHECK(part.scalar_type() == dtype, "dtype mismatch between parts");
     TORCH_CHECK((part.dim() > 1 ? w : 1) == width || part.size(0) == 0, "row width mismatch");
-    tbl.base[tbl.num_parts] = dev_ptr(part);
+    tbl.base[tbl.num_parts] = part.size(0) > 0 ? dev_ptr(part) : nullptr;
     tbl.row_begin[tbl.num_parts + 1] = tbl.row_begin[tbl.num_parts] + part.size(0);
     tbl.num_parts++;
     keep.push_back(part);

@@ -191,6 +191,11 @@ class GraphSageEngine(object):
   def seeds_dev(self):
     return self._seeds[self._cur]
 
+  @property
+  def g32(self):
+    """Flat fp32 gradient buffer of the batch being trained (per parity when double-buffered)."""
+    return self._g[self._cur % len(self._g)]
+
   # ------------------------------------------------------------------ capacity calibration
   def _calibrate(self, pool: torch.Tensor, num_nodes: int, margin: float, n_batches: int):
     """Size the arena from observed frontier sizes instead of the worst case
@@ -250,17 +255,25 @@ class GraphSageEngine(object):
       self._w_off.append((off, n, k)); off += n * k
       self._b_off.append((off, n)); off += n
     self.p16 = self.p32.to(torch.bfloat16)
-    self.g32 = torch.zeros_like(self.p32)
+    self._g = [torch.zeros_like(self.p32)]
+    self._peer_groups = []
     if self.world > 1 and self.use_peer_allreduce:
       # gradients live in a symmetric-heap segment: the optimizer kernel of every rank reads
       # all peers' gradients over NVLink (all-reduce fused into Adam, no NCCL in the step)
       import torch.distributed as dist
       from ..parallel.peer import exchange_peer_tensors
       rank = dist.get_rank(self.group)
-      peers_g = exchange_peer_tensors(self.g32, self.group)
-      flags = exchange_peer_tensors(torch.zeros(2 * self.world, dtype=torch.int32, device=dev), self.group)
-      self.g32 = peers_g[rank]
-      self.peer_group = self.nat.PeerGroup(dev.index, rank, peers_g, flags)
+      # pipelined engines run parity graphs, so each parity gets its own gradient segment and
+      # flag set: one cross-GPU barrier per step is then enough (the buffer written at step k is
+      # not touched again before step k+2, after everybody passed the barrier of step k+1)
+      n_par = 2 if self.pipeline else 1
+      self._g = []
+      for _ in range(n_par):
+        peers_g = exchange_peer_tensors(torch.zeros_like(self.p32), self.group)
+        flags = exchange_peer_tensors(torch.zeros(2 * self.world, dtype=torch.int32, device=dev), self.group)
+        self._g.append(peers_g[rank])
+        self._peer_groups.append(self.nat.PeerGroup(dev.index, rank, peers_g, flags))
+      self.peer_group = self._peer_groups[0]
     self.m = torch.zeros_like(self.p32)
     self.v = torch.zeros_like(self.p32)
 
@@ -349,7 +362,7 @@ class GraphSageEngine(object):
 
   def _backward(self):
     nat, ar = self.nat, self.arena
-    if self.peer_group is not None:
+    if self.peer_group is not None and len(self._peer_groups) == 1:
       self.peer_group.barrier(1)          # peers finished reading last step's gradients
       self._k(1)
     for l in range(self.L, 0, -1):
@@ -395,8 +408,9 @@ class GraphSageEngine(object):
   def _optimizer(self):
     self.step_dev.add_(1)
     if self.peer_group is not None:
-      self.peer_group.barrier(0)          # every rank finished writing its gradients
-      self.peer_group.adam(self.p32, self.m, self.v, self.p16, self.lr, 0.9, 0.999, 1e-8, self.wd,
+      pg = self._peer_groups[self._cur % len(self._peer_groups)]
+      pg.barrier(0)                       # every rank finished writing its gradients
+      pg.adam(self.p32, self.m, self.v, self.p16, self.lr, 0.9, 0.999, 1e-8, self.wd,
                            self.step_dev, 1.0 / self.world)
       self._k(2)
     else:
@@ -580,6 +594,29 @@ class GraphSageEngine(object):
     self._primed = False
     self.step_idx += 1
     return self.loss
+
+  def profile_sections(self, seeds: torch.Tensor, iters: int = 10):
+    """Device time (ms) of each stage of an *eager, unpipelined* step (CUDA events; the other
+    ranks run the same sequence so the peer barriers inside are matched).  Diagnostic only."""
+    names = ['sample', 'forward_l1', 'forward_rest', 'backward', 'optimizer']
+    acc = {n: 0.0 for n in names}
+    self._cur = 0
+    self._stage_seeds(self._seeds[0], seeds)
+    for it in range(iters + 2):
+      ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+      ev[0].record()
+      self._sample(0); ev[1].record()
+      self._forward_layer(1); ev[2].record()
+      for l in range(2, self.L + 1):
+        self._forward_layer(l)
+      self._forward_loss(); ev[3].record()
+      self._backward(); self._allreduce(); ev[4].record()
+      self._optimizer(); ev[5].record()
+      torch.cuda.synchronize()
+      if it >= 2:
+        for i, n in enumerate(names):
+          acc[n] += ev[i].elapsed_time(ev[i + 1]) / iters
+    return acc
 
   @torch.no_grad()
   def evaluate_batch(self, seeds: torch.Tensor):

@@ -81,7 +81,10 @@ class PartitionedFeature(object):
   """
 
   def __init__(self, local_rows: torch.Tensor, bounds: List[int], device: torch.device, group=None,
-               hot_rows: int = 0, use_multicast: bool = True):
+               hot_rows: int = 0, use_multicast: bool = True, hot_per_rank: int = 0):
+    """hot_rows: replicate the global prefix [0, hot_rows) (ids globally hotness-ordered).
+    hot_per_rank: replicate the first `hot_per_rank` rows of EVERY rank's range (ids dealt
+    round-robin by hotness, see `hotness_balanced_order`): balanced ownership + hot replica."""
     rank, world = world_info(group)
     assert local_rows.shape[0] == bounds[rank + 1] - bounds[rank]
     self.bounds, self.rank, self.world = bounds, rank, world
@@ -90,9 +93,22 @@ class PartitionedFeature(object):
     self.peers = exchange_peer_tensors(self.local, group)
     self.local = self.peers[rank]
     self.hot_rows = int(min(max(hot_rows, 0), bounds[-1])) if world > 1 else 0
+    self.hot_per_rank = int(min(hot_per_rank, min(bounds[r + 1] - bounds[r] for r in range(world)))) \
+        if world > 1 else 0
     self.replica = None
     self.fill_mode = None
     self.unified = UnifiedTensor(self.device.index, self.local.dtype)
+    if self.hot_per_rank > 0:
+      assert 2 * world <= 16, 'per-rank hot replicas need 2 table parts per rank'
+      h = self.hot_per_rank
+      self.replica = self._build_replica_per_rank(group, use_multicast)
+      for r, p in enumerate(self.peers):
+        self.unified.append_shared_tensor(self.replica[r * h:(r + 1) * h])   # hot head of rank r: local
+        if bounds[r + 1] - bounds[r] > h:
+          self.unified.append_shared_tensor(p[h:])                           # cold tail: owner's HBM
+        else:
+          self.unified.append_shared_tensor(p[:0])
+      return
     if self.hot_rows > 0:
       self.replica = self._build_replica(group, use_multicast)
       self.unified.append_shared_tensor(self.replica)                  # rows [0, H): local replica
@@ -135,6 +151,34 @@ class PartitionedFeature(object):
     self.fill_mode = 'peer-pull'
     return rep
 
+  def _build_replica_per_rank(self, group, use_multicast: bool) -> torch.Tensor:
+    import torch.distributed as dist
+    h, W, F = self.hot_per_rank, self.world, self.local.shape[1:]
+    if use_multicast:
+      try:
+        import torch.distributed._symmetric_memory as symm_mem
+        rep = symm_mem.empty((W * h, *F), dtype=self.local.dtype, device=self.device)
+        hdl = symm_mem.rendezvous(rep, group=group if group is not None else dist.group.WORLD)
+        mc = int(getattr(hdl, 'multicast_ptr', 0) or 0)
+        row_bytes = rep[0].numel() * rep.element_size()
+        if mc != 0 and row_bytes % 16 == 0:
+          # every rank multicasts its own hot head once; NVSwitch delivers it to all replicas
+          require_native().multimem_copy(self.local[:h].contiguous(), mc, self.rank * h * row_bytes)
+          torch.cuda.synchronize(self.device)
+          dist.barrier(group=group)
+          self.fill_mode = 'nvswitch-multicast'
+          self._symm_handle = hdl
+          return rep
+      except Exception as ex:  # noqa: BLE001
+        self._multicast_error = repr(ex)
+    rep = torch.empty((W * h, *F), dtype=self.local.dtype, device=self.device)
+    for r, p in enumerate(self.peers):
+      rep[r * h:(r + 1) * h].copy_(p[:h])
+    torch.cuda.synchronize(self.device)
+    dist.barrier(group=group)
+    self.fill_mode = 'peer-pull'
+    return rep
+
   @property
   def table(self):
     return self.unified._table()
@@ -145,6 +189,24 @@ class PartitionedFeature(object):
   @property
   def shape(self):
     return self.unified.shape
+
+
+def hotness_balanced_order(hotness: torch.Tensor, world: int):
+  """Relabelling that makes range partitions balanced *and* hot-first: nodes are sorted by
+  hotness (e.g. degree or sample_prob) and dealt round-robin to the ranks, so every rank's id
+  range starts with its hottest rows.  -> (old2new [N], bounds [world+1])."""
+  n = hotness.numel()
+  order = torch.argsort(hotness, descending=True, stable=True)
+  counts = [(n - r + world - 1) // world for r in range(world)]
+  bounds = [0]
+  for c in counts:
+    bounds.append(bounds[-1] + c)
+  i = torch.arange(n, device=hotness.device)
+  b = torch.tensor(bounds[:-1], device=hotness.device, dtype=torch.int64)
+  new_pos = b[i % world] + i // world
+  old2new = torch.empty(n, dtype=torch.int64, device=hotness.device)
+  old2new[order] = new_pos
+  return old2new, bounds
 
 
 def partition_hetero_graph(topo_dict: dict, num_nodes: dict, rank: int, world: int, device: torch.device,

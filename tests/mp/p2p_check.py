@@ -52,6 +52,11 @@ def main():
   assert torch.equal(pfh[ids], full[ids]), 'hot-replica gather mismatch'
   assert torch.equal(pfh.replica, full[:3000])
   ok(f'hot-cache replica ({pfh.fill_mode}; parts={pfh.unified._table().num_parts})')
+  pfr = PartitionedFeature(full[bounds[rank]:bounds[rank + 1]].clone(), bounds, dev, hot_per_rank=500)
+  assert torch.equal(pfr[ids], full[ids]), 'per-rank hot-replica gather mismatch'
+  for r in range(world):
+    assert torch.equal(pfr.replica[r * 500:(r + 1) * 500], full[bounds[r]:bounds[r] + 500])
+  ok(f'per-rank hot replica ({pfr.fill_mode}; parts={pfr.unified._table().num_parts})')
 
   # 3. one-hop + multi-hop sampling on the partitioned CSR == sampling on the full CSR
   ei = rmat_edges(N, 100000, seed=1, device=dev)
