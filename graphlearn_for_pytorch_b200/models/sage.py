@@ -168,7 +168,6 @@ class GraphSageEngine(object):
       self._seeds = [torch.zeros(self.bs, dtype=torch.int64, device=dev) for _ in range(n_arenas)]
       self._side = torch.cuda.Stream(device=dev) if self.pipeline else None
       self._primed = False
-      self.y = torch.zeros(self.bs, dtype=torch.int64, device=dev)
       self.loss = torch.zeros(1, dtype=f32, device=dev)
       self.correct = torch.zeros(1, dtype=torch.int32, device=dev)
       self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -335,24 +334,24 @@ class GraphSageEngine(object):
 
   def _forward_layer(self, l: int):
     nat, ar = self.nat, self.arena
-    if True:
-      ell, ks, nh = self._ell(l)
-      d = self.dims_in[l - 1]
-      relu = l < self.L
-      feat = self.feat if l == 1 else None
-      nodes = ar.nodes if l == 1 else None
-      src_local = None if l == 1 else self.Z[l - 1]
-      if self.fused_ok[l]:
-        nat.sage_fused(feat, nodes, src_local, d, ar.counters, nh, ell, ks, ar.deg, self.w_packed[l],
-                       self.b(l), relu, self.Z[l], self.A[l])
-        self._k(1)
-      else:
-        nat.sage_aggregate(feat, nodes, src_local, d, ar.counters, nh, ell, ks, ar.deg, self.A[l])
-        torch.mm(self.A[l], self.W(l).t(), out=self.Z[l])
-        nat.bias_relu(self.Z[l], self.b(l), ar.counters, nh, relu)
-        self._k(2)
-    # labels[nodes[r]] is looked up inside the loss kernel (no gather launch)
+    ell, ks, nh = self._ell(l)
+    d = self.dims_in[l - 1]
+    relu = l < self.L
+    feat = self.feat if l == 1 else None
+    nodes = ar.nodes if l == 1 else None
+    src_local = None if l == 1 else self.Z[l - 1]
+    if self.fused_ok[l]:
+      nat.sage_fused(feat, nodes, src_local, d, ar.counters, nh, ell, ks, ar.deg, self.w_packed[l],
+                     self.b(l), relu, self.Z[l], self.A[l])
+      self._k(1)
+    else:
+      nat.sage_aggregate(feat, nodes, src_local, d, ar.counters, nh, ell, ks, ar.deg, self.A[l])
+      torch.mm(self.A[l], self.W(l).t(), out=self.Z[l])
+      nat.bias_relu(self.Z[l], self.b(l), ar.counters, nh, relu)
+      self._k(2)
+
   def _forward_loss(self):
+    # labels[nodes[r]] is looked up inside the loss kernel (no gather launch)
     nat, ar = self.nat, self.arena
     boff, n = self._b_off[self.L - 1]
     # the bias gradient of the last layer (column sums of dlogits) is produced by the loss kernel

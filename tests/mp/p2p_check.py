@@ -93,6 +93,20 @@ def main():
   dist.all_reduce(p, op=dist.ReduceOp.MAX)
   assert torch.allclose(p, eng.p32), 'ranks diverged'
   ok('DDP parameters in sync')
+  # pipelined engine: parity double-buffered gradient segments, one peer barrier per step
+  eng2 = GraphSageEngine(pg.graph, pf2.table, labels, in_dim=128, num_nodes=N, fanouts=[4, 3], batch_size=256,
+                         hidden=256, num_classes=8, device=dev, use_cuda_graph=True, pipeline=True,
+                         calibration_seeds=torch.arange(N))
+  eng2.warmup_and_capture(1)
+  for i in range(7):
+    eng2.train_step(torch.randperm(N, device=dev)[:256])
+  eng2.flush()
+  p2 = eng2.p32.clone()
+  dist.all_reduce(p2, op=dist.ReduceOp.MAX)
+  assert torch.allclose(p2, eng2.p32), 'pipelined ranks diverged'
+  assert int(eng2.peer_group.err.item()) == 0 and eng2.overflow_count() == 0
+  ok(f'pipelined engine in sync, loss={float(eng2.loss.item()):.3f}')
+  eng2.close()
   eng.close()
   dist.barrier()
   torch.cuda.synchronize()

@@ -200,3 +200,25 @@ def test_neighbor_loader_cuda_ring(native):
     check_homo_batch(b)
     seen += b.batch.tolist()
   assert sorted(seen) == list(range(40))
+
+
+def test_arena_capacity_guard(native):
+  """Calibrated (too small) capacities: excess nodes are dropped and counted, nothing overflows."""
+  topo, gc, gg = _graphs(5000, 100000)
+  caps = [256, 300, 500, 700]
+  arena = native.SamplerArena(0, 256, [10, 5, 3], False, 5000, caps)
+  seeds = torch.randperm(5000, device=DEV)[:256].contiguous()
+  arena.sample(gg.graph_handler, seeds, None, 3, 0, False, False, False)
+  c = arena.counters.cpu().tolist()
+  cum = c[:5]
+  assert cum[1] == 256
+  for h in range(1, 4):
+    assert cum[h + 1] - cum[h] <= arena.cap_rows[h], (h, cum, arena.cap_rows)
+  assert cum[4] <= arena.cap_nodes
+  assert c[12] > 0                                           # something was dropped
+  for h in range(3):
+    rows = cum[h + 1] - cum[h]
+    ell = arena.ell[h][:rows * [10, 5, 3][h]]
+    assert int(ell.max()) < cum[h + 2] and int(ell.min()) >= -1
+  node, row, col, _, nn, ne = arena.to_coo()
+  assert node.numel() == cum[4] and int(row.max()) < node.numel() and int(row.min()) >= -1
