@@ -93,6 +93,25 @@ def main():
   dist.all_reduce(p, op=dist.ReduceOp.MAX)
   assert torch.allclose(p, eng.p32), 'ranks diverged'
   ok('DDP parameters in sync')
+  # distributed loader API on the P2P plane: DistDataset.from_p2p + DistNeighborLoader (collocated)
+  import graphlearn_for_pytorch_b200.distributed as gd
+  gd.init_worker_group(world, rank)
+  idfeat = torch.arange(N, dtype=torch.float32, device=dev).unsqueeze(1).repeat(1, 16)
+  pfi = PartitionedFeature(idfeat[bounds[rank]:bounds[rank + 1]].clone(), bounds, dev)
+  dds = gd.DistDataset.from_p2p(pg, pfi, labels=torch.arange(N, device=dev))
+  loader = gd.DistNeighborLoader(dds, [4, 3], torch.arange(bounds[rank], bounds[rank + 1])[:600], batch_size=128,
+                                 shuffle=True, collect_features=True, to_device=dev,
+                                 worker_options=gd.CollocatedDistSamplingWorkerOptions(master_addr='127.0.0.1',
+                                                                                       master_port=29555))
+  adj = None
+  n_b = 0
+  for b in loader:
+    assert torch.equal(b.x[:, 0].long(), b.node) and torch.equal(b.y, b.node)
+    n_b += 1
+  assert n_b == 5
+  loader.shutdown()
+  ok('DistNeighborLoader over the P2P data plane (features/labels verified)')
+
   # pipelined engine: parity double-buffered gradient segments, one peer barrier per step
   eng2 = GraphSageEngine(pg.graph, pf2.table, labels, in_dim=128, num_nodes=N, fanouts=[4, 3], batch_size=256,
                          hidden=256, num_classes=8, device=dev, use_cuda_graph=True, pipeline=True,

@@ -222,3 +222,37 @@ def test_arena_capacity_guard(native):
     assert int(ell.max()) < cum[h + 2] and int(ell.min()) >= -1
   node, row, col, _, nn, ne = arena.to_coo()
   assert node.numel() == cum[4] and int(row.max()) < node.numel() and int(row.min()) >= -1
+
+
+def test_hetero_and_link_sampling_gpu_matches_cpu(native):
+  """Hetero multi-hop + link sampling with negatives on the GPU (generic IdTable path)."""
+  from graphlearn_for_pytorch_b200.sampler import EdgeSamplerInput, NegativeSampling
+  g = torch.Generator().manual_seed(0)
+  u2i = torch.stack([torch.randint(0, 300, (3000,), generator=g), torch.randint(0, 200, (3000,), generator=g)])
+  i2i = torch.stack([torch.randint(0, 200, (2000,), generator=g), torch.randint(0, 200, (2000,), generator=g)])
+  outs = {}
+  for mode in ('CPU', 'CUDA'):
+    ds = glt.data.Dataset(edge_dir='out')
+    ds.init_graph({('user', 'u2i', 'item'): u2i, ('item', 'i2i', 'item'): i2i}, graph_mode=mode, device=0,
+                  num_nodes={'user': 300, 'item': 200})
+    s = NeighborSampler(ds.graph, [3, 2], with_edge=True, seed=5, device=DEV if mode == 'CUDA' else None)
+    outs[mode] = s.sample_from_nodes(NodeSamplerInput(torch.arange(0, 300, 7), 'user'))
+  a, b = outs['CPU'], outs['CUDA']
+  assert set(a.row.keys()) == set(b.row.keys())
+  for nt in a.node:
+    assert set(a.node[nt].tolist()) == set(b.node[nt].cpu().tolist())
+  for et in a.row:
+    st, dt = et[0], et[2]
+    ea = set(zip(a.node[st][a.row[et]].tolist(), a.node[dt][a.col[et]].tolist(), a.edge[et].tolist()))
+    eb = set(zip(b.node[st][b.row[et]].cpu().tolist(), b.node[dt][b.col[et]].cpu().tolist(), b.edge[et].cpu().tolist()))
+    assert ea == eb
+  assert a.num_sampled_nodes == b.num_sampled_nodes
+  # homogeneous link sampling with strict binary negatives on the GPU
+  ds = ring_dataset(40, graph_mode='CUDA', with_gpu=True, device=0, split_ratio=1.0)
+  s = NeighborSampler(ds.graph, [2], with_neg=True, seed=3, device=DEV)
+  row, col = torch.tensor([0, 1, 2], device=DEV), torch.tensor([1, 3, 3], device=DEV)
+  out = s.sample_from_edges(EdgeSamplerInput(row, col, neg_sampling=NegativeSampling('binary', 2)))
+  eli, lab = out.metadata['edge_label_index'], out.metadata['edge_label']
+  assert eli.shape == (2, 9) and lab.tolist() == [1, 1, 1] + [0] * 6
+  ns, nd = out.node[eli[0, 3:]], out.node[eli[1, 3:]]
+  assert torch.all(((nd - ns) % 40 != 1) & ((nd - ns) % 40 != 2))
