@@ -83,3 +83,40 @@ def run_workers(fn, world=2, args=(), timeout=240):
       errs.append(('?', 'timeout'))
   assert not errs, '\n'.join(f'[rank {r}] {e}' for r, e in errs)
   assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+
+
+def build_hetero_partition(rank: int, world: int = 2, edge_dir: str = 'out'):
+  """user -u2i-> item, item -i2i-> item; 20 users, 20 items; feature rows encode (type offset + id)."""
+  import graphlearn_for_pytorch_b200 as glt
+  from graphlearn_for_pytorch_b200.distributed import DistDataset
+  from graphlearn_for_pytorch_b200.partition import GLTPartitionBook
+  from graphlearn_for_pytorch_b200.utils.synthetic import id_features
+  from graphlearn_for_pytorch_b200.utils.tensor import id2idx
+  nu = ni = 20
+  u = torch.arange(nu)
+  u2i = torch.stack([u.repeat_interleave(2), torch.stack([u % ni, (u + 1) % ni], 1).flatten()])
+  i = torch.arange(ni)
+  i2i = torch.stack([i, (i + 3) % ni])
+  edges = {('user', 'u2i', 'item'): u2i, ('item', 'i2i', 'item'): i2i}
+  node_pb = {'user': GLTPartitionBook(torch.arange(nu) % world), 'item': GLTPartitionBook(torch.arange(ni) % world)}
+  ei_local, eids_local, edge_pb = {}, {}, {}
+  for et, ei in edges.items():
+    key_t = et[0] if edge_dir == 'out' else et[2]
+    key = ei[0] if edge_dir == 'out' else ei[1]
+    owners = node_pb[key_t][key]
+    edge_pb[et] = GLTPartitionBook(owners.clone())
+    m = owners == rank
+    ei_local[et] = ei[:, m]
+    eids_local[et] = torch.arange(ei.shape[1])[m]
+  ds = DistDataset(edge_dir=edge_dir)
+  ds.num_partitions, ds.partition_idx = world, rank
+  ds.init_graph(ei_local, eids_local, graph_mode='CPU', num_nodes={'user': nu, 'item': ni})
+  feats, i2x = {}, {}
+  for nt, off in (('user', 0), ('item', 1000)):
+    own = torch.nonzero(node_pb[nt][torch.arange(20)] == rank).view(-1)
+    feats[nt] = (id_features(20, 4) + off)[own]
+    i2x[nt] = id2idx(own)
+  ds.init_node_features(feats, i2x, with_gpu=False)
+  ds.init_node_labels({'user': torch.arange(nu)})
+  ds.node_pb, ds.edge_pb = node_pb, edge_pb
+  return ds, edges

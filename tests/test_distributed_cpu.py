@@ -194,3 +194,46 @@ def test_dist_random_partitioner():
       assert torch.equal(ef.feats[:, 0].long(), ef.ids) and sorted(ef.ids.tolist()) == sorted(g.eids.tolist())
       nodes += nf.ids.tolist(); edges += g.eids.tolist()
     assert sorted(nodes) == list(range(N)) and sorted(edges) == list(range(ei.shape[1]))
+
+
+def _w_hetero_loader(rank, world, port, edge_dir):
+  import graphlearn_for_pytorch_b200.distributed as d
+  from dist_utils import build_hetero_partition
+  d.init_worker_group(world, rank)
+  ds, edges = build_hetero_partition(rank, world, edge_dir)
+  opts = d.CollocatedDistSamplingWorkerOptions(master_addr='127.0.0.1', master_port=port)
+  seed_t = 'user' if edge_dir == 'out' else 'item'
+  seeds = torch.arange(rank, 20, world)
+  loader = d.DistNeighborLoader(ds, [2, 2], (seed_t, seeds), batch_size=4, shuffle=True, with_edge=True,
+                                edge_dir=edge_dir, collect_features=True, to_device=torch.device('cpu'),
+                                worker_options=opts)
+  true_u2i = set(zip(edges[('user', 'u2i', 'item')][0].tolist(), edges[('user', 'u2i', 'item')][1].tolist()))
+  true_i2i = set(zip(edges[('item', 'i2i', 'item')][0].tolist(), edges[('item', 'i2i', 'item')][1].tolist()))
+  seen = []
+  for b in loader:
+    assert torch.equal(b['user'].x[:, 0].long(), b['user'].node) if b['user'].x is not None else True
+    if b['item'].x is not None:
+      assert torch.equal(b['item'].x[:, 0].long() - 1000, b['item'].node)
+    for et, ei in b.edge_index_dict.items():
+      s_nodes, d_nodes = b[et[0]].node[ei[0]], b[et[2]].node[ei[1]]
+      if edge_dir == 'out':   # reversed relations: messages flow neighbour -> seed
+        if et == ('item', 'rev_u2i', 'user'):
+          assert all((u, i) in true_u2i for i, u in zip(s_nodes.tolist(), d_nodes.tolist()))
+        else:
+          assert et == ('item', 'i2i', 'item')
+          assert all((a, c) in true_i2i for c, a in zip(s_nodes.tolist(), d_nodes.tolist()))
+      else:
+        truth = true_u2i if et == ('user', 'u2i', 'item') else true_i2i
+        assert all((a, c) in truth for a, c in zip(s_nodes.tolist(), d_nodes.tolist()))
+    seen += b[seed_t].batch.tolist()
+    if seed_t == 'user':
+      assert torch.equal(b['user'].y[:b['user'].batch_size], b['user'].batch)
+  assert sorted(seen) == seeds.tolist()
+  loader.shutdown()
+  d.barrier()
+  d.shutdown_rpc()
+
+
+@pytest.mark.parametrize('edge_dir', ['out', 'in'])
+def test_dist_hetero_neighbor_loader(edge_dir):
+  run_workers(_w_hetero_loader, args=(edge_dir,), timeout=300)

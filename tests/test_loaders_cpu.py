@@ -117,3 +117,56 @@ def test_hetero_neighbor_loader():
     assert ei.shape[0] == 2 and ei[1].max() < b['user'].node.numel()
     assert set(b.edge_index_dict.keys()) <= {('item', 'rev_u2i', 'user'), ('item', 'i2i', 'item')}
     assert len(b.num_sampled_nodes['item']) == 3
+
+
+def _hetero_ds(edge_dir='out'):
+  u2i = torch.tensor([[0, 0, 1, 2, 3, 3, 1], [0, 1, 1, 2, 3, 0, 2]])
+  i2i = torch.tensor([[0, 1, 2, 3], [1, 2, 3, 0]])
+  ds = glt.data.Dataset(edge_dir=edge_dir)
+  ds.init_graph({('user', 'u2i', 'item'): u2i, ('item', 'i2i', 'item'): i2i}, graph_mode='CPU',
+                num_nodes={'user': 4, 'item': 4})
+  ds.init_node_features({'user': glt.utils.id_features(4, 8), 'item': glt.utils.id_features(4, 8) + 100},
+                        with_gpu=False)
+  return ds, u2i
+
+
+def test_hetero_link_neighbor_loader_binary_and_triplet():
+  ds, u2i = _hetero_ds()
+  et = ('user', 'u2i', 'item')
+  loader = LinkNeighborLoader(ds, [2, 2], edge_label_index=(et, u2i), neg_sampling=NegativeSampling('binary', 1),
+                              batch_size=4, shuffle=True, seed=0)
+  pos_edges = set(zip(u2i[0].tolist(), u2i[1].tolist()))
+  n_pos = 0
+  for b in loader:
+    rev = ('item', 'rev_u2i', 'user')
+    eli, lab = b[rev].edge_label_index, b[rev].edge_label
+    # reversed relation: row 0 = item (dst), row 1 = user (src)
+    users, items = b['user'].node[eli[1]], b['item'].node[eli[0]]
+    for u, i, l in zip(users.tolist(), items.tolist(), lab.tolist()):
+      assert ((u, i) in pos_edges) == (l == 1)
+    assert torch.equal(b['user'].x[:, 0].long(), b['user'].node)
+    assert torch.equal(b['item'].x[:, 0].long() - 100, b['item'].node)
+    n_pos += int((lab == 1).sum())
+  assert n_pos == u2i.shape[1]
+  loader = LinkNeighborLoader(ds, [2], edge_label_index=(et, u2i), neg_sampling=NegativeSampling('triplet', 2),
+                              batch_size=4)
+  for b in loader:
+    src = b['user'].node[b['user'].src_index]
+    dst = b['item'].node[b['item'].dst_pos_index]
+    assert all((u, i) in pos_edges for u, i in zip(src.tolist(), dst.tolist()))
+    assert b['item'].dst_neg_index.shape == (src.numel(), 2)
+
+
+def test_table_dataset_from_columns():
+  import numpy as np
+  from graphlearn_for_pytorch_b200.data import TableDataset
+  edges = {'src_id': np.array([0, 1, 2, 3]), 'dst_id': np.array([1, 2, 3, 0])}
+  nodes = {'id': np.arange(4), 'feature': np.array(['0:0', '1:1', '2:2', '3:3'], dtype=object),
+           'label': np.array([0, 1, 0, 1])}
+  ds = TableDataset().load(edge_tables={('n', 'e', 'n'): edges}, node_tables={'n': nodes}, graph_mode='CPU',
+                           directed=True)
+  loader = NeighborLoader(ds, [1], torch.arange(4), batch_size=2)
+  for b in loader:
+    assert torch.equal(b.x[:, 0].long(), b.node) and torch.equal(b.y, b.node % 2)
+    src, dst = b.node[b.edge_index[0]], b.node[b.edge_index[1]]
+    assert torch.all((src - dst) % 4 == 1)
