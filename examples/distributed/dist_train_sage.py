@@ -44,7 +44,7 @@ if args.workers > 0:
                                         master_port=args.master_port + 1, pin_memory=cuda)
 else:
   opts = gd.CollocatedDistSamplingWorkerOptions(master_addr=args.master_addr, master_port=args.master_port + 1)
-loader = gd.DistNeighborLoader(ds, [15, 10, 5], train, batch_size=512, shuffle=True, drop_last=True,
+loader = gd.DistNeighborLoader(ds, [15, 10, 5], train, batch_size=512, shuffle=True, drop_last=False,
                                collect_features=True, to_device=device, worker_options=opts)
 n_cls = int(ds.node_labels.max()) + 1
 model = torch.nn.parallel.DistributedDataParallel(GraphSAGE(ds.node_features.shape[1], 256, n_cls, 3).to(device))
@@ -57,3 +57,6 @@ for epoch in range(args.epochs):
   print(f'[rank {args.rank}] epoch {epoch} loss {float(loss):.4f}')
 loader.shutdown()
 dist.barrier()
+if gd.rpc_is_initialized():
+  gd.barrier()
+  gd.shutdown_rpc()
