@@ -12,11 +12,11 @@ import torch.nn.functional as F
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from common import glt, synthetic_igbh  # noqa: E402
-from graphlearn_for_pytorch_b200.models import RGNN  # noqa: E402
+from graphlearn_for_pytorch_b200.models import HGT, RGNN  # noqa: E402
 from graphlearn_for_pytorch_b200.utils import EventLogger, load_ckpt, save_ckpt  # noqa: E402
 
 p = argparse.ArgumentParser()
-p.add_argument('--model', default='rsage', choices=['rsage', 'rgcn', 'rgat'])
+p.add_argument('--model', default='rsage', choices=['rsage', 'rgcn', 'rgat', 'hgt'])
 p.add_argument('--papers', type=int, default=20_000)
 p.add_argument('--fanout', default='15,10')
 p.add_argument('--batch', type=int, default=512)
@@ -39,8 +39,12 @@ train_idx = torch.randperm(args.papers)[: args.papers // 2]
 loader = glt.loader.NeighborLoader(ds, fan, ('paper', train_idx), batch_size=args.batch, shuffle=True,
                                    drop_last=True, device=device)
 first = next(iter(loader))
-model = RGNN(list(first.edge_index_dict.keys()), 128, 256, int(labels['paper'].max()) + 1, num_layers=len(fan),
-             node_type='paper', model=args.model).to(device)
+if args.model == 'hgt':
+  model = HGT(list(sizes.keys()), list(first.edge_index_dict.keys()), 128, 256, int(labels['paper'].max()) + 1,
+              num_layers=len(fan), heads=4, node_type='paper').to(device)
+else:
+  model = RGNN(list(first.edge_index_dict.keys()), 128, 256, int(labels['paper'].max()) + 1, num_layers=len(fan),
+               node_type='paper', model=args.model).to(device)
 opt = torch.optim.Adam(model.parameters(), lr=1e-3)
 start_epoch = 0
 if args.ckpt_dir:
@@ -50,7 +54,8 @@ log.start('RUN')
 for epoch in range(start_epoch, args.epochs):
   t0, correct, seen = time.time(), 0, 0
   for b in loader:
-    out = model(b.x_dict, b.edge_index_dict, b.num_sampled_nodes, b.num_sampled_edges)[:b['paper'].batch_size]
+    out = (model(b.x_dict, b.edge_index_dict) if args.model == 'hgt' else
+           model(b.x_dict, b.edge_index_dict, b.num_sampled_nodes, b.num_sampled_edges))[:b['paper'].batch_size]
     tgt = b['paper'].y[:b['paper'].batch_size].to(device)
     loss = F.cross_entropy(out, tgt)
     opt.zero_grad(); loss.backward(); opt.step()

@@ -1,3 +1,4 @@
 from .sage import SAGEConv, GraphSAGE, GraphSageEngine
 from .rgnn import RGNN, RelSAGEConv, RelGCNConv, RelGATConv
 from .seal import drnl_node_labeling, DGCNN
+from .hgt import HGT, HGTConv

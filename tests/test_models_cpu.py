@@ -2,7 +2,7 @@ import torch
 
 import graphlearn_for_pytorch_b200 as glt
 from graphlearn_for_pytorch_b200.loader import NeighborLoader
-from graphlearn_for_pytorch_b200.models import DGCNN, RGNN, GraphSAGE, drnl_node_labeling
+from graphlearn_for_pytorch_b200.models import DGCNN, HGT, RGNN, GraphSAGE, drnl_node_labeling
 from helpers import ring_dataset
 
 
@@ -67,3 +67,29 @@ def test_drnl_and_dgcnn():
   out = model(zz, e2, batch, 2)
   assert out.shape == (2,)
   out.sum().backward()
+
+
+def test_hgt_trains_on_hetero_batches():
+  torch.manual_seed(0)
+  g = torch.Generator().manual_seed(0)
+  u2i = torch.stack([torch.randint(0, 60, (400,), generator=g), torch.randint(0, 40, (400,), generator=g)])
+  ds = glt.data.Dataset(edge_dir='out')
+  ds.init_graph({('user', 'u2i', 'item'): u2i, ('item', 'rev_u2i', 'user'): u2i.flip(0)}, graph_mode='CPU',
+                num_nodes={'user': 60, 'item': 40})
+  xu, xi = torch.randn(60, 8, generator=g), torch.randn(40, 12, generator=g)
+  ds.init_node_features({'user': xu, 'item': xi}, with_gpu=False)
+  ds.init_node_labels({'user': (xu[:, 0] > 0).long()})
+  loader = NeighborLoader(ds, [4, 4], ('user', torch.arange(60)), batch_size=30, shuffle=True, seed=0)
+  b0 = next(iter(loader))
+  model = HGT(['user', 'item'], list(b0.edge_index_dict.keys()), {'user': 8, 'item': 12}, 16, 2, num_layers=2,
+              heads=4, node_type='user')
+  opt = torch.optim.Adam(model.parameters(), lr=0.02)
+  first = last = None
+  for epoch in range(25):
+    for b in loader:
+      out = model(b.x_dict, b.edge_index_dict)[:b['user'].batch_size]
+      loss = torch.nn.functional.cross_entropy(out, b['user'].y[:b['user'].batch_size])
+      opt.zero_grad(); loss.backward(); opt.step()
+      first = first if first is not None else loss.item()
+      last = loss.item()
+  assert last < 0.7 * first, (first, last)
