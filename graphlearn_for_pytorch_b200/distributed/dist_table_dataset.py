@@ -32,6 +32,7 @@ class DistTableRandomPartitioner(DistRandomPartitioner):
       ei[et] = e
       eids[et] = torch.arange(off, off + e.shape[1]) if 'edge_id' not in cols else \
           torch.from_numpy(cols['edge_id'].astype(np.int64))
+      off += e.shape[1]
     for nt, src in (node_tables or {}).items():
       cols = _read_table(src)
       nids[nt] = torch.from_numpy(cols[id_col].astype(np.int64))
@@ -44,17 +45,46 @@ class DistTableRandomPartitioner(DistRandomPartitioner):
         nf, nids = nf[kn], nids[kn]
       else:
         nf = nids = None
-    return cls(output_dir, num_nodes, ei, eids, nf or None, nids or None, **kwargs)
+    if isinstance(nf, dict) and not nf:
+      nf = nids = None
+    return cls(output_dir, num_nodes, ei, eids, nf, nids, **kwargs)
 
 
 class DistTableDataset(DistDataset):
   def load(self, num_nodes, edge_tables, node_tables=None, graph_mode: str = 'CPU', feature_with_gpu=False,
            label_col: Optional[str] = 'label', id_col: str = 'id', device=None, **kwargs):
     """Collectively partition the table slices and load this rank's partition."""
+    from .rpc import all_gather, rpc_is_initialized
     ctx = get_context()
-    assert ctx is not None, 'init_worker_group() + init_rpc() first'
-    out = kwargs.pop('output_dir', None) or tempfile.mkdtemp(prefix='glt_b200_table_')
-    part = DistTableRandomPartitioner.from_tables(out, num_nodes, edge_tables, node_tables, id_col=id_col, **kwargs)
+    assert ctx is not None and rpc_is_initialized(), 'init_worker_group() + init_rpc() first'
+    out = kwargs.pop('output_dir', None)
+    if out is None:
+      # every rank must write under the same root: rank 0 picks it
+      mine = tempfile.mkdtemp(prefix='glt_b200_table_') if ctx.rank == 0 else None
+      out = [v for v in all_gather(mine).values() if v is not None][0]
+    # dense global edge ids: this rank's slice starts after the slices of the lower ranks
+    n_local = sum(len(_read_table(src)[kwargs.get('src_col', 'src_id')]) for src in edge_tables.values())
+    counts = all_gather((ctx.rank, n_local))
+    offset = sum(n for r, n in counts.values() if r < ctx.rank)
+    part = DistTableRandomPartitioner.from_tables(out, num_nodes, edge_tables, node_tables, id_col=id_col,
+                                                  edge_id_offset=offset, **kwargs)
     part.partition()
     DistDataset.load(self, out, ctx.rank, graph_mode=graph_mode, feature_with_gpu=feature_with_gpu, device=device)
+    if label_col:
+      # labels travel with the node tables: gather every rank's (id, label) slice
+      import numpy as np
+      mine = {}
+      for nt, src in (node_tables or {}).items():
+        cols = _read_table(src)
+        if label_col in cols:
+          mine[nt] = (torch.from_numpy(cols[id_col].astype(np.int64)), torch.from_numpy(cols[label_col].astype(np.int64)))
+      gathered = all_gather(mine)
+      labels = {}
+      for part_labels in gathered.values():
+        for nt, (ids, lab) in part_labels.items():
+          n = num_nodes[nt] if isinstance(num_nodes, dict) else num_nodes
+          full = labels.setdefault(nt, torch.full((n,), -1, dtype=torch.int64))
+          full[ids] = lab
+      if labels:
+        self.init_node_labels(labels if isinstance(num_nodes, dict) else next(iter(labels.values())))
     return self

@@ -237,3 +237,38 @@ def _w_hetero_loader(rank, world, port, edge_dir):
 @pytest.mark.parametrize('edge_dir', ['out', 'in'])
 def test_dist_hetero_neighbor_loader(edge_dir):
   run_workers(_w_hetero_loader, args=(edge_dir,), timeout=300)
+
+
+def _w_dist_table(rank, world, port, out):
+  import numpy as np
+  import graphlearn_for_pytorch_b200.distributed as d
+  from graphlearn_for_pytorch_b200.utils.synthetic import ring_graph
+  d.init_worker_group(world, rank)
+  d.init_rpc('127.0.0.1', port)
+  ei = ring_graph(N)
+  half = ei.shape[1] // 2
+  sl = slice(rank * half, (rank + 1) * half)
+  ids = np.arange(rank * N // 2, (rank + 1) * N // 2)
+  edges = {'src_id': ei[0, sl].numpy(), 'dst_id': ei[1, sl].numpy()}
+  nodes = {'id': ids, 'feature': np.array([f'{i}:{i}' for i in ids], dtype=object), 'label': ids % 3}
+  ds = d.DistTableDataset()
+  ds.load(N, {None: edges}, {None: nodes}, graph_mode='CPU', output_dir=out)
+  assert ds.num_partitions == 2 and ds.partition_idx == rank
+  own = torch.nonzero(ds.node_pb == rank).view(-1)
+  assert torch.equal(ds.node_features.cpu_get(own)[:, 0].long(), own)
+  assert torch.equal(ds.node_labels, torch.arange(N) % 3)
+  opts = d.CollocatedDistSamplingWorkerOptions(master_addr='127.0.0.1', master_port=port)
+  loader = d.DistNeighborLoader(ds, [2, 2], own, batch_size=6, collect_features=True, to_device=torch.device('cpu'),
+                                worker_options=opts)
+  for b in loader:
+    assert torch.equal(b.x[:, 0].long(), b.node) and torch.equal(b.y, b.node % 3)
+    src, dst = b.node[b.edge_index[0]], b.node[b.edge_index[1]]
+    assert torch.all(((src - dst) % N == 1) | ((src - dst) % N == 2))
+  loader.shutdown()
+  d.barrier()
+  d.shutdown_rpc()
+
+
+def test_dist_table_dataset():
+  with tempfile.TemporaryDirectory() as out:
+    run_workers(_w_dist_table, args=(out,), timeout=300)
