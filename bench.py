@@ -225,7 +225,8 @@ def run_ours(args):
   eng.warmup_and_capture(n_eager=2)
   if args.sections:
     eng._graphs = []
-    sec = eng.profile_sections(pool[:bs].to(device), iters=10)
+    nb = max(1, min(12, pool.numel() // bs))
+    sec = eng.profile_sections(pool[:nb * bs].view(nb, bs).to(device), iters=10)
     t = torch.tensor([sec[k] for k in sorted(sec)], device=device)
     if world > 1:
       dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -834,6 +834,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("zero_rows", &zero_rows);
   m.def("sage_fused", &sage_fused);
   m.def("sage_fused_supported", &sage_fused_supported);
+  m.def("sage_fused_trace", []() {
+    // [148, 32] int64 clock64 timeline of the last fused launch made with GLT_B200_FUSED_TRACE=1
+    Tensor t = torch::zeros({148, kFusedTraceSlots}, torch::kInt64);
+    sage_fused_trace_copy(reinterpret_cast<unsigned long long*>(t.data_ptr<int64_t>()));
+    return t;
+  });
   py::class_<PeerBuffer, std::shared_ptr<PeerBuffer>>(m, "PeerBuffer")
       .def_static("allocate", &PeerBuffer::allocate)
       .def_static("open", &PeerBuffer::open)

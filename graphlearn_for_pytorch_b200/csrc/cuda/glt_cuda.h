@@ -207,8 +207,12 @@ struct SageFusedArgs {
   int relu;
   void* z;                      // bf16 [cap_targets, N]
   void* a_save;                 // optional bf16 [cap_targets, 2d] for backward
+  unsigned long long* trace;    // optional per-CTA clock64 timeline (diagnostics, see sage_fused_trace)
 };
 int sage_fused_supported(int d, int n_out);
+// Copies the per-CTA timeline of the last traced launch (GLT_B200_FUSED_TRACE=1) to `host` [148*32].
+void sage_fused_trace_copy(unsigned long long* host);
+constexpr int kFusedTraceSlots = 32;
 void launch_sage_fused(const SageFusedArgs& a, int num_sms, cudaStream_t s);
 // W [N, K] row-major bf16 -> packed swizzled image used by launch_sage_fused.
 void launch_pack_weight(const void* w, int n, int k, void* packed, cudaStream_t s);

@@ -14,6 +14,7 @@ from typing import List, Optional
 import torch
 
 from ..utils.device import get_available_device
+from ..parallel.peer import IpcCudaTensor
 from .unified_tensor import UnifiedTensor
 
 
@@ -110,12 +111,12 @@ class Feature(object):
         for i, dev in enumerate(group.device_list):
           part = hot_rows[i * per: min((i + 1) * per, hot)]
           if part.shape[0] > 0:
-            shards.append(part.to(torch.device('cuda', dev)))
+            shards.append(IpcCudaTensor.from_tensor(part, dev))
         self._cuda_parts_by_group[group.group_id] = shards
       if self._group.group_id not in self._cuda_parts_by_group:
-        self._cuda_parts_by_group[self._group.group_id] = [hot_rows.to(torch.device('cuda', self.device))]
+        self._cuda_parts_by_group[self._group.group_id] = [IpcCudaTensor.from_tensor(hot_rows, self.device)]
       for shard in self._cuda_parts_by_group[self._group.group_id]:
-        ut.append_shared_tensor(shard)
+        ut.append_shared_tensor(shard.local(self.device))
     if hot < n:
       self._cpu_part = self.feature_tensor[hot:]
       ut.append_cpu_tensor(self._cpu_part)
@@ -123,7 +124,8 @@ class Feature(object):
 
   # ------------------------------------------------------------------ IPC
   def share_ipc(self):
-    """Handle for spawned processes: GPU shards travel as CUDA IPC, host part as shm."""
+    """Handle for spawned processes: GPU shards travel as raw CUDA IPC handles that the consumer
+    maps on ITS device (parallel/peer.py IpcCudaTensor), the host part as shared memory."""
     with self._lock:
       if self._ipc_handle is not None:
         return self._ipc_handle
@@ -161,7 +163,7 @@ class Feature(object):
     if shards is None and parts_by_group:
       shards = next(iter(parts_by_group.values()))
     for s in shards or []:
-      ut.append_shared_tensor(s)
+      ut.append_shared_tensor(s.local(self.device))
     if cpu is not None:
       self._cpu_part = cpu
       ut.append_cpu_tensor(cpu)

@@ -141,6 +141,18 @@ class Topology(object):
     setattr(self, key, value)
 
 
+def _page_lock(t: torch.Tensor) -> torch.Tensor:
+  """Make a host tensor readable by kernels in place.  A shared-memory tensor (a Graph that
+  travelled to a spawned process) is registered where it is, so N processes keep ONE copy."""
+  if t.is_pinned():
+    return t
+  if t.is_shared() and t.numel() > 0:
+    err = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), t.numel() * t.element_size(), 0)
+    if int(err) == 0:
+      return t
+  return t.pin_memory()
+
+
 class Graph(object):
   """A topology placed for sampling.
 
@@ -204,10 +216,9 @@ class Graph(object):
         eids_d = eids.to(dev) if eids is not None else None
         w_d = w.to(dev) if w is not None else None
       else:  # ZERO_COPY: page-lock and read in place
-        indptr_d = indptr if indptr.is_pinned() else indptr.pin_memory()
-        indices_d = indices if indices.is_pinned() else indices.pin_memory()
-        eids_d = (eids if eids.is_pinned() else eids.pin_memory()) if eids is not None else None
-        w_d = (w if w.is_pinned() else w.pin_memory()) if w is not None else None
+        indptr_d, indices_d = _page_lock(indptr), _page_lock(indices)
+        eids_d = _page_lock(eids) if eids is not None else None
+        w_d = _page_lock(w) if w is not None else None
       h.add_shard(indptr_d, indices_d, eids_d, w_d, 0, indptr.numel() - 1)
       self._handle = h
 

@@ -32,6 +32,8 @@ class UnifiedTensor(object):
     self._part_devices: List[int] = []
     self._handle = None
     self._cpu_part: Optional[torch.Tensor] = None
+    self._ipc_parts = None
+    self._keep_ipc = []
 
   # ------------------------------------------------------------------ build
   def _table(self):
@@ -122,15 +124,33 @@ class UnifiedTensor(object):
 
   # ------------------------------------------------------------------ IPC
   def share_ipc(self):
-    """(list of CUDA parts [torch shares them through CUDA IPC on pickling], cpu part)."""
-    cuda_parts = [p for p, d in zip(self._parts, self._part_devices) if d >= 0]
+    """(picklable GPU parts, shared-memory host part).
+
+    GPU parts are re-homed once into cudaMalloc'ed IPC segments (parallel/peer.py
+    IpcCudaTensor): the consumer process maps them on ITS OWN device, which is what lets a
+    kernel on GPU k read a shard that lives on GPU j of another process.
+    """
+    from ..parallel.peer import IpcCudaTensor
+    if self._ipc_parts is None:
+      ipc_parts = []
+      for i, (p, d) in enumerate(zip(self._parts, self._part_devices)):
+        if d < 0:
+          continue
+        h = IpcCudaTensor.from_tensor(p, d)
+        self._parts[i] = h.local(self.current_device)  # drop the duplicate copy
+        ipc_parts.append(h)
+      self._ipc_parts = ipc_parts
+      self._handle = None
     cpu = self._cpu_part
     if cpu is not None and not cpu.is_shared():
       cpu = cpu.clone().share_memory_()
-    return cuda_parts, cpu
+    return self._ipc_parts, cpu
 
   def from_ipc_handle(self, cuda_ipc_list, cpu_part):
     for t in cuda_ipc_list:
+      if not isinstance(t, torch.Tensor):
+        self._keep_ipc.append(t)
+        t = t.local(self.current_device)
       self.append_shared_tensor(t)
     if cpu_part is not None:
       self.append_cpu_tensor(cpu_part)

@@ -600,8 +600,11 @@ class GraphSageEngine(object):
     names = ['sample', 'forward_l1', 'forward_rest', 'backward', 'optimizer']
     acc = {n: 0.0 for n in names}
     self._cur = 0
-    self._stage_seeds(self._seeds[0], seeds)
+    # `seeds` may hold several batches ([n_batches, batch]): rotating them keeps the feature rows
+    # of every iteration cold in L2, like a real epoch
+    batches = seeds if seeds.dim() == 2 else seeds.unsqueeze(0)
     for it in range(iters + 2):
+      self._stage_seeds(self._seeds[0], batches[it % batches.shape[0]])
       ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
       ev[0].record()
       self._sample(0); ev[1].record()

@@ -68,3 +68,72 @@ def range_bounds(num_rows: int, world: int) -> List[int]:
   """Contiguous, near-equal row ranges: owner(v) is arithmetic / a tiny scan in-kernel."""
   per = (num_rows + world - 1) // world
   return [min(r * per, num_rows) for r in range(world + 1)]
+
+
+# --------------------------------------------------------------------------- picklable HBM
+_OWNED = {}  # handle bytes -> IpcCudaTensor owned by this process (a process cannot open its own handle)
+
+
+class IpcCudaTensor(object):
+  """A CUDA tensor that can be handed to *another process running on another GPU*.
+
+  torch's own CUDA-IPC pickling re-opens the allocation in the exporter device's context,
+  which kernels of a different GPU cannot dereference.  Here the rows live in a
+  cudaMalloc'ed PeerBuffer; the pickle carries the raw cudaIpcMemHandle and the consumer
+  maps it **on the device that will read it** with lazy peer access, so the UnifiedTensor
+  gather kernel can chase the pointer over NVLink.  Reference counterpart:
+  csrc/cuda/unified_tensor.cu:168-199 (ShareCUDAIpc) and :367-381 (InitFrom handles).
+  """
+
+  def __init__(self, meta, owner_buf=None, owner_tensor=None):
+    self._meta = meta  # (handle, nbytes, dtype_name, shape, owner_device, owner_pid)
+    self._buf = owner_buf
+    self._tensor = owner_tensor
+    self._opened = {}
+
+  @classmethod
+  def from_tensor(cls, t: torch.Tensor, device: int) -> 'IpcCudaTensor':
+    import os
+    nat = require_native()
+    device = int(device)
+    t = t.contiguous()
+    nbytes = t.numel() * t.element_size()
+    buf = nat.PeerBuffer.allocate(device, nbytes)
+    own = buf.as_tensor(t.dtype, list(t.shape))
+    own.copy_(t)
+    torch.cuda.synchronize(device)
+    meta = (buf.handle(), nbytes, str(t.dtype).split('.')[-1], list(t.shape), device, os.getpid())
+    self = cls(meta, buf, own)
+    _OWNED[meta[0]] = self
+    return self
+
+  @property
+  def owner_device(self) -> int:
+    return self._meta[4]
+
+  @property
+  def shape(self):
+    return self._meta[3]
+
+  def local(self, device: int) -> torch.Tensor:
+    """A tensor usable by kernels launched on `device`."""
+    import os
+    device = int(device)
+    if self._tensor is not None:  # owner process: plain cudaMalloc memory + peer access
+      if device != self.owner_device:
+        require_native().enable_peer_access(device, self.owner_device)
+      return self._tensor
+    handle, nbytes, dtype_s, shape, _, owner_pid = self._meta
+    if owner_pid == os.getpid():
+      owner = _OWNED.get(handle)
+      if owner is None:
+        raise RuntimeError('IPC handle exported by this process but its owner was released')
+      return owner.local(device)
+    if device not in self._opened:
+      nat = require_native()
+      buf = nat.PeerBuffer.open(handle, device, nbytes)
+      self._opened[device] = (buf, buf.as_tensor(getattr(torch, dtype_s), shape))
+    return self._opened[device][1]
+
+  def __reduce__(self):
+    return (IpcCudaTensor, (self._meta,))
