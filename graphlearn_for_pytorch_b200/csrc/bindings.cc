@@ -220,7 +220,7 @@ struct DeviceTable {
     Tensor counters = torch::zeros({16}, o32);
     BatchCounters c{counters.data_ptr<int32_t>(), counters.data_ptr<int32_t>() + 6, cursor.data_ptr<int32_t>(), nullptr};
     launch_init_seeds(k.data_ptr<int64_t>(), k.numel(), nullptr, ht, nodes.data_ptr<int64_t>(),
-                      out.data_ptr<int32_t>(), scratch.data_ptr<int32_t>(), c, cur_stream());
+                      out.data_ptr<int32_t>(), scratch.data_ptr<int32_t>(), c, nullptr, 0, cur_stream());
     check_cuda_err("table init_ordered");
     return out;
   }
@@ -309,7 +309,7 @@ struct SamplerArena {
   }
 
   void sample(GraphHandle& g, const Tensor& seeds, const c10::optional<Tensor>& n_dev, int64_t seed,
-              int64_t stream_base, bool weighted, bool replace, bool use_dev_step) {
+              int64_t stream_base, bool weighted, bool replace, bool use_dev_step, int64_t step_inc) {
     c10::cuda::CUDAGuard guard(device);
     TORCH_CHECK(seeds.is_cuda() && seeds.scalar_type() == torch::kInt64 && seeds.is_contiguous());
     TORCH_CHECK(seeds.numel() <= max_seeds, "more seeds than the arena was built for");
@@ -319,7 +319,9 @@ struct SamplerArena {
     launch_table_clear(table->ht, s);
     const int32_t* nd = (n_dev.has_value() && n_dev->defined()) ? n_dev->data_ptr<int32_t>() : nullptr;
     launch_init_seeds(seeds.data_ptr<int64_t>(), seeds.numel(), nd, table->ht, nodes.data_ptr<int64_t>(),
-                      seed_local.data_ptr<int32_t>(), scratch.data_ptr<int32_t>(), bc(), s);
+                      seed_local.data_ptr<int32_t>(), scratch.data_ptr<int32_t>(), bc(),
+                      (use_dev_step && step_inc != 0) ? step.data_ptr<int32_t>() : nullptr,
+                      static_cast<int>(step_inc), s);
     for (size_t h = 0; h < fanouts.size(); ++h) {
       HopArgs a{};
       a.g = g.tbl;
@@ -558,6 +560,8 @@ static void adam_step(Tensor p, const Tensor& g, Tensor m, Tensor v, const c10::
                       double lr, double b1, double b2, double eps, double wd, const Tensor& step_dev,
                       double gscale) {
   c10::cuda::CUDAGuard guard(p.device());
+  TORCH_CHECK(step_dev.scalar_type() == torch::kInt32 && step_dev.numel() >= 2,
+              "step_dev must be int32[2]: {steps taken, block ticket}");
   launch_adam(p.data_ptr<float>(), g.data_ptr<float>(), m.data_ptr<float>(), v.data_ptr<float>(),
               (p_bf16.has_value() && p_bf16->defined()) ? p_bf16->data_ptr() : nullptr, p.numel(), lr,
               b1, b2, eps, wd, step_dev.data_ptr<int32_t>(), gscale, cur_stream());
@@ -701,6 +705,8 @@ struct PeerGroup {
             double eps, double wd, const Tensor& step_dev, double gscale) {
     c10::cuda::CUDAGuard guard(device);
     TORCH_CHECK(param.numel() % 4 == 0, "flat parameter buffer must be padded to a multiple of 4");
+    TORCH_CHECK(step_dev.scalar_type() == torch::kInt32 && step_dev.numel() >= 2,
+                "step_dev must be int32[2]: {steps taken, block ticket}");
     launch_adam_peer(p, param.data_ptr<float>(), m.data_ptr<float>(), v.data_ptr<float>(),
                      (p_bf16.has_value() && p_bf16->defined()) ? p_bf16->data_ptr() : nullptr, param.numel(), lr,
                      b1, b2, eps, wd, step_dev.data_ptr<int32_t>(), gscale, cur_stream());
@@ -801,7 +807,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def(py::init<int, int64_t, std::vector<int64_t>, bool, int64_t, std::vector<int64_t>>(), py::arg("device"),
            py::arg("max_seeds"), py::arg("fanouts"), py::arg("with_edge"), py::arg("num_graph_nodes"),
            py::arg("cap_override") = std::vector<int64_t>{})
-      .def("sample", &SamplerArena::sample)
+      .def("sample", &SamplerArena::sample, py::arg("graph"), py::arg("seeds"), py::arg("n_dev"), py::arg("seed"),
+           py::arg("stream_base"), py::arg("weighted"), py::arg("replace"), py::arg("use_dev_step"),
+           py::arg("step_inc") = 0)
       .def("to_coo", &SamplerArena::to_coo)
       .def_readonly("nodes", &SamplerArena::nodes)
       .def_readonly("deg", &SamplerArena::deg)

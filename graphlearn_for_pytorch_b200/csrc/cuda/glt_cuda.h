@@ -64,7 +64,7 @@ void launch_table_clear(HashTable t, cudaStream_t s);
 // seed_local[i] (local id of seeds[i]), cum[0]=0, cum[1]=n0, cursor=n0.
 void launch_init_seeds(const int64_t* seeds, int n_seeds, const int32_t* n_seeds_dev,
                        HashTable t, int64_t* nodes, int32_t* seed_local, int32_t* scratch,
-                       BatchCounters c, cudaStream_t s);
+                       BatchCounters c, int32_t* step_dev, int step_inc, cudaStream_t s);
 
 struct HopArgs {
   GraphTable g;
@@ -183,7 +183,7 @@ void launch_colsum_bf16(const void* X, const int32_t* cum, int n_hops, int cap, 
 void launch_zero_rows(float* p, const int32_t* cum, int n_hops, int cap, int d, cudaStream_t s);
 // flat fp32 Adam over [n] with bf16 shadow copy refresh.
 void launch_adam(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr,
-                 float b1, float b2, float eps, float wd, const int32_t* step_dev, float gscale,
+                 float b1, float b2, float eps, float wd, int32_t* step_dev, float gscale,
                  cudaStream_t s);
 void launch_bf16_to_f32(const void* src, float* dst, int64_t n, cudaStream_t s);
 
@@ -195,7 +195,7 @@ struct PeerPtrs {
 };
 void launch_peer_barrier(const PeerPtrs& p, int which, int32_t* epoch_dev, int32_t* err, cudaStream_t s);
 void launch_adam_peer(const PeerPtrs& p, float* param, float* m, float* v, void* p_bf16, int64_t n, float lr,
-                      float b1, float b2, float eps, float wd, const int32_t* step_dev, float gscale,
+                      float b1, float b2, float eps, float wd, int32_t* step_dev, float gscale,
                       cudaStream_t s);
 
 // ---- sage_tc.cu (tcgen05 fused gather+aggregate+GEMM) -------------------------

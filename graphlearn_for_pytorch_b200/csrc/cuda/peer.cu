@@ -58,8 +58,9 @@ __device__ __forceinline__ float4 ld_cv4(const float* p) {
 
 __global__ void __launch_bounds__(256) k_adam_peer(PeerPtrs p, float* param, float* m, float* v,
                                                    __nv_bfloat16* pb, int64_t n, float lr, float b1, float b2,
-                                                   float eps, float wd, const int32_t* step_dev, float gscale) {
-  const float t = static_cast<float>(*step_dev);
+                                                   float eps, float wd, int32_t* step_dev, float gscale) {
+  // t = steps so far + 1; the last block to finish publishes it (see k_adam)
+  const float t = static_cast<float>(*reinterpret_cast<volatile int32_t*>(step_dev) + 1);
   const float c1 = 1.f - __powf(b1, t), c2 = 1.f - __powf(b2, t);
   const int64_t n4 = n >> 2;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
@@ -91,6 +92,14 @@ __global__ void __launch_bounds__(256) k_adam_peer(PeerPtrs p, float* param, flo
       o[1] = __floats2bfloat162_rn(pa[2], pa[3]);
     }
   }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(step_dev + 1, 1) == static_cast<int>(gridDim.x) - 1) {
+      step_dev[1] = 0;
+      step_dev[0] += 1;
+    }
+  }
 }
 
 }  // namespace
@@ -100,7 +109,7 @@ void launch_peer_barrier(const PeerPtrs& p, int which, int32_t* epoch_dev, int32
 }
 
 void launch_adam_peer(const PeerPtrs& p, float* param, float* m, float* v, void* p_bf16, int64_t n, float lr,
-                      float b1, float b2, float eps, float wd, const int32_t* step_dev, float gscale,
+                      float b1, float b2, float eps, float wd, int32_t* step_dev, float gscale,
                       cudaStream_t s) {
   int64_t blocks = ((n >> 2) + 255) / 256;
   if (blocks > 148 * 4) blocks = 148 * 4;

@@ -264,10 +264,13 @@ __global__ void k_softmax_nll(const __nv_bfloat16* logits, int ld, int C, const 
   }
 }
 
+// step_dev[0] = number of optimizer steps taken so far, step_dev[1] = block ticket.  The kernel
+// uses t = step + 1 and the LAST block to finish publishes it (every block has read the old
+// value by then), which saves the separate `step += 1` launch.
 __global__ void k_adam(float* p, const float* g, float* m, float* v, __nv_bfloat16* pb, int64_t n,
-                       float lr, float b1, float b2, float eps, float wd, const int32_t* step_dev,
+                       float lr, float b1, float b2, float eps, float wd, int32_t* step_dev,
                        float gscale) {
-  const float t = static_cast<float>(*step_dev);
+  const float t = static_cast<float>(*reinterpret_cast<volatile int32_t*>(step_dev) + 1);
   const float c1 = 1.f - __powf(b1, t), c2 = 1.f - __powf(b2, t);
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -279,6 +282,14 @@ __global__ void k_adam(float* p, const float* g, float* m, float* v, __nv_bfloat
     const float pi = p[i] - lr * upd;
     p[i] = pi;
     if (pb) pb[i] = __float2bfloat16(pi);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(step_dev + 1, 1) == static_cast<int>(gridDim.x) - 1) {
+      step_dev[1] = 0;
+      step_dev[0] += 1;
+    }
   }
 }
 
@@ -383,7 +394,7 @@ void launch_softmax_nll(const void* logits, int ld, int C, const int64_t* y, con
 }
 
 void launch_adam(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr,
-                 float b1, float b2, float eps, float wd, const int32_t* step_dev, float gscale,
+                 float b1, float b2, float eps, float wd, int32_t* step_dev, float gscale,
                  cudaStream_t s) {
   k_adam<<<grid_for(n, 256, 148 * 4), 256, 0, s>>>(p, g, m, v, reinterpret_cast<__nv_bfloat16*>(p_bf16),
                                                    n, lr, b1, b2, eps, wd, step_dev, gscale);

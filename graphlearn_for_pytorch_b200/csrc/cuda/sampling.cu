@@ -193,9 +193,13 @@ __global__ void k_relabel_hop(HopArgs a) {
 __global__ void __launch_bounds__(1024) k_init_seeds(const int64_t* seeds, int n_host,
                                                      const int32_t* n_dev, HashTable t,
                                                      int64_t* nodes, int32_t* seed_local,
-                                                     int32_t* slot_of, BatchCounters c, int max_hops) {
+                                                     int32_t* slot_of, BatchCounters c, int max_hops,
+                                                     int32_t* step_dev, int step_inc) {
   __shared__ int s_warp[32];
   __shared__ int s_running;
+  // first kernel of a batch: advance the device-side Philox step here instead of paying a
+  // separate elementwise launch (the hop kernels that follow read the new value)
+  if (threadIdx.x == 0 && step_dev) *step_dev += step_inc;
   const int n = n_dev ? min(*n_dev, n_host) : n_host;
   const int tid = threadIdx.x;
   // 1a: claim slots; the claimer seeds aux with its own index
@@ -384,8 +388,9 @@ void launch_table_clear(HashTable t, cudaStream_t s) {
 
 void launch_init_seeds(const int64_t* seeds, int n_seeds, const int32_t* n_seeds_dev, HashTable t,
                        int64_t* nodes, int32_t* seed_local, int32_t* scratch, BatchCounters c,
-                       cudaStream_t s) {
-  k_init_seeds<<<1, 1024, 0, s>>>(seeds, n_seeds, n_seeds_dev, t, nodes, seed_local, scratch, c, 4);
+                       int32_t* step_dev, int step_inc, cudaStream_t s) {
+  k_init_seeds<<<1, 1024, 0, s>>>(seeds, n_seeds, n_seeds_dev, t, nodes, seed_local, scratch, c, 4, step_dev,
+                                  step_inc);
 }
 
 #define GLT_DISPATCH_FANOUT(K, ...)                                  \

@@ -170,7 +170,7 @@ class GraphSageEngine(object):
       self._primed = False
       self.loss = torch.zeros(1, dtype=f32, device=dev)
       self.correct = torch.zeros(1, dtype=torch.int32, device=dev)
-      self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+      self.step_dev = torch.zeros(2, dtype=torch.int32, device=dev)   # {steps taken, block ticket}
       self._autotune_fused = (use_fused == 'auto')
       self.fused_ok = [False] + [bool(use_fused and self.nat.sage_fused_supported(self.dims_in[l - 1],
                                                                                     self.dims_out[l - 1]))
@@ -292,13 +292,14 @@ class GraphSageEngine(object):
 
   def state_dict(self):
     return {'p32': self.p32.clone(), 'm': self.m.clone(), 'v': self.v.clone(),
-            'step': int(self.step_dev.item()), 'sample_step': [int(a.step.item()) for a in self._arenas],
+            'step': int(self.step_dev[0].item()), 'sample_step': [int(a.step.item()) for a in self._arenas],
             'step_idx': self.step_idx, 'seed': self.seed}
 
   def load_state_dict(self, s):
     self.p32.copy_(s['p32']); self.m.copy_(s['m']); self.v.copy_(s['v'])
     self.p16.copy_(self.p32)
-    self.step_dev.fill_(s['step'])
+    self.step_dev.zero_()
+    self.step_dev[0] = int(s['step'])
     ss = s.get('sample_step', None)
     if ss is not None:
       for a, v in zip(self._arenas, ss if isinstance(ss, (list, tuple)) else [ss]):
@@ -322,9 +323,9 @@ class GraphSageEngine(object):
     # CUDA-graph replay draws fresh samples every step
     which = self._cur if which is None else which
     ar = self._arenas[which]
-    ar.step.add_(len(self._arenas))
-    ar.sample(self.gh, self._seeds[which], None, self.seed, 0, False, False, True)
-    self._k(2 + 2 * self.L)  # memset + init_seeds + (sample, relabel) per hop
+    # (the increment itself is folded into the first sampling kernel: step_inc)
+    ar.sample(self.gh, self._seeds[which], None, self.seed, 0, False, False, True, len(self._arenas))
+    self._k(2 + 2 * self.L)  # table clear + init_seeds + (sample, relabel) per hop
 
   def _forward(self):
     nat, ar = self.nat, self.arena
@@ -346,9 +347,13 @@ class GraphSageEngine(object):
       self._k(1)
     else:
       nat.sage_aggregate(feat, nodes, src_local, d, ar.counters, nh, ell, ks, ar.deg, self.A[l])
-      torch.mm(self.A[l], self.W(l).t(), out=self.Z[l])
-      nat.bias_relu(self.Z[l], self.b(l), ar.counters, nh, relu)
-      self._k(2)
+      # library GEMM with the bias (+ ReLU) applied in the cuBLASLt epilogue: no separate
+      # elementwise pass over Z
+      if relu:
+        torch._addmm_activation(self.b(l), self.A[l], self.W(l).t(), out=self.Z[l])
+      else:
+        torch.addmm(self.b(l), self.A[l], self.W(l).t(), out=self.Z[l])
+      self._k(1)
 
   def _forward_loss(self):
     # labels[nodes[r]] is looked up inside the loss kernel (no gather launch)
@@ -405,7 +410,7 @@ class GraphSageEngine(object):
       out.copy_(torch.mm(a, b))
 
   def _optimizer(self):
-    self.step_dev.add_(1)
+    # Adam's step counter is advanced by the kernel itself (last block to finish)
     if self.peer_group is not None:
       pg = self._peer_groups[self._cur % len(self._peer_groups)]
       pg.barrier(0)                       # every rank finished writing its gradients

@@ -166,13 +166,13 @@ def test_softmax_nll_and_adam(native):
   assert Y[:257].abs().sum() == 0 and Y[257:].sum() == 43 * 64
   p = torch.randn(1000, device=DEV); g = torch.randn(1000, device=DEV)
   p_ref = p.clone().requires_grad_(True); opt = torch.optim.Adam([p_ref], lr=1e-2)
-  m = torch.zeros_like(p); v = torch.zeros_like(p); p16 = p.to(torch.bfloat16); step = torch.zeros(1, dtype=torch.int32, device=DEV)
+  m = torch.zeros_like(p); v = torch.zeros_like(p); p16 = p.to(torch.bfloat16); step = torch.zeros(2, dtype=torch.int32, device=DEV)
   for _ in range(3):
-    step += 1
     native.adam_step(p, g, m, v, p16, 1e-2, 0.9, 0.999, 1e-8, 0.0, step, 1.0)
     p_ref.grad = g.clone(); opt.step()
   assert torch.allclose(p, p_ref.detach(), atol=1e-5)
   assert torch.allclose(p16.float(), p, atol=2e-2)
+  assert step.tolist() == [3, 0]   # the kernel advances its own step counter (last block publishes)
 
 
 @pytest.mark.parametrize('graph', [False, True])
