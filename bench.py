@@ -129,6 +129,8 @@ def setup_dist(args):
   torch.cuda.set_device(local_rank)
   if world > 1:
     os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+    # stdout carries exactly one JSON line: NCCL's banner / debug lines go to stderr
+    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
     dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
   return rank, world, local_rank
 

@@ -131,12 +131,16 @@ class Feature(object):
         return self._ipc_handle
       if self.with_gpu:
         self.lazy_init()
-        cpu = self._cpu_part
-        if cpu is not None and not cpu.is_shared():
-          cpu = cpu.clone().share_memory_()
+        # Share the full matrix first: the cold part is a view of it and becomes shared with it.
+        # Nothing temporary may be created here -- while a Process is being spawned the pickler
+        # hands file descriptors over by NUMBER, so a shared tensor that is collected before the
+        # spawn leaves a recycled fd behind ("unable to resize file" in the child).
         full = self.feature_tensor
         if full is not None and not full.is_shared():
-          full = full.share_memory_()
+          full.share_memory_()
+        cpu = self._cpu_part
+        if cpu is not None and not cpu.is_shared():
+          self._cpu_part = cpu = cpu.clone().share_memory_()
         if self.id2index is not None:
           self.id2index = self.id2index.cpu().share_memory_()
         return (self._cuda_parts_by_group, cpu, full, self.id2index, self.split_ratio,

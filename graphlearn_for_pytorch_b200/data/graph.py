@@ -16,6 +16,8 @@ from typing import List, Literal, Optional, Tuple, Union
 
 import torch
 
+from ..utils.tensor import page_lock_in_place
+
 from ..ops import require_native
 from ..typing import TensorDataType
 from ..utils.tensor import convert_to_tensor, share_memory
@@ -146,10 +148,8 @@ def _page_lock(t: torch.Tensor) -> torch.Tensor:
   travelled to a spawned process) is registered where it is, so N processes keep ONE copy."""
   if t.is_pinned():
     return t
-  if t.is_shared() and t.numel() > 0:
-    err = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), t.numel() * t.element_size(), 0)
-    if int(err) == 0:
-      return t
+  if t.is_shared() and t.numel() > 0 and page_lock_in_place(t):
+    return t
   return t.pin_memory()
 
 

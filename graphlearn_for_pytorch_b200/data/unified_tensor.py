@@ -10,6 +10,7 @@ from typing import List, Optional
 import torch
 
 from ..ops import require_native
+from ..utils.tensor import page_lock_in_place
 
 
 def _enable_peer(cur: int, other: int):
@@ -33,6 +34,7 @@ class UnifiedTensor(object):
     self._handle = None
     self._cpu_part: Optional[torch.Tensor] = None
     self._ipc_parts = None
+    self._ipc_cpu = None
     self._keep_ipc = []
 
   # ------------------------------------------------------------------ build
@@ -64,10 +66,8 @@ class UnifiedTensor(object):
     self._cpu_part = t
     if torch.cuda.is_available():
       if not t.is_pinned():
-        if t.is_shared():
-          # keep the shared-memory mapping (other processes see the same rows)
-          torch.cuda.cudart().cudaHostRegister(t.data_ptr(), t.numel() * t.element_size(), 0)
-        else:
+        # a shared-memory part keeps its mapping (all processes read the same physical rows)
+        if not (t.is_shared() and page_lock_in_place(t)):
           t = t.pin_memory()
     self._append(t, -1)
 
@@ -141,9 +141,14 @@ class UnifiedTensor(object):
         ipc_parts.append(h)
       self._ipc_parts = ipc_parts
       self._handle = None
+    # NB: anything created here must stay referenced by `self`: when a Process is being spawned
+    # the pickler passes file descriptors by NUMBER (inheritance), so a temporary shared tensor
+    # that is collected before the spawn leaves a dangling / recycled fd behind.
     cpu = self._cpu_part
     if cpu is not None and not cpu.is_shared():
-      cpu = cpu.clone().share_memory_()
+      if self._ipc_cpu is None:
+        self._ipc_cpu = cpu.clone().share_memory_()
+      cpu = self._ipc_cpu
     return self._ipc_parts, cpu
 
   def from_ipc_handle(self, cuda_ipc_list, cpu_part):

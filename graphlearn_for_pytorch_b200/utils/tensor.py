@@ -60,3 +60,20 @@ def share_memory(data: Any):
 
 def squeeze(data: Any):
   return apply_to_all_tensor(data, lambda t: t.squeeze())
+
+
+def page_lock_in_place(t: torch.Tensor) -> bool:
+  """cudaHostRegister the storage behind a (shared-memory) host tensor so kernels can read it where
+  it is.  Registers the WHOLE storage (page-aligned mapping base), tolerates "already registered".
+  Returns False when the driver refuses -- the caller then falls back to a pinned copy."""
+  if t.is_pinned():
+    return True
+  st = t.untyped_storage()
+  if st.nbytes() == 0:
+    return False
+  err = int(torch.cuda.cudart().cudaHostRegister(st.data_ptr(), st.nbytes(), 0))
+  if err not in (0, 712):   # 712 = cudaErrorHostMemoryAlreadyRegistered
+    import warnings
+    warnings.warn(f'cudaHostRegister failed with error {err}; using a pinned copy instead')
+    return False
+  return bool(t.is_pinned())

@@ -61,15 +61,53 @@ def main():
   topo = glt.data.Topology(torch.stack([row, col]), layout='CSC')
   graph = glt.data.Graph(topo, 'ZERO_COPY', 0)
 
+  mode = os.environ.get('IPC_MODE', 'conc')          # conc | seq   (debug knobs)
+  objs = os.environ.get('IPC_OBJS', 'all')           # all | feat | graph | ut | plain
+  if os.environ.get('IPC_PRESHARE', '0') == '1':
+    feat.share_ipc(); graph.share_ipc()
+  if objs != 'all':
+    small = glt.data.Feature(x[perm][:64].clone(), None, split_ratio=0.5, device=0)
+    small[torch.arange(4)]
+    if objs != 'feat':
+      feat = small
+    if objs != 'graph':
+      graph = glt.data.Graph(glt.data.Topology(torch.stack([row[:64] % 64, col[:64] % 64]), layout='CSC'), 'CPU', 0)
+    if objs != 'ut':
+      u2 = glt.data.UnifiedTensor(0, torch.float32); u2.init_from([x[:8], x[8:16]], [0, -1]); ut_handle = u2.share_ipc()
   ctx = mp.get_context('spawn')
   q = ctx.Queue()
   procs = [ctx.Process(target=_reader, args=(r, feat, graph, ut_handle, devices, ids, x[ids], q))
            for r in range(2)]
-  for p in procs:
-    p.start()
-  res = [q.get(timeout=120) for _ in procs]
+  import queue as _queue
+  import time
+
+  def wait_results(ps, n):
+    out, t0 = [], time.time()
+    while len(out) < n and time.time() - t0 < 100:
+      try:
+        out.append(q.get(timeout=1))
+      except _queue.Empty:
+        dead = [p_ for p_ in ps if p_.exitcode not in (None, 0)]
+        if dead:   # a reader died before reporting (e.g. while unpickling its arguments)
+          raise RuntimeError(f'reader process exited with code {dead[0].exitcode} before reporting')
+    if len(out) < n:
+      raise RuntimeError('timed out waiting for the reader processes')
+    return out
+
+  res = []
+  if mode == 'seq':
+    for p in procs:
+      p.start()
+      res += wait_results([p], 1)
+  else:
+    for p in procs:
+      p.start()
+    res = wait_results(procs, len(procs))
   for p in procs:
     p.join(60)
+  if objs != 'all':
+    print('variant finished', mode, objs, [r[4][-300:] for r in res], flush=True)
+    return
   for rank, ok_feat, ok_ut, ok_graph, err in res:
     assert ok_feat and ok_ut and ok_graph, f'reader {rank}: feat={ok_feat} ut={ok_ut} graph={ok_graph}\n{err}'
 
