@@ -78,10 +78,79 @@ class Dataset(object):
     if node_split is not None:
       self.train_idx, self.val_idx, self.test_idx = squeeze(convert_to_tensor(node_split))
 
-  def load_vineyard(self, *args, **kwargs):
-    """GraphScope/vineyard ingestion is an optional plug-in (reference dataset.py:155-234);
-    vineyard is not available in this build."""
-    raise NotImplementedError('vineyard loader plug-in is not built (WITH_VINEYARD)')
+  def load_vineyard(self, vineyard_id: str, vineyard_socket: str, edges: List[EdgeType],
+                    edge_weights: Optional[Dict[EdgeType, str]] = None,
+                    node_features: Optional[Dict[NodeType, List[str]]] = None,
+                    edge_features: Optional[Dict[EdgeType, List[str]]] = None,
+                    node_labels: Optional[Dict[NodeType, str]] = None,
+                    graph_mode: str = 'CPU', with_gpu: bool = False, global_rows: bool = False):
+    """Build the dataset from one property-graph fragment (reference dataset.py:155-234).
+
+    `global_rows=True` re-keys the CSR and the labels by GLOBAL id (rows of other fragments are
+    empty / -1), which is what the distributed runtime addresses partitions with.
+
+    `vineyard_socket` selects the fragment backend (data/vineyard_utils.py: an Arrow fragment
+    directory, or a registered live-vineyard backend), `vineyard_id` the fragment.  Graph rows are
+    the fragment's inner vertices (local offsets), neighbour ids stay global; features are indexed
+    through `VineyardGid2Lid`.  The reference loads CPU-only (its TODO at dataset.py:165);
+    `graph_mode` / `with_gpu` let the caller place topology and hot rows in HBM right away.
+    """
+    from .vineyard_utils import (VineyardGid2Lid, _open, load_edge_feature_from_vineyard,
+                                 load_vertex_feature_from_vineyard, vineyard_to_csr)
+    is_homo = len(edges) == 1 and edges[0][0] == edges[0][2]
+    ei, eids, ew, layout = {}, {}, {}, {}
+    for et in edges:
+      key_ntype = et[0] if self.edge_dir == 'out' else et[2]
+      indptr, indices, eid = vineyard_to_csr(vineyard_socket, vineyard_id, key_ntype, et[1], self.edge_dir, True)
+      if global_rows:
+        fr = _open(vineyard_socket, vineyard_id)
+        off, total = fr.vertex_offset(key_ntype), int(fr.vertex_ranges(key_ntype)[-1])
+        indptr = torch.cat([indptr.new_zeros(off), indptr,
+                            indptr.new_full((total - off - (indptr.numel() - 1),), int(indptr[-1]))])
+      ei[et] = (indptr, indices) if self.edge_dir == 'out' else (indices, indptr)
+      eids[et] = eid
+      layout[et] = 'CSR' if self.edge_dir == 'out' else 'CSC'
+      if edge_weights and edge_weights.get(et):
+        w = load_edge_feature_from_vineyard(vineyard_socket, vineyard_id, [edge_weights[et]], et[1])
+        ew[et] = w.squeeze(1).float()[eid]      # edge-table order -> CSR order
+    if is_homo:
+      et = edges[0]
+      self.init_graph(edge_index=ei[et], edge_ids=eids[et], edge_weights=ew.get(et), layout=layout[et],
+                      graph_mode=graph_mode)
+    else:
+      self.init_graph(edge_index=ei, edge_ids=eids, edge_weights=ew or None, layout=layout,
+                      graph_mode=graph_mode)
+
+    def per_type(spec, loader, label_of=lambda k: k):
+      return {k: loader(vineyard_socket, vineyard_id, cols if isinstance(cols, (list, tuple)) else [cols],
+                        label_of(k)) for k, cols in spec.items()}
+
+    if node_features:
+      data = per_type(node_features, load_vertex_feature_from_vineyard)
+      frag = _open(vineyard_socket, vineyard_id)
+      id2idx = {nt: _gid2lid_tensor(VineyardGid2Lid(vineyard_socket, vineyard_id, nt),
+                                    int(frag.vertex_ranges(nt)[-1])) for nt in data}
+      if is_homo:
+        nt = edges[0][0]
+        data, id2idx = data[nt], id2idx[nt]
+      self.init_node_features(node_feature_data=data, id2idx=id2idx, with_gpu=with_gpu)
+    if edge_features:
+      data = per_type(edge_features, load_edge_feature_from_vineyard, label_of=lambda et: et[1])
+      if is_homo:
+        data = data[edges[0]]
+      self.init_edge_features(edge_feature_data=data, with_gpu=with_gpu)
+    if node_labels:
+      data = {nt: v.squeeze(1) for nt, v in per_type(node_labels, load_vertex_feature_from_vineyard).items()}
+      if global_rows:
+        fr = _open(vineyard_socket, vineyard_id)
+        for nt, v in list(data.items()):
+          full = v.new_full((int(fr.vertex_ranges(nt)[-1]),), -1)
+          full[fr.vertex_offset(nt):fr.vertex_offset(nt) + v.numel()] = v
+          data[nt] = full
+      if is_homo:
+        data = data[edges[0][0]]
+      self.init_node_labels(node_label_data=data)
+    self._vineyard = (vineyard_socket, vineyard_id)
 
   # ------------------------------------------------------------------ features
   def init_node_features(self, node_feature_data=None, id2idx=None,
@@ -211,6 +280,15 @@ def _build_features(feature_data, id2idx, split_ratio, device_group_list, device
   topo = topo_fn() if topo_fn is not None else None
   return _build_one(feature_data, id2idx, split_ratio, device_group_list, device, with_gpu, dtype,
                     sort_func, topo)
+
+
+def _gid2lid_tensor(g2l, total: int):
+  """Feature.id2index is a lookup tensor here (applied inside the gather kernel): materialise the
+  fragment's `gid - offset` map over all `total` gids, -1 for ids owned by other fragments."""
+  off, num = g2l._offset, len(g2l)
+  t = torch.full((max(total, off + num),), -1, dtype=torch.int64)
+  t[off:off + num] = torch.arange(num, dtype=torch.int64)
+  return t
 
 
 def random_split(num_total: int, num_val: Union[int, float], num_test: Union[int, float]):

@@ -82,6 +82,31 @@ class DistDataset(Dataset):
         self.init_node_labels(torch.load(whole_node_label_file))
     return self
 
+  def load_vineyard(self, vineyard_id: str, vineyard_socket: str, edges, edge_weights=None, node_features=None,
+                    edge_features=None, node_labels=None, graph_mode: str = 'CPU', feature_with_gpu: bool = False,
+                    fid2pid: Optional[Dict[int, int]] = None):
+    """One property-graph fragment per worker (reference dist_dataset.py:215-243): partition id =
+    fragment id, node partition books resolve gid -> fragment through the fragment store.  The
+    topology and labels are keyed by global id so that the RPC sampler / feature lookups address
+    them exactly like the partitions produced by the partitioners."""
+    from ..data import vineyard_utils as vu
+    frag = vu._open(vineyard_socket, vineyard_id)
+    self.num_partitions, self.partition_idx = frag.fnum, frag.fid
+    if fid2pid is not None:
+      self.partition_idx = int(fid2pid[frag.fid])
+    super().load_vineyard(vineyard_id, vineyard_socket, edges, edge_weights, node_features, edge_features,
+                          node_labels, graph_mode=graph_mode, with_gpu=feature_with_gpu, global_rows=True)
+    is_homo = len(edges) == 1 and edges[0][0] == edges[0][2]
+    ntypes = sorted({et[0] for et in edges} | {et[2] for et in edges})
+    books = {nt: vu.VineyardPartitionBook(vineyard_socket, vineyard_id, nt, fid2pid) for nt in ntypes}
+    self.node_pb = books[ntypes[0]] if is_homo else books
+    self.edge_pb = None
+    if node_features:
+      self._node_feat_pb = self.node_pb if is_homo else {nt: books[nt] for nt in node_features}
+    self.id_select = vu.v6d_id_select
+    self.id_filter = vu.v6d_id_filter
+    return self
+
   # ------------------------------------------------------------------ p2p
   @classmethod
   def from_p2p(cls, partitioned_graph, partitioned_feature=None, labels=None, edge_dir: str = 'out'):

@@ -272,3 +272,42 @@ def _w_dist_table(rank, world, port, out):
 def test_dist_table_dataset():
   with tempfile.TemporaryDirectory() as out:
     run_workers(_w_dist_table, args=(out,), timeout=300)
+
+
+def _w_vineyard_fragments(rank, world, port, root):
+  """Each worker loads ITS fragment of an Arrow fragment store (the GraphScope / vineyard path of
+  the reference: dist_dataset.py:215-243) and runs the RPC neighbor loader over it."""
+  import graphlearn_for_pytorch_b200.distributed as d
+  d.init_worker_group(world, rank)
+  ds = d.DistDataset(edge_dir='out')
+  ds.load_vineyard(f'ring_{rank}', root, [('v', 'e', 'v')], node_features={'v': ['feat']}, node_labels={'v': 'label'})
+  assert (ds.num_partitions, ds.partition_idx) == (world, rank)
+  ds.random_node_split(0.0, 0.0)
+  seeds = ds.train_idx
+  per = N // world
+  assert sorted(seeds.tolist()) == list(range(rank * per, (rank + 1) * per))
+  loader = d.DistNeighborLoader(ds, [2, 2], seeds, batch_size=5, shuffle=True, collect_features=True,
+                                to_device=torch.device('cpu'), random_seed=5,
+                                worker_options=d.CollocatedDistSamplingWorkerOptions(master_addr='127.0.0.1',
+                                                                                     master_port=port))
+  seen, foreign = [], 0
+  for b in loader:
+    assert torch.equal(b.x[:, 0].long(), b.node)
+    src, dst = b.node[b.edge_index[0]], b.node[b.edge_index[1]]
+    assert torch.all(((src - dst) % N == 1) | ((src - dst) % N == 2))
+    assert torch.equal(b.y[:b.batch_size], b.batch)     # labels of the (locally owned) seeds
+    foreign += int((b.node // per != rank).sum())
+    seen += b.batch.tolist()
+  assert sorted(seen) == sorted(seeds.tolist())
+  assert foreign > 0      # neighbourhoods cross into the other worker's fragment (served over RPC)
+  loader.shutdown()
+  d.barrier()
+  d.shutdown_rpc()
+
+
+def test_dist_loader_on_vineyard_fragments(tmp_path):
+  from graphlearn_for_pytorch_b200.data.vineyard_utils import write_arrow_fragments
+  from graphlearn_for_pytorch_b200.utils.synthetic import id_features, ring_graph
+  write_arrow_fragments(str(tmp_path), 'ring', 2, {'v': {'feat': id_features(N, 8), 'label': torch.arange(N)}},
+                        {'e': ('v', 'v', ring_graph(N), {})})
+  run_workers(_w_vineyard_fragments, args=(str(tmp_path),), timeout=300)
