@@ -3,6 +3,8 @@ from typing import Optional, Tuple, Union
 
 import torch
 
+from ..utils.tracing import nvtx_range
+
 from ..data import Dataset
 from ..sampler import BaseSampler, EdgeSamplerInput, NegativeSampling
 from ..typing import InputEdges
@@ -57,5 +59,7 @@ class LinkLoader(NodeLoader):
 
   def __next__(self):
     idx = next(self._seeds_iter)
-    out = self.sampler.sample_from_edges(self.input_data[idx])
-    return self._collate_fn(out)
+    with nvtx_range('glt.sample'):
+      out = self.sampler.sample_from_edges(self.input_data[idx])
+    with nvtx_range('glt.collate'):
+      return self._collate_fn(out)

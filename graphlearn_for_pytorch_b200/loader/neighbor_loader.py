@@ -3,6 +3,8 @@ from typing import Optional
 
 import torch
 
+from ..utils.tracing import nvtx_range
+
 from ..data import Dataset
 from ..sampler import NeighborSampler, NodeSamplerInput
 from ..typing import InputNodes, NumNeighbors
@@ -36,6 +38,9 @@ class NeighborLoader(NodeLoader):
   def __next__(self):
     seeds = next(self._seeds_iter).to(self.sampler.device)
     if not self.as_pyg_v1:
-      out = self.sampler.sample_from_nodes(NodeSamplerInput(node=seeds, input_type=self._input_type))
-      return self._collate_fn(out)
-    return self.sampler.sample_pyg_v1(seeds)
+      with nvtx_range('glt.sample'):
+        out = self.sampler.sample_from_nodes(NodeSamplerInput(node=seeds, input_type=self._input_type))
+      with nvtx_range('glt.collate'):
+        return self._collate_fn(out)
+    with nvtx_range('glt.sample'):
+      return self.sampler.sample_pyg_v1(seeds)

@@ -4,6 +4,8 @@ from typing import Optional
 
 import torch
 
+from ..utils.tracing import nvtx_range
+
 from ..data import Dataset
 from ..sampler import NeighborSampler, NodeSamplerInput
 from ..typing import InputNodes, NumNeighbors
@@ -26,6 +28,8 @@ class SubGraphLoader(NodeLoader):
 
   def __next__(self):
     seeds = next(self._seeds_iter).to(self.sampler.device)
-    out = self.sampler.subgraph(NodeSamplerInput(node=seeds, input_type=self._input_type))
+    with nvtx_range('glt.sample'):
+      out = self.sampler.subgraph(NodeSamplerInput(node=seeds, input_type=self._input_type))
     out.batch = seeds
-    return self._collate_fn(out)
+    with nvtx_range('glt.collate'):
+      return self._collate_fn(out)

@@ -18,6 +18,8 @@ import math
 from typing import List, Optional
 
 import torch
+
+from ..utils.tracing import nvtx_range
 import torch.nn as nn
 import torch.nn.functional as F
 
@@ -570,8 +572,9 @@ class GraphSageEngine(object):
     samples (returns None), later calls return the loss of the batch passed one call earlier;
     `flush()` trains the last pending batch."""
     if not self.pipeline:
-      self._stage_seeds(self._seeds[0], seeds)
-      self._run_captured_or_eager(0)
+      with nvtx_range('glt.engine.step'):
+        self._stage_seeds(self._seeds[0], seeds)
+        self._run_captured_or_eager(0)
       self.step_idx += 1
       return self.loss
     if not self._primed:
@@ -581,8 +584,9 @@ class GraphSageEngine(object):
       self._primed = True
       return None
     cur = self._cur
-    self._stage_seeds(self._seeds[1 - cur], seeds)
-    self._run_captured_or_eager(cur)
+    with nvtx_range('glt.engine.step(sample b+1 || train b)'):
+      self._stage_seeds(self._seeds[1 - cur], seeds)
+      self._run_captured_or_eager(cur)
     self._cur = 1 - cur
     self.step_idx += 1
     return self.loss
