@@ -144,6 +144,15 @@ def _w_server_client(rank, world, port):
   feat = d.request_server(1, d.DistServer.get_node_feature, None, torch.tensor([1, 3]))
   assert feat[:, 0].tolist() == [1.0, 3.0]
   assert d.request_server(0, d.DistServer.get_node_partition_id, None, torch.tensor([4, 5])).tolist() == [0, 1]
+  # the rest of the PyG remote-backend surface (reference test_pyg_remote_backend.py:145-281)
+  assert d.request_server(0, d.DistServer.get_node_label, None, torch.tensor([7, 30])).tolist() == [7, 30]
+  assert tuple(d.request_server(1, d.DistServer.get_tensor_size, None)) == (N // 2, 8)
+  for srv in (0, 1):
+    row, col = d.request_server(srv, d.DistServer.get_edge_index, None)
+    assert row.numel() == N and torch.all(row % 2 == srv)               # hash partition: edges keyed by source
+    assert torch.all(((col - row) % N == 1) | ((col - row) % N == 2))
+    rows, cols = d.request_server(srv, d.DistServer.get_edge_size, None)
+    assert rows == N and cols == N
   opts = d.RemoteDistSamplingWorkerOptions(server_rank=[0, 1], num_workers=1, worker_concurrency=2,
                                            master_addr='127.0.0.1', master_port=port + 1 + crank,
                                            buffer_size='16MB', prefetch_size=2)
