@@ -118,6 +118,32 @@ def test_unified_tensor_gather(native, dtype, width):
   assert ut.shape == [n, width]
 
 
+@pytest.mark.parametrize('dtype,width', [(torch.bfloat16, 128), (torch.float32, 128), (torch.float32, 1024),
+                                         (torch.int64, 2)])
+def test_gather_large_lookup_four_rows_in_flight(native, dtype, width):
+  """Large lookups take the 4-rows-per-group variant of k_gather_vec: also cover negative ids,
+  the id2index indirection, a device-side row count and a ragged tail."""
+  n, m = 20000, 150_001
+  full = (torch.randn(n, width) * 50).to(dtype)
+  ut = glt.data.UnifiedTensor(0, dtype)
+  ut.init_from([full[:9000], full[9000:15000], full[15000:]], [0, 0, -1])
+  ids = torch.randint(0, n, (m,))
+  ids[::97] = -1
+  perm = torch.randperm(n)
+  table = ut._table()
+  got = table.gather(ids.to(DEV), perm.to(DEV), 0).cpu()
+  exp = full[perm[ids.clamp(min=0)]]
+  exp[ids < 0] = 0
+  assert torch.equal(got, exp)
+  out = torch.full((m, width), 7, dtype=dtype, device=DEV)
+  n_dev = torch.tensor([100_000], dtype=torch.int32, device=DEV)
+  table.gather_into(ids.to(DEV), None, n_dev, out)
+  exp2 = full[ids.clamp(min=0)]
+  exp2[ids < 0] = 0
+  exp2[100_000:] = 0                       # rows past the device-side count are zero-filled
+  assert torch.equal(out.cpu(), exp2)
+
+
 def test_feature_split_and_reorder(native):
   ei, topo = rmat_csr(2000, 30000)
   feat = glt.utils.id_features(2000, 16)
