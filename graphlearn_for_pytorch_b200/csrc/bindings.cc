@@ -416,7 +416,7 @@ struct RowTableHandle {
                                     : torch::zeros({idx.numel(), out_width}, o);
     const int64_t* map = (id2index.has_value() && id2index->defined()) ? id2index->data_ptr<int64_t>() : nullptr;
     launch_gather_rows(tbl, idx.data_ptr<int64_t>(), map, idx.numel(), nullptr, out.data_ptr(),
-                       out_width * out.element_size(), cur_stream());
+                       out_width * out.element_size(), cur_stream(), map ? id2index->numel() : 0);
     check_cuda_err("gather_rows");
     return out;
   }
@@ -429,7 +429,7 @@ struct RowTableHandle {
     const int32_t* nd = (n_dev.has_value() && n_dev->defined()) ? n_dev->data_ptr<int32_t>() : nullptr;
     TORCH_CHECK(out.is_contiguous() && out.size(0) >= idx.numel());
     launch_gather_rows(tbl, idx.data_ptr<int64_t>(), map, idx.numel(), nd, out.data_ptr(),
-                       out.stride(0) * out.element_size(), cur_stream());
+                       out.stride(0) * out.element_size(), cur_stream(), map ? id2index->numel() : 0);
     check_cuda_err("gather_into");
   }
 };

@@ -22,7 +22,7 @@ template <int LPR, int R>
 __global__ void __launch_bounds__(256) k_gather_vec(RowTable t, const int64_t* idx,
                                                     const int64_t* id2index, int64_t n,
                                                     const int32_t* n_dev, uint8_t* out,
-                                                    int64_t out_row_bytes) {
+                                                    int64_t out_row_bytes, int64_t map_len) {
   constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31;
   const int gl = lane % LPR;
@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(256) k_gather_vec(RowTable t, const int64_t* i
     if (id2index) {
 #pragma unroll
       for (int k = 0; k < R; ++k)
-        if (row[k] >= 0) row[k] = id2index[row[k]];
+        if (row[k] >= 0) row[k] = (map_len <= 0 || row[k] < map_len) ? id2index[row[k]] : -1;
     }
     const uint4* src[R];
 #pragma unroll
@@ -64,7 +64,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) k_gather_scalar(RowTable t, const int64_t* idx,
                                                        const int64_t* id2index, int64_t n,
                                                        const int32_t* n_dev, uint8_t* out,
-                                                       int64_t out_row_bytes) {
+                                                       int64_t out_row_bytes, int64_t map_len) {
   const int lane = threadIdx.x & 31;
   const int64_t n_valid = n_dev ? min(static_cast<int64_t>(*n_dev), n) : n;
   const int nel = static_cast<int>(t.row_bytes / sizeof(T));
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(256) k_gather_scalar(RowTable t, const int64_t
     const uint8_t* src = nullptr;
     if (r < n_valid) {
       int64_t row = idx[r];
-      if (row >= 0 && id2index) row = id2index[row];
+      if (row >= 0 && id2index) row = (map_len <= 0 || row < map_len) ? id2index[row] : -1;
       if (row >= 0) src = row_ptr(t, row);
     }
     T* dst = reinterpret_cast<T*>(out + r * out_row_bytes);
@@ -107,7 +107,8 @@ inline int grid_for(int64_t items, int per_block, int max_blocks = 148 * 16) {
 }  // namespace
 
 void launch_gather_rows(RowTable t, const int64_t* idx, const int64_t* id2index, int64_t n,
-                        const int32_t* n_dev, void* out, int64_t out_row_bytes, cudaStream_t s) {
+                        const int32_t* n_dev, void* out, int64_t out_row_bytes, cudaStream_t s,
+                        int64_t id2index_len) {
   if (n <= 0) return;
   uint8_t* o = reinterpret_cast<uint8_t*>(out);
   bool aligned = (t.row_bytes % 16 == 0) && (out_row_bytes % 16 == 0) &&
@@ -121,10 +122,11 @@ void launch_gather_rows(RowTable t, const int64_t* idx, const int64_t* id2index,
   do {                                                                                                 \
     if (n >= static_cast<int64_t>(148) * 2 * 8 * (32 / LPR) * 4)                                       \
       k_gather_vec<LPR, 4><<<grid_for(n, 8 * (32 / LPR) * 4), 256, 0, s>>>(t, idx, id2index, n, n_dev, \
-                                                                            o, out_row_bytes);         \
+                                                                            o, out_row_bytes,          \
+                                                                            id2index_len);             \
     else                                                                                               \
       k_gather_vec<LPR, 1><<<grid_for(n, 8 * (32 / LPR)), 256, 0, s>>>(t, idx, id2index, n, n_dev, o,  \
-                                                                        out_row_bytes);                \
+                                                                        out_row_bytes, id2index_len);  \
   } while (0)
     if (nvec <= 1) GLT_LAUNCH_VEC(1);
     else if (nvec <= 2) GLT_LAUNCH_VEC(2);
@@ -137,11 +139,11 @@ void launch_gather_rows(RowTable t, const int64_t* idx, const int64_t* id2index,
   }
   const int g = grid_for(n, 8);
   if (t.row_bytes % 4 == 0 && out_row_bytes % 4 == 0)
-    k_gather_scalar<uint32_t><<<g, 256, 0, s>>>(t, idx, id2index, n, n_dev, o, out_row_bytes);
+    k_gather_scalar<uint32_t><<<g, 256, 0, s>>>(t, idx, id2index, n, n_dev, o, out_row_bytes, id2index_len);
   else if (t.row_bytes % 2 == 0 && out_row_bytes % 2 == 0)
-    k_gather_scalar<uint16_t><<<g, 256, 0, s>>>(t, idx, id2index, n, n_dev, o, out_row_bytes);
+    k_gather_scalar<uint16_t><<<g, 256, 0, s>>>(t, idx, id2index, n, n_dev, o, out_row_bytes, id2index_len);
   else
-    k_gather_scalar<uint8_t><<<g, 256, 0, s>>>(t, idx, id2index, n, n_dev, o, out_row_bytes);
+    k_gather_scalar<uint8_t><<<g, 256, 0, s>>>(t, idx, id2index, n, n_dev, o, out_row_bytes, id2index_len);
 }
 
 // NVSwitch multicast store: one write lands in the replica of every GPU bound to the

@@ -126,8 +126,10 @@ void launch_nbr_prob(GraphTable g, GraphTable nbr_g, const float* last, const fl
 // ---- gather.cu ---------------------------------------------------------------
 // out[i, :] = table[idx[i]] (idx optionally remapped through id2index); rows
 // with idx < 0 or i >= *n_dev (when n_dev != nullptr) are zero-filled.
+// id2index_len > 0: ids outside [0, id2index_len) produce zero rows instead of an out-of-bounds read
 void launch_gather_rows(RowTable t, const int64_t* idx, const int64_t* id2index, int64_t n,
-                        const int32_t* n_dev, void* out, int64_t out_row_bytes, cudaStream_t s);
+                        const int32_t* n_dev, void* out, int64_t out_row_bytes, cudaStream_t s,
+                        int64_t id2index_len = 0);
 void launch_gather_i64(RowTable t, const int64_t* idx, int64_t n, const int32_t* n_dev,
                        int64_t* out, cudaStream_t s);
 // copy `nbytes` (multiple of 16) from local memory to an NVSwitch multicast address

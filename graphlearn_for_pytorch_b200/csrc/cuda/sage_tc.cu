@@ -478,7 +478,10 @@ __global__ void __launch_bounds__(kThreads3, 1) k_sage_fused3(SageFusedArgs f) {
   }
   if (threadIdx.x < kMaxParts) {  // shard base table (one entry for a dense local source)
     const void* b = nullptr;
-    if (a.src_local) b = (threadIdx.x == 0) ? a.src_local : nullptr;
+    if (a.src_local)  // dense local source: "shard" p is the same matrix advanced by p * 2^28 rows, so any
+                      // non-negative 32-bit row index decodes correctly
+      b = reinterpret_cast<const uint8_t*>(a.src_local) +
+          static_cast<int64_t>(threadIdx.x) * (int64_t(1) << 28) * row_bytes;
     else if (static_cast<int>(threadIdx.x) < a.feat.num_parts) b = a.feat.base[threadIdx.x];
     sts64(base_u32 + threadIdx.x * 8, reinterpret_cast<uint64_t>(b));
   }
@@ -824,6 +827,15 @@ int fused_version(int d, int n_out) {
   return fused3_smem_bytes(d, n_out) <= kMaxSmem ? 3 : 2;
 }
 
+// v3 publishes 32-bit row handles (4-bit shard, 28-bit row inside the shard)
+bool handles_fit(const SageAggArgs& a) {
+  if (a.src_local) return true;
+  if (a.feat.num_parts > 16) return false;
+  for (int p = 0; p < a.feat.num_parts; ++p)
+    if (a.feat.row_begin[p + 1] - a.feat.row_begin[p] >= (int64_t(1) << 28)) return false;
+  return true;
+}
+
 }  // namespace
 
 int sage_fused_supported(int d, int n_out) {
@@ -841,15 +853,19 @@ static void launch_fused_nc(const SageFusedArgs& a_in, int grid, cudaStream_t s)
   }();
   a.trace = nullptr;
   if (trace_on && grid <= 148) {
-    // resolved on the first (eager) launch, i.e. outside any stream capture
-    static unsigned long long* sym = [] {
-      void* p = nullptr;
-      cudaGetSymbolAddress(&p, g_fused_trace);
-      return reinterpret_cast<unsigned long long*>(p);
-    }();
-    a.trace = sym;
+    // resolved per device on its first (eager) launch, i.e. outside any stream capture
+    static unsigned long long* sym[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64) {
+      if (sym[dev] == nullptr) {
+        void* p = nullptr;
+        if (cudaGetSymbolAddress(&p, g_fused_trace) == cudaSuccess) sym[dev] = reinterpret_cast<unsigned long long*>(p);
+      }
+      a.trace = sym[dev];
+    }
   }
-  if (fused_version(a.agg.d, a.n_out) == 3) {
+  if (fused_version(a.agg.d, a.n_out) == 3 && handles_fit(a.agg)) {
     const size_t smem = fused3_smem_bytes(a.agg.d, a.n_out);
     cudaFuncSetAttribute(k_sage_fused3<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     k_sage_fused3<NC><<<grid, kThreads3, smem, s>>>(a);

@@ -142,6 +142,9 @@ def test_gather_large_lookup_four_rows_in_flight(native, dtype, width):
   exp2[ids < 0] = 0
   exp2[100_000:] = 0                       # rows past the device-side count are zero-filled
   assert torch.equal(out.cpu(), exp2)
+  # ids beyond the id2index table are answered with zero rows, not an out-of-bounds read
+  oob = table.gather(torch.tensor([5, n + 10, 2 ** 40], device=DEV), perm.to(DEV), 0).cpu()
+  assert torch.equal(oob[0], full[perm[5]]) and oob[1:].abs().sum() == 0
 
 
 def test_feature_split_and_reorder(native):
