@@ -505,6 +505,10 @@ static void relu_bwd_cast(const Tensor& dH, const Tensor& Z, const Tensor& count
                           Tensor dPre, const c10::optional<Tensor>& colsum) {
   c10::cuda::CUDAGuard guard(dH.device());
   TORCH_CHECK(dPre.size(0) <= dH.size(0) && dPre.size(0) <= Z.size(0) && dPre.size(1) % 8 == 0);
+  TORCH_CHECK(dH.scalar_type() == torch::kFloat32 && Z.scalar_type() == torch::kBFloat16 &&
+              dPre.scalar_type() == torch::kBFloat16, "relu_bwd_cast: dH fp32, Z/dPre bf16");
+  TORCH_CHECK(dH.is_contiguous() && Z.is_contiguous() && dPre.is_contiguous() && dH.size(1) == dPre.size(1) &&
+              Z.size(1) == dPre.size(1), "relu_bwd_cast: contiguous [rows, d] operands of equal width");
   launch_relu_bwd_cast(dH.data_ptr<float>(), Z.data_ptr(), counters.data_ptr<int32_t>(), n_hops,
                        dPre.size(0), dPre.size(1), dPre.data_ptr(),
                        (colsum.has_value() && colsum->defined()) ? colsum->data_ptr<float>() : nullptr, cur_stream());
@@ -562,6 +566,10 @@ static void adam_step(Tensor p, const Tensor& g, Tensor m, Tensor v, const c10::
   c10::cuda::CUDAGuard guard(p.device());
   TORCH_CHECK(step_dev.scalar_type() == torch::kInt32 && step_dev.numel() >= 2,
               "step_dev must be int32[2]: {steps taken, block ticket}");
+  TORCH_CHECK(p.scalar_type() == torch::kFloat32 && g.scalar_type() == torch::kFloat32 &&
+              m.scalar_type() == torch::kFloat32 && v.scalar_type() == torch::kFloat32, "adam: fp32 state");
+  TORCH_CHECK(g.numel() >= p.numel() && m.numel() >= p.numel() && v.numel() >= p.numel() && p.is_contiguous() &&
+              g.is_contiguous() && m.is_contiguous() && v.is_contiguous(), "adam: state size / layout mismatch");
   launch_adam(p.data_ptr<float>(), g.data_ptr<float>(), m.data_ptr<float>(), v.data_ptr<float>(),
               (p_bf16.has_value() && p_bf16->defined()) ? p_bf16->data_ptr() : nullptr, p.numel(), lr,
               b1, b2, eps, wd, step_dev.data_ptr<int32_t>(), gscale, cur_stream());
