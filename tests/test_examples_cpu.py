@@ -18,3 +18,35 @@ def _run(args, timeout=300):
 def test_llm_on_subgraphs_stub_backend():
   out = _run(['examples/gpt/arxiv_llm.py', '--backend', 'stub', '--batches', '8'])
   assert 'link-prediction accuracy' in out
+
+
+def test_igbh_pipeline_single_and_distributed(tmp_path):
+  """examples/igbh: synthetic IGBH on disk -> split seeds -> compress (CSC, fp16) -> single-process training,
+  then two-stage partitioning (topology, per-partition features) -> 2-process distributed R-GNN training."""
+  import threading
+  sys.path.insert(0, os.path.join(ROOT, 'examples', 'igbh'))
+  sys.path.insert(0, os.path.join(ROOT, 'examples'))
+  from dataset import make_synthetic_igbh
+  d, parts = str(tmp_path / 'igbh'), str(tmp_path / 'parts')
+  make_synthetic_igbh(d, papers=1500)
+  _run(['examples/igbh/split_seeds.py', '--path', d, '--validation_frac', '0.1'])
+  _run(['examples/igbh/compress_graph.py', '--path', d, '--layout', 'CSC', '--use_fp16'])
+  out = _run(['examples/igbh/train_rgnn.py', '--path', d, '--layout', 'CSC', '--use_fp16', '--fan_out', '4,4',
+              '--epochs', '1', '--max_steps', '5', '--batch_size', '128'])
+  assert 'val-acc' in out and 'EVAL_ACCURACY' in out
+  _run(['examples/igbh/partition.py', '--src_path', d, '--dst_path', parts, '--num_partitions', '2',
+        '--with_feature', '0', '--edge_assign_strategy', 'by_dst'])
+  for r in (0, 1):
+    _run(['examples/igbh/build_partition_feature.py', '--src_path', d, '--dst_path', parts, '--partition_idx', str(r)])
+  from graphlearn_for_pytorch_b200.utils.common import get_free_port
+  port = get_free_port()
+  outs = {}
+
+  def rank(r):
+    outs[r] = _run(['examples/igbh/dist_train_rgnn.py', '--path', parts, '--rank', str(r), '--world', '2',
+                    '--fan_out', '4,4', '--epochs', '1', '--max_steps', '4', '--batch_size', '128',
+                    '--master_port', str(port)], timeout=500)
+  th = [threading.Thread(target=rank, args=(r,)) for r in (0, 1)]
+  [t.start() for t in th]
+  [t.join() for t in th]
+  assert 'val-acc' in outs.get(0, '') and 'RUN_STOP' in outs.get(0, '')
