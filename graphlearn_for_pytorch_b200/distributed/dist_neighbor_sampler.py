@@ -228,9 +228,21 @@ class DistNeighborSampler(ConcurrentEventLoop):
     cap = s._hetero_table_cap(sum(v.numel() for v in seeds_dict.values()))
     tables: Dict[NodeType, IdTable] = {}
 
+    n_seed_total = sum(v.numel() for v in seeds_dict.values())
+
     def table_of(nt):
       if nt not in tables:
-        tables[nt] = IdTable(self.device, cap)
+        # global node count of the type, when the partition book can tell (the local shard cannot)
+        pb = self.data.node_pb.get(nt) if isinstance(self.data.node_pb, dict) else None
+        total = None
+        if isinstance(pb, torch.Tensor):
+          total = pb.numel()
+        elif hasattr(pb, 'partition_bounds'):
+          total = int(pb.partition_bounds[-1])
+        elif hasattr(pb, '_ranges'):
+          total = int(pb._ranges[-1])
+        bound = s._hetero_type_bound(nt, n_seed_total, total) if total is not None else None
+        tables[nt] = IdTable(self.device, min(cap, bound) if bound else cap)
       return tables[nt]
     src_dict, src_local, num_nodes, num_edges = {}, {}, {}, {}
     for nt, sd in seeds_dict.items():

@@ -282,6 +282,25 @@ class NeighborSampler(BaseSampler):
         return 1 << 26
     return total
 
+  def _hetero_type_bound(self, nt: NodeType, n_seeds: int, total_hint: Optional[int] = None) -> Optional[int]:
+    """A table of node type `nt` can never hold more distinct ids than the type has nodes: without
+    this bound the worst-case fan-out product sizes (and initialises) 2^26-slot tables per type."""
+    if total_hint is not None:
+      return int(total_hint) + n_seeds
+    if not hasattr(self, '_type_bounds'):
+      self._type_bounds = {}
+    if nt not in self._type_bounds:
+      bound = 0
+      for et in self.edge_types:
+        frm, to = self._etype_ends(et)
+        g = self.graph[et]
+        if frm == nt:
+          bound = max(bound, int(g.row_count))
+        if to == nt:
+          bound = max(bound, int(g.col_count))
+      self._type_bounds[nt] = bound
+    return self._type_bounds[nt] + n_seeds if self._type_bounds[nt] > 0 else None
+
   def _hetero_sample_from_nodes(self, seeds_dict: Dict[NodeType, torch.Tensor]) -> HeteroSamplerOutput:
     n_seed_total = sum(v.numel() for v in seeds_dict.values())
     cap = self._hetero_table_cap(n_seed_total)
@@ -289,7 +308,8 @@ class NeighborSampler(BaseSampler):
 
     def table_of(nt):
       if nt not in tables:
-        tables[nt] = IdTable(self.device, cap)
+        bound = self._hetero_type_bound(nt, n_seed_total)
+        tables[nt] = IdTable(self.device, min(cap, bound) if bound else cap)
       return tables[nt]
 
     src_dict, src_local = {}, {}

@@ -50,3 +50,29 @@ def test_igbh_pipeline_single_and_distributed(tmp_path):
   [t.start() for t in th]
   [t.join() for t in th]
   assert 'val-acc' in outs.get(0, '') and 'RUN_STOP' in outs.get(0, '')
+
+
+def test_table_examples_single_and_distributed(tmp_path):
+  """examples/table (the reference's PAI/ODPS examples): tables on disk -> TableDataset training, and
+  table slices -> DistTableDataset online partitioning -> 2-process training."""
+  import threading
+  tables = str(tmp_path / 'tables')
+  _run(['examples/table/data_preprocess.py', '--out', tables, '--nodes', '3000', '--edges', '30000'])
+  out = _run(['examples/table/train_products_sage.py', '--tables', tables, '--epochs', '1', '--max_steps', '5'])
+  assert 'train-acc' in out
+  from graphlearn_for_pytorch_b200.utils.common import get_free_port
+  port = get_free_port()
+  outs = {}
+
+  def rank(r):
+    outs[r] = _run(['examples/table/dist_train_products_sage.py', '--tables', tables, '--rank', str(r), '--world', '2',
+                    '--max_steps', '3', '--master_port', str(port), '--out', str(tmp_path / 'parts')], timeout=500)
+  th = [threading.Thread(target=rank, args=(r,)) for r in (0, 1)]
+  [t.start() for t in th]
+  [t.join() for t in th]
+  assert 'epoch 0 loss' in outs.get(0, '') and 'epoch 0 loss' in outs.get(1, '')
+
+
+def test_hierarchical_hetero_sage_example():
+  out = _run(['examples/hetero/hierarchical_sage.py', '--papers', '2000', '--epochs', '1', '--max_steps', '4'])
+  assert 'trimmed' in out and 'train-acc' in out

@@ -138,3 +138,22 @@ def test_hetero_sampler():
   out = s.sample_from_nodes(NodeSamplerInput(torch.tensor([1]), 'item'))
   k = ('user', 'u2i', 'item')
   assert set(out.node['user'][out.row[k]].tolist()) == {0, 1} and out.col[k].tolist() == [0, 0]
+
+
+def test_hetero_id_tables_are_bounded_by_type_sizes():
+  """Regression: the per-type id tables of a hetero sample used to be sized by the worst-case fan-out product
+  (2^26 slots each, seconds per batch); they are now bounded by the number of nodes of the type."""
+  import time
+  from graphlearn_for_pytorch_b200.utils.synthetic import rmat_edges
+  g = torch.Generator().manual_seed(0)
+  nu, ni = 500, 300
+  u2i = torch.stack([torch.randint(0, nu, (4000,), generator=g), torch.randint(0, ni, (4000,), generator=g)])
+  ds = glt.data.Dataset(edge_dir='out')
+  ds.init_graph({('u', 'to', 'i'): u2i, ('i', 'rev', 'u'): u2i.flip(0)}, graph_mode='CPU', num_nodes={'u': nu, 'i': ni})
+  s = glt.sampler.NeighborSampler(ds.graph, [20, 20, 20, 20], device=torch.device('cpu'))
+  assert s._hetero_table_cap(256) == 1 << 26                      # the unbounded estimate explodes ...
+  assert s._hetero_type_bound('u', 256) <= nu + 256               # ... the per-type bound does not
+  t0 = time.time()
+  out = s.sample_from_nodes(glt.sampler.NodeSamplerInput(node=torch.arange(256), input_type='u'))
+  assert time.time() - t0 < 5.0
+  assert out.node['u'].numel() <= nu and out.node['i'].numel() <= ni
