@@ -76,3 +76,44 @@ def test_table_examples_single_and_distributed(tmp_path):
 def test_hierarchical_hetero_sage_example():
   out = _run(['examples/hetero/hierarchical_sage.py', '--papers', '2000', '--epochs', '1', '--max_steps', '4'])
   assert 'trimmed' in out and 'train-acc' in out
+
+
+def _run_ranks(cmds, timeout=600):
+  """Run several example processes concurrently (one per rank); return their stdouts."""
+  import threading
+  outs = {}
+
+  def go(i, args):
+    outs[i] = _run(args, timeout=timeout)
+  th = [threading.Thread(target=go, args=(i, c)) for i, c in enumerate(cmds)]
+  [t.start() for t in th]
+  [t.join() for t in th]
+  assert len(outs) == len(cmds), 'a rank failed (see the assertion of its thread above)'
+  return outs
+
+
+def test_distributed_examples_and_benchmark(tmp_path):
+  """examples/distributed/* and benchmarks/bench_dist_neighbor_loader.py on a freshly partitioned graph:
+  worker mode with sampling SUB-PROCESSES (needs the __main__ guards), server-client mode, ZeRO + Join."""
+  from graphlearn_for_pytorch_b200.utils.common import get_free_port
+  parts = str(tmp_path / 'parts')
+  _run(['examples/distributed/partition_dataset.py', '--out', parts, '--parts', '2', '--nodes', '4000', '--edges', '40000'])
+  port = get_free_port()
+  outs = _run_ranks([['examples/distributed/dist_train_sage.py', '--root', parts, '--rank', str(r), '--world', '2',
+                      '--epochs', '1', '--workers', '1', '--master-port', str(port)] for r in (0, 1)])
+  assert all('epoch 0 loss' in o for o in outs.values())
+  port = get_free_port()
+  outs = _run_ranks([['benchmarks/bench_dist_neighbor_loader.py', '--root', parts, '--rank', str(r), '--world', '2',
+                      '--epochs', '1', '--workers', '1', '--master-port', str(port)] for r in (0, 1)])
+  assert all('edges/s' in o for o in outs.values())
+  port = get_free_port()
+  srv = [['examples/distributed/server_client_mode/sage_server.py', '--root', parts, '--rank', str(r), '--servers', '2',
+          '--clients', '1', '--master-port', str(port)] for r in (0, 1)]
+  cli = [['examples/distributed/server_client_mode/sage_client.py', '--rank', '0', '--servers', '2', '--clients', '1',
+          '--master-port', str(port)]]
+  outs = _run_ranks(srv + cli)
+  assert 'epoch 1 loss' in outs[2]
+  port = get_free_port()
+  outs = _run_ranks([['examples/distributed/dist_sage_unsup_zero.py', '--root', parts, '--rank', str(r), '--world', '2',
+                      '--master-port', str(port)] for r in (0, 1)])
+  assert all('epoch 1 loss' in o for o in outs.values())
