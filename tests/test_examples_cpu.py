@@ -117,3 +117,18 @@ def test_distributed_examples_and_benchmark(tmp_path):
   outs = _run_ranks([['examples/distributed/dist_sage_unsup_zero.py', '--root', parts, '--rank', str(r), '--world', '2',
                       '--master-port', str(port)] for r in (0, 1)])
   assert all('epoch 1 loss' in o for o in outs.values())
+
+
+@pytest.mark.parametrize('args', [
+    ['examples/train_sage_products.py', '--nodes', '4000', '--edges', '40000', '--epochs', '1', '--batch', '256'],
+    ['examples/graph_sage_unsup.py'],
+    ['examples/hetero/train_rgnn_igbh.py', '--papers', '2000', '--fanout', '4,4', '--epochs', '1', '--batch', '256'],
+    ['examples/hetero/train_rgnn_igbh.py', '--papers', '2000', '--fanout', '4,4', '--epochs', '1', '--batch', '256',
+     '--model', 'hgt'],
+    ['examples/hetero/bipartite_sage_unsup.py'],
+    ['examples/feature_mp.py'],
+    ['examples/seal_link_pred.py'],
+], ids=lambda a: os.path.basename(a[0]) + ('-hgt' if 'hgt' in a else ''))
+def test_single_process_examples(args):
+  out = _run(args)
+  assert 'loss' in out or 'first column' in out
