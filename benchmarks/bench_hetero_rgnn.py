@@ -93,7 +93,7 @@ if rank == 0:
                     'value': args.steps * args.batch * world / (ms.item() / 1e3), 'n_gpus': world,
                     'ms_per_step': ms.item() / args.steps, 'model': args.model, 'papers': args.papers,
                     'fanout': fan, 'nodes_per_batch': nodes / args.steps, 'edges_per_batch': edges_n / args.steps,
-                    'loss': float(loss), 'path': 'hetero NeighborSampler (per-edge-type device sampling, P2P shards) '
+                    'loss': float(loss.detach()), 'path': 'hetero NeighborSampler (per-edge-type device sampling, P2P shards) '
                     '+ eager RGNN (bf16)'}))
 if world > 1:
   dist.barrier()

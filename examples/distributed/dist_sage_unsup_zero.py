@@ -46,5 +46,5 @@ for epoch in range(2):
       logit = (h[b.edge_label_index[1]] * h[b.edge_label_index[0]]).sum(-1)
       loss = F.binary_cross_entropy_with_logits(logit, b.edge_label.float())
       opt.zero_grad(); loss.backward(); opt.step()
-  print(f'[rank {args.rank}] epoch {epoch} loss {float(loss):.4f}')
+  print(f'[rank {args.rank}] epoch {epoch} loss {float(loss.detach()):.4f}')
 loader.shutdown()

@@ -39,7 +39,7 @@ def main():
       out = model(b.x, b.edge_index, b.num_sampled_nodes, b.num_sampled_edges)[:b.batch_size]
       loss = F.cross_entropy(out, b.y[:b.batch_size])
       opt.zero_grad(); loss.backward(); opt.step()
-    print(f'[client {args.rank}] epoch {epoch} loss {float(loss):.4f}')
+    print(f'[client {args.rank}] epoch {epoch} loss {float(loss.detach()):.4f}')
   loader.shutdown()
   gd.shutdown_client()
 

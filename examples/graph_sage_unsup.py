@@ -25,5 +25,5 @@ for epoch in range(2):
     logit = (h[src] * h[dst]).sum(-1)
     loss = F.binary_cross_entropy_with_logits(logit, b.edge_label.float().to(device))
     opt.zero_grad(); loss.backward(); opt.step()
-    tot += float(loss)
+    tot += float(loss.detach())
   print(f'epoch {epoch}: loss {tot / len(loader):.4f}')

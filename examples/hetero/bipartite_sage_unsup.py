@@ -36,5 +36,5 @@ for epoch in range(2):
     src, pos, neg = b['user'].src_index, b['item'].dst_pos_index, b['item'].dst_neg_index[:, 0]
     loss = F.softplus(-(hu[src] * hi[pos]).sum(-1)).mean() + F.softplus((hu[src] * hi[neg]).sum(-1)).mean()
     opt.zero_grad(); loss.backward(); opt.step()
-    tot += float(loss)
+    tot += float(loss.detach())
   print(f'epoch {epoch}: loss {tot / len(loader):.4f}')

@@ -61,7 +61,7 @@ for epoch in range(start_epoch, args.epochs):
     opt.zero_grad(); loss.backward(); opt.step()
     correct += int((out.argmax(1) == tgt).sum()); seen += tgt.numel()
   log.event('EVAL_ACCURACY', correct / seen, {'epoch': epoch})
-  print(f'epoch {epoch}: loss {float(loss):.4f} train-acc {correct / seen:.4f} time {time.time() - t0:.2f}s')
+  print(f'epoch {epoch}: loss {float(loss.detach()):.4f} train-acc {correct / seen:.4f} time {time.time() - t0:.2f}s')
   if args.ckpt_dir:
     save_ckpt(0, args.ckpt_dir, model, opt, epoch, extra=loader.state_dict())
 log.end('RUN')

@@ -47,5 +47,5 @@ for epoch in range(2):
     y = labels[idx].to(device)
     loss = F.binary_cross_entropy_with_logits(logit, y)
     opt.zero_grad(); loss.backward(); opt.step()
-    tot += float(loss) * idx.numel(); correct += int(((logit > 0).float() == y).sum())
+    tot += float(loss.detach()) * idx.numel(); correct += int(((logit > 0).float() == y).sum())
   print(f'epoch {epoch}: loss {tot / perm.numel():.4f} acc {correct / perm.numel():.4f}')

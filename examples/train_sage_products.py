@@ -45,7 +45,7 @@ if args.mode == 'loader':
       tgt = b.y[:b.batch_size].to(device)
       loss = F.cross_entropy(out, tgt)
       opt.zero_grad(); loss.backward(); opt.step()
-      tot += float(loss); correct += int((out.argmax(1) == tgt).sum()); seen += b.batch_size
+      tot += float(loss.detach()); correct += int((out.argmax(1) == tgt).sum()); seen += b.batch_size
     print(f'epoch {epoch}: loss {tot / len(loader):.4f} acc {correct / seen:.4f} time {time.time() - t0:.2f}s')
 else:
   assert cuda, 'the engine needs a GPU'

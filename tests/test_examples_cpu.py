@@ -132,3 +132,20 @@ def test_distributed_examples_and_benchmark(tmp_path):
 def test_single_process_examples(args):
   out = _run(args)
   assert 'loss' in out or 'first column' in out
+
+
+def test_cluster_launcher_local_plan(tmp_path):
+  """examples/distributed/launch.py: YAML plan -> one process per rank (local here, ssh for remote hosts)."""
+  import yaml
+  parts = str(tmp_path / 'parts')
+  _run(['examples/distributed/partition_dataset.py', '--out', parts, '--parts', '2', '--nodes', '3000', '--edges', '30000'])
+  from graphlearn_for_pytorch_b200.utils.common import get_free_port
+  cfg = yaml.safe_load(open(os.path.join(ROOT, 'examples', 'distributed', 'dist_train_sage_config.yml')))
+  cfg['master_port'] = get_free_port()
+  cfg['args'] = [parts if a == '/tmp/glt_parts' else a for a in cfg['args']]
+  path = str(tmp_path / 'plan.yml')
+  yaml.safe_dump(cfg, open(path, 'w'))
+  dry = _run(['examples/distributed/launch.py', '--config', path, '--dry-run'])
+  assert dry.count('dist_train_sage.py') == 2 and '--rank 1 --world 2' in dry
+  out = _run(['examples/distributed/launch.py', '--config', path])
+  assert '2/2 ranks finished cleanly' in out
