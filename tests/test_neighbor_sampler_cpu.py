@@ -157,3 +157,26 @@ def test_hetero_id_tables_are_bounded_by_type_sizes():
   out = s.sample_from_nodes(glt.sampler.NodeSamplerInput(node=torch.arange(256), input_type='u'))
   assert time.time() - t0 < 5.0
   assert out.node['u'].numel() <= nu and out.node['i'].numel() <= ni
+
+
+def test_behavioural_edge_cases_from_survey_appendix_c():
+  """ids beyond the CSR get no neighbours, seeds are de-duplicated in first-occurrence order,
+  `batch` is the seed prefix of `node`, fan-out -1 returns the whole neighbourhood, and a frontier that runs dry ends
+  the expansion without failing."""
+  ei = torch.tensor([[0, 0, 1, 2, 5], [1, 2, 2, 0, 0]])          # node 3, 4 isolated; node 5 -> 0; rows up to 5
+  topo = glt.data.Topology(ei, layout='CSR')
+  g = glt.data.Graph(topo, 'CPU', 0)
+  s = glt.sampler.NeighborSampler(g, [-1, -1], device=torch.device('cpu'))
+  out = s.sample_from_nodes(torch.tensor([2, 0, 2, 9]))           # duplicate seed, id 9 is outside the CSR
+  assert out.node[:3].tolist() == [2, 0, 9] and out.batch.tolist() == [2, 0, 9]
+  src, dst = out.node[out.col], out.node[out.row]                  # edge_dir='out': col = seed side, row = neighbour
+  pairs = sorted(zip(src.tolist(), dst.tolist()))
+  assert (2, 0) in pairs and (0, 1) in pairs and (0, 2) in pairs and all(a != 9 for a, _ in pairs)
+  assert set(out.node.tolist()) == {0, 1, 2, 9}
+  # a seed without out-edges: the expansion stops, the output is just the seed
+  out = s.sample_from_nodes(torch.tensor([3]))
+  assert out.node.tolist() == [3] and out.row.numel() == 0 and out.num_sampled_nodes[0] == 1
+  assert sum(out.num_sampled_nodes) == 1 and sum(out.num_sampled_edges) == 0
+  # one-hop API: neighbour counts are min(degree, fanout); ids beyond the CSR return 0
+  nbr = glt.sampler.NeighborSampler(g, [1], device=torch.device('cpu')).sample_one_hop(torch.tensor([0, 3, 9]), 1)
+  assert nbr.nbr_num.tolist() == [1, 0, 0]
