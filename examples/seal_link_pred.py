@@ -1,5 +1,7 @@
 """SEAL link prediction: enclosing-subgraph sampling + DRNL + DGCNN
 (counterpart of the reference's examples/seal_link_pred.py)."""
+import argparse
+
 import torch
 import torch.nn.functional as F
 
@@ -7,16 +9,21 @@ from common import glt, synthetic_homo
 from graphlearn_for_pytorch_b200.models import DGCNN, drnl_node_labeling
 from graphlearn_for_pytorch_b200.sampler import NeighborSampler, NodeSamplerInput, RandomNegativeSampler
 
+ap = argparse.ArgumentParser()
+ap.add_argument('--links', type=int, default=2000, help='positive (and negative) links')
+ap.add_argument('--epochs', type=int, default=2)
+args = ap.parse_args()
+L = args.links
 cuda = torch.cuda.is_available()
 device = torch.device('cuda', 0) if cuda else torch.device('cpu')
 ei, _, _ = synthetic_homo(3_000, 24_000, feat_dim=4, num_classes=2)
 topo = glt.data.Topology(ei, layout='CSR', num_nodes=3000)
 graph = glt.data.Graph(topo, 'CUDA' if cuda else 'CPU')
 sampler = NeighborSampler(graph, [-1], device=device)          # 1-hop enclosing subgraphs
-neg = RandomNegativeSampler(graph, 'CUDA' if cuda else 'CPU').sample(2000, padding=True).cpu()
-pos = ei[:, torch.randperm(ei.shape[1])[:2000]]
+neg = RandomNegativeSampler(graph, 'CUDA' if cuda else 'CPU').sample(L, padding=True).cpu()
+pos = ei[:, torch.randperm(ei.shape[1])[:L]]
 links = torch.cat([pos, neg], 1)
-labels = torch.cat([torch.ones(2000), torch.zeros(2000)])
+labels = torch.cat([torch.ones(L), torch.zeros(L)])
 model = DGCNN(num_labels=200, hidden=32, num_layers=3, k=30).to(device)
 opt = torch.optim.Adam(model.parameters(), lr=1e-3)
 
@@ -37,7 +44,7 @@ def extract(batch_links):
   return torch.cat(zs), torch.cat(eis, 1), torch.cat(batch)
 
 
-for epoch in range(2):
+for epoch in range(args.epochs):
   perm = torch.randperm(links.shape[1])
   tot, correct = 0.0, 0
   for i in range(0, perm.numel(), 32):

@@ -127,7 +127,7 @@ def test_distributed_examples_and_benchmark(tmp_path):
      '--model', 'hgt'],
     ['examples/hetero/bipartite_sage_unsup.py'],
     ['examples/feature_mp.py'],
-    ['examples/seal_link_pred.py'],
+    ['examples/seal_link_pred.py', '--links', '400', '--epochs', '2'],
 ], ids=lambda a: os.path.basename(a[0]) + ('-hgt' if 'hgt' in a else ''))
 def test_single_process_examples(args):
   out = _run(args)
