@@ -267,6 +267,11 @@ struct SamplerArena {
   Tensor nodes, deg, counters, seed_local, scratch, step;
   std::vector<Tensor> ell, ell_eids;
   std::unique_ptr<DeviceTable> table;
+  // optional transposed adjacency (EXPERIMENTAL, see cuda/transpose.cu): built after the hops of
+  // every sample() once enable_transpose(n_hops) was called
+  int tr_hops = 0;
+  int64_t tr_cap_edges = 0;
+  Tensor tr_cnt, tr_off, tr_cursor, tr_tgt, tr_block_sums;
 
   // cap_override: optional calibrated frontier capacities per hop (+ one trailing entry for the
   // number of nodes the last hop may add); empty = worst case (max_seeds * prod(fanouts)).
@@ -301,6 +306,42 @@ struct SamplerArena {
     seed_local = torch::zeros({max_seeds}, o32);
     scratch = torch::zeros({max_seeds}, o32);
     step = torch::zeros({1}, o32);
+  }
+
+  void enable_transpose(int64_t n_hops) {
+    c10::cuda::CUDAGuard guard(device);
+    TORCH_CHECK(n_hops >= 1 && n_hops <= static_cast<int64_t>(fanouts.size()), "bad number of hops to transpose");
+    auto o32 = torch::TensorOptions().dtype(torch::kInt32).device(torch::kCUDA, device);
+    tr_hops = static_cast<int>(n_hops);
+    tr_cap_edges = 0;
+    for (int h = 0; h < tr_hops; ++h) tr_cap_edges += cap_rows[h] * fanouts[h];
+    TORCH_CHECK(tr_cap_edges < (1LL << 31), "transposed adjacency too large");
+    tr_cnt = torch::zeros({tr_hops, cap_nodes}, o32);
+    tr_cursor = torch::zeros({tr_hops, cap_nodes}, o32);
+    tr_off = torch::zeros({cap_nodes + 1}, o32);
+    tr_tgt = torch::zeros({std::max<int64_t>(tr_cap_edges, 1)}, o32);
+    tr_block_sums = torch::zeros({cap_nodes / 1024 + 2}, o32);
+  }
+
+  void build_transpose(cudaStream_t s) {
+    TransposeArgs a{};
+    a.cum = counters.data_ptr<int32_t>();
+    a.deg = deg.data_ptr<int32_t>();
+    for (int h = 0; h < 4; ++h) { a.ell[h] = nullptr; a.k[h] = 1; a.cap_rows[h] = 0; }
+    for (int h = 0; h < tr_hops; ++h) {
+      a.ell[h] = ell[h].data_ptr<int32_t>();
+      a.k[h] = static_cast<int>(fanouts[h]);
+      a.cap_rows[h] = static_cast<int>(cap_rows[h]);
+    }
+    a.n_hops = tr_hops;
+    a.cap_nodes = static_cast<int>(cap_nodes);
+    a.cap_edges = static_cast<int>(tr_cap_edges);
+    a.cnt = tr_cnt.data_ptr<int32_t>();
+    a.off = tr_off.data_ptr<int32_t>();
+    a.cursor = tr_cursor.data_ptr<int32_t>();
+    a.tgt = tr_tgt.data_ptr<int32_t>();
+    a.block_sums = tr_block_sums.data_ptr<int32_t>();
+    launch_build_transpose(a, s);
   }
 
   BatchCounters bc() {
@@ -344,6 +385,7 @@ struct SamplerArena {
       launch_sample_hop(a, s);
       launch_relabel_hop(a, s);
     }
+    if (tr_hops > 0) build_transpose(s);
     check_cuda_err("arena sample");
   }
 
@@ -499,6 +541,40 @@ static void sage_scatter_bwd(const Tensor& dA, int64_t d, const Tensor& counters
   a.dH = dH.data_ptr<float>();
   launch_sage_scatter_bwd(a, cur_stream());
   check_cuda_err("sage_scatter_bwd");
+}
+
+// EXPERIMENTAL atomics-free backward of the mean aggregation over the arena's transposed adjacency
+static void sage_gather_bwd(const Tensor& dA, int64_t d, SamplerArena& ar, int64_t n_hops_targets,
+                            const c10::optional<Tensor>& Z, Tensor dPre, const c10::optional<Tensor>& colsum) {
+  c10::cuda::CUDAGuard guard(dA.device());
+  TORCH_CHECK(ar.tr_hops >= n_hops_targets && n_hops_targets >= 1, "enable_transpose(n_hops) covers too few hops");
+  TORCH_CHECK(dA.scalar_type() == torch::kBFloat16 && dA.is_contiguous() && dA.size(1) == 2 * d && d % 8 == 0);
+  TORCH_CHECK(dPre.scalar_type() == torch::kBFloat16 && dPre.is_contiguous() && dPre.size(1) == d);
+  SageGatherBwdArgs a{};
+  a.dA = dA.data_ptr();
+  a.d = static_cast<int>(d);
+  a.cum = ar.counters.data_ptr<int32_t>();
+  a.n_hops_targets = static_cast<int>(n_hops_targets);
+  a.cap_targets = static_cast<int>(dA.size(0));
+  a.cap_src = static_cast<int>(dPre.size(0));
+  TORCH_CHECK(a.cap_src <= ar.cap_nodes, "dPre has more rows than the arena has nodes");
+  a.deg = ar.deg.data_ptr<int32_t>();
+  a.off = ar.tr_off.data_ptr<int32_t>();
+  a.cnt_upto = ar.tr_cnt.data_ptr<int32_t>() + (n_hops_targets - 1) * ar.cap_nodes;
+  a.tgt = ar.tr_tgt.data_ptr<int32_t>();
+  a.Z = nullptr;
+  if (Z.has_value() && Z->defined()) {
+    TORCH_CHECK(Z->scalar_type() == torch::kBFloat16 && Z->is_contiguous() && Z->size(1) == d && Z->size(0) >= dPre.size(0));
+    a.Z = Z->data_ptr();
+  }
+  a.dPre = dPre.data_ptr();
+  a.colsum = nullptr;
+  if (colsum.has_value() && colsum->defined()) {
+    TORCH_CHECK(colsum->scalar_type() == torch::kFloat32 && colsum->numel() >= d);
+    a.colsum = colsum->data_ptr<float>();
+  }
+  launch_sage_gather_bwd(a, cur_stream());
+  check_cuda_err("sage_gather_bwd");
 }
 
 static void relu_bwd_cast(const Tensor& dH, const Tensor& Z, const Tensor& counters, int64_t n_hops,
@@ -824,6 +900,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def_readonly("counters", &SamplerArena::counters)
       .def_readonly("seed_local", &SamplerArena::seed_local)
       .def_readonly("step", &SamplerArena::step)
+      .def("enable_transpose", &SamplerArena::enable_transpose)
+      .def_readonly("tr_hops", &SamplerArena::tr_hops)
+      .def_readonly("tr_off", &SamplerArena::tr_off)
+      .def_readonly("tr_cnt", &SamplerArena::tr_cnt)
+      .def_readonly("tr_tgt", &SamplerArena::tr_tgt)
       .def_readonly("ell", &SamplerArena::ell)
       .def_readonly("ell_eids", &SamplerArena::ell_eids)
       .def_readonly("cap_rows", &SamplerArena::cap_rows)
@@ -843,6 +924,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("sage_aggregate", &sage_aggregate);
   m.def("sage_scatter_bwd", &sage_scatter_bwd);
   m.def("relu_bwd_cast", &relu_bwd_cast);
+  m.def("sage_gather_bwd", &sage_gather_bwd);
   m.def("bias_relu", &bias_relu);
   m.def("softmax_nll", &softmax_nll);
   m.def("adam_step", &adam_step);

@@ -167,6 +167,47 @@ struct SageScatterArgs {
 };
 void launch_sage_scatter_bwd(const SageScatterArgs& a, cudaStream_t s);
 
+// ---- transpose.cu: per-batch transposed adjacency + atomics-free backward (EXPERIMENTAL) ----------
+// The forward ELL blocks are keyed by TARGET (row t lists its sampled sources).  The backward of the
+// mean aggregation needs the opposite view (for a source s: all targets that sampled it).  It is
+// built once per batch on the sampling stream as a CSR over local source ids, ordered by hop inside
+// every segment, so that one structure serves every layer (layer l uses the hops 0..L-l prefix).
+struct TransposeArgs {
+  const int32_t* cum;        // device counters (cum[h] = nodes before hop h's new nodes)
+  const int32_t* deg;        // [cap_nodes] valid ELL entries per target
+  const int32_t* ell[4];
+  int k[4];
+  int cap_rows[4];
+  int n_hops;                // hops 0..n_hops-1 are transposed
+  int cap_nodes;             // capacity of the local id space
+  int cap_edges;             // capacity of tgt
+  int32_t* cnt;              // [n_hops][cap_nodes]: in-counts per hop, then cumulative over hops
+  int32_t* off;              // [cap_nodes + 1]: segment start per source
+  int32_t* cursor;           // [n_hops][cap_nodes]: fill cursor per hop
+  int32_t* tgt;              // [cap_edges]: target local ids
+  int32_t* block_sums;       // [>= cap_nodes / 1024 + 2]
+};
+void launch_build_transpose(const TransposeArgs& a, cudaStream_t s);
+
+struct SageGatherBwdArgs {
+  const void* dA;            // bf16 [cap_targets, 2d] = gradient of [mean | self]
+  int d;
+  const int32_t* cum;
+  int n_hops_targets;        // targets = cum[n_hops_targets], sources = cum[n_hops_targets + 1]
+  int cap_targets;
+  int cap_src;               // rows of dPre / Z
+  const int32_t* deg;
+  const int32_t* off;        // transposed CSR
+  const int32_t* cnt_upto;   // [cap_nodes] in-edges of the hops used by this layer (prefix of the segment)
+  const int32_t* tgt;
+  const void* Z;             // bf16 [cap_src, d] activations of the previous layer (ReLU mask) or nullptr
+  void* dPre;                // bf16 [cap_src, d]
+  float* colsum;             // optional fp32 [d]: bias gradient
+};
+// dPre[s] = relu'(Z[s]) * (dA_self[s] + sum_{t in in(s)} dA_mean[t] / deg[t]); rows >= sources are zero-filled.
+// Replaces zero_rows + sage_scatter_bwd (fp32 atomics) + relu_bwd_cast.
+void launch_sage_gather_bwd(const SageGatherBwdArgs& a, cudaStream_t s);
+
 // dPre = (Z > 0) ? bf16(dH) : 0 for rows < cum[n_hops]; 0 beyond.
 // colsum (optional, fp32 [d]): fused bias gradient = column sums of dPre.
 void launch_relu_bwd_cast(const float* dH, const void* Z, const int32_t* cum, int n_hops, int cap,

@@ -107,10 +107,17 @@ class GraphSageEngine(object):
                device: Optional[torch.device] = None, group=None, use_fused: bool = True,
                use_cuda_graph: bool = True, calibration_seeds: Optional[torch.Tensor] = None,
                calibration_margin: float = 1.3, calibration_batches: int = 16, pipeline: bool = False,
-               use_peer_allreduce: bool = True):
+               use_peer_allreduce: bool = True, use_gather_bwd: Optional[bool] = None):
     self.nat = require_native()
     self.pipeline = bool(pipeline)
     self.use_peer_allreduce = bool(use_peer_allreduce)
+    # EXPERIMENTAL (csrc/cuda/transpose.cu): the sampler also builds the transposed adjacency of the batch and
+    # the backward of the aggregation becomes an atomics-free gather (replaces zero_rows + scatter + relu_bwd_cast).
+    # Off by default until it has been validated on hardware; GLT_B200_GATHER_BWD=1 turns it on globally.
+    if use_gather_bwd is None:
+      import os as _os
+      use_gather_bwd = _os.environ.get('GLT_B200_GATHER_BWD', '0') == '1'
+    self.use_gather_bwd = bool(use_gather_bwd)
     self.peer_group = None
     self.graph = graph
     graph.lazy_init()
@@ -148,6 +155,8 @@ class GraphSageEngine(object):
       self._cur = 0
       for p_, ar_ in enumerate(self._arenas):
         ar_.step.fill_(p_ - n_arenas)          # disjoint Philox stream ids per arena
+        if self.use_gather_bwd and self.L >= 2:
+          ar_.enable_transpose(self.L - 1)     # layer 2 uses hops 0..L-2, deeper layers a prefix of them
       self.calibrated = bool(cap_override)
       self.cap_rows = list(self.arena.cap_rows)           # frontier capacity per hop (+ last-hop additions)
       # layer l (1-based) targets = nodes of hops 0..L-l
@@ -381,9 +390,14 @@ class GraphSageEngine(object):
       # bias gradients are fused into the kernels that produce dPre (loss / relu_bwd_cast)
       if l > 1:
         torch.mm(self.dPre[l], self.W(l), out=self.dA[l])
+        pboff, pn = self._b_off[l - 2]
+        if self.use_gather_bwd:
+          nat.sage_gather_bwd(self.dA[l], self.dims_in[l - 1], ar, nh, self.Z[l - 1], self.dPre[l - 1],
+                              self.g32[pboff:pboff + pn])
+          self._k(1)
+          continue
         nat.zero_rows(self.dH[l - 1], ar.counters, nh + 1)
         nat.sage_scatter_bwd(self.dA[l], self.dims_in[l - 1], ar.counters, nh, ell, ks, ar.deg, self.dH[l - 1])
-        pboff, pn = self._b_off[l - 2]
         nat.relu_bwd_cast(self.dH[l - 1], self.Z[l - 1], ar.counters, nh + 1, self.dPre[l - 1],
                           self.g32[pboff:pboff + pn])
         self._k(3)
