@@ -320,3 +320,40 @@ def test_dist_loader_on_vineyard_fragments(tmp_path):
   write_arrow_fragments(str(tmp_path), 'ring', 2, {'v': {'feat': id_features(N, 8), 'label': torch.arange(N)}},
                         {'e': ('v', 'v', ring_graph(N), {})})
   run_workers(_w_vineyard_fragments, args=(str(tmp_path),), timeout=300)
+
+
+def _w_fault_and_replay(rank, world, port):
+  """(a) an exception inside a sampling SUB-PROCESS must reach the consumer as an error (the
+  reference only logs it and the epoch hangs); (b) sampling is replayable from (seed, epoch, batch) counters."""
+  import graphlearn_for_pytorch_b200.distributed as d
+  d.init_worker_group(world, rank)
+  ds = build_partition(0, 1)
+  bad = torch.tensor([0, 1, 2, 3, 4, 5, 10 ** 6, 7, 8, 9])     # one id far outside the graph / feature table
+  opts = d.MpDistSamplingWorkerOptions(num_workers=1, worker_concurrency=1, master_addr='127.0.0.1', master_port=port,
+                                       channel_size='8MB')
+  loader = d.DistNeighborLoader(ds, [2, 2], bad, batch_size=5, collect_features=True, to_device=torch.device('cpu'),
+                                worker_options=opts)
+  try:
+    for _ in loader:
+      pass
+    raise AssertionError('the worker failure was swallowed')
+  except RuntimeError as e:
+    assert 'sampling worker' in str(e) and 'IndexError' in str(e)
+  loader.shutdown()
+
+  def epoch_of(seed, port_):
+    ld = d.DistNeighborLoader(ds, [2, 2], torch.arange(N), batch_size=8, shuffle=True, collect_features=True,
+                              to_device=torch.device('cpu'), random_seed=seed,
+                              worker_options=d.CollocatedDistSamplingWorkerOptions(master_addr='127.0.0.1',
+                                                                                   master_port=port_))
+    out = [(b.batch.tolist(), b.node.tolist(), b.edge_index.tolist()) for b in ld]
+    ld.shutdown()
+    return out
+  a, b, c = epoch_of(11, port + 1), epoch_of(11, port + 1), epoch_of(12, port + 1)
+  assert a == b, 'same seed must replay the same batches, nodes and edges'
+  assert a != c
+  d.shutdown_rpc()
+
+
+def test_worker_failure_reaches_consumer_and_sampling_replays():
+  run_workers(_w_fault_and_replay, world=1, timeout=300)
