@@ -23,6 +23,7 @@ from .dist_context import DistContext, DistRole, get_context
 _rpc_init_lock = threading.RLock()
 _rpc_inited = False
 _rpc_worker_names: Optional[Dict[DistRole, List[str]]] = None
+_rpc_dynamic = False
 _rpc_current_group_worker_names: Optional[List[str]] = None
 _rpc_master_addr: Optional[str] = None
 _rpc_master_port: Optional[int] = None
@@ -106,6 +107,7 @@ def all_gather(obj, timeout=None):
     seq = _gather_seq
     _gather_seq += 1
   leader = names[0]
+  _wait_for_member(leader)
   kw = {} if timeout is None else {'timeout': timeout}
   return rpc.rpc_sync(leader, _role_gather_on_leader, args=(seq, len(names), ctx.worker_name, obj), **kw)
 
@@ -153,10 +155,22 @@ def init_rpc(master_addr: str, master_port: int, num_rpc_threads: int = 16, rpc_
                    rpc_backend_options=opts)
     _rpc_master_addr, _rpc_master_port = master_addr, master_port
     _rpc_inited = True
+    global _rpc_dynamic
+    _rpc_dynamic = bool(is_dynamic)
     if is_dynamic:
       # dynamic membership: derive names from the contexts instead of a global gather
+      # (torch's dynamic RPC groups have no collectives; names follow the `<group>_<rank>` convention, the peer
+      # role uses its default group name unless GLT_B200_PEER_GROUP names another one)
+      import os
+      from .dist_context import _DEFAULT_CLIENT_GROUP, _DEFAULT_SERVER_GROUP
       names = collections.defaultdict(list)
       names[ctx.role] = [f'{ctx.group_name}_{r}' for r in range(ctx.world_size)]
+      if ctx.role == DistRole.CLIENT:
+        g = os.environ.get('GLT_B200_PEER_GROUP', _DEFAULT_SERVER_GROUP)
+        names[DistRole.SERVER] = [f'{g}_{r}' for r in range(ctx.num_servers())]
+      elif ctx.role == DistRole.SERVER:
+        g = os.environ.get('GLT_B200_PEER_GROUP', _DEFAULT_CLIENT_GROUP)
+        names[DistRole.CLIENT] = [f'{g}_{r}' for r in range(ctx.num_clients())]
       _rpc_worker_names = dict(names)
       _rpc_current_group_worker_names = names[ctx.role]
       return
@@ -175,7 +189,7 @@ def shutdown_rpc(graceful: bool = True):
     if not _rpc_inited:
       return
     try:
-      if graceful:
+      if graceful and not _rpc_dynamic:     # dynamic groups have no collectives: members just leave
         try:
           global_barrier()
         except Exception:  # noqa: BLE001
@@ -263,6 +277,27 @@ def rpc_request(worker_name: str, callee_id: int, args=None, kwargs=None):
   return rpc_request_async(worker_name, callee_id, args, kwargs).wait()
 
 
+_known_members = set()
+
+
+def _wait_for_member(name: str, timeout: float = 120.0, interval: float = 0.2):
+  """Dynamic membership has no rendezvous: a peer may simply not have joined yet.  Poll (bounded) until the
+  RPC agent knows it -- the reference retries its dynamic joins the same way (rpc.py:286-318)."""
+  if not _rpc_dynamic or name in _known_members:
+    return
+  import time
+  deadline = time.time() + timeout
+  while True:
+    try:
+      rpc.get_worker_info(name)
+      _known_members.add(name)
+      return
+    except RuntimeError:
+      if time.time() > deadline:
+        raise
+      time.sleep(interval)
+
+
 @_require_initialized
 def rpc_global_request_async(target_role: DistRole, role_rank: int, func: Callable, args=None, kwargs=None):
   """Call `func` on process `role_rank` of another role (e.g. client -> server)."""
@@ -274,6 +309,7 @@ def rpc_global_request_async(target_role: DistRole, role_rank: int, func: Callab
     to = f'{prefix}_{role_rank}'
   else:
     to = names[role_rank]
+  _wait_for_member(to)
   return rpc.rpc_async(to, func, args=args, kwargs=kwargs)
 
 

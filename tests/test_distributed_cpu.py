@@ -357,3 +357,44 @@ def _w_fault_and_replay(rank, world, port):
 
 def test_worker_failure_reaches_consumer_and_sampling_replays():
   run_workers(_w_fault_and_replay, world=1, timeout=300)
+
+
+def _w_server_client_auto(rank, world, port, seed_files, dynamic):
+  """2 servers + 2 clients: servers are assigned to clients automatically (client c <- server c), the seeds are
+  read BY THE SERVER from a file path (RemoteNodePathSamplerInput); optionally with dynamic RPC membership."""
+  import graphlearn_for_pytorch_b200.distributed as d
+  from graphlearn_for_pytorch_b200.sampler import RemoteNodePathSamplerInput
+  if rank < 2:
+    ds = build_partition(rank, 2)
+    d.init_server(2, rank, ds, '127.0.0.1', port, num_clients=2, is_dynamic=dynamic)
+    d.wait_and_shutdown_server()
+    return
+  crank = rank - 2
+  d.init_client(2, 2, crank, '127.0.0.1', port, is_dynamic=dynamic)
+  # one producer per server: the sampling workers of ALL servers form one RPC group (they serve each other's
+  # cross-partition hops), so both clients name the same rendezvous port
+  opts = d.RemoteDistSamplingWorkerOptions(num_workers=1, worker_concurrency=2, master_addr='127.0.0.1',
+                                           master_port=port + 1, buffer_size='16MB', prefetch_size=2)
+  assert opts.server_rank in (crank, [crank])                       # assignment by order
+  loader = d.DistNeighborLoader(None, [2, 2], RemoteNodePathSamplerInput(seed_files[crank]), batch_size=4,
+                                collect_features=True, with_edge=True, to_device=torch.device('cpu'),
+                                worker_options=opts)
+  expect = sorted(torch.load(seed_files[crank]).tolist())
+  for epoch in range(2):
+    seen = []
+    for b in loader:
+      check_batch(b)
+      seen += b.batch.tolist()
+    assert sorted(seen) == expect
+  loader.shutdown()
+  d.shutdown_client()
+
+
+@pytest.mark.parametrize('dynamic', [False, True])
+def test_server_client_auto_assignment_and_path_seeds(tmp_path, dynamic):
+  files = []
+  for c in range(2):
+    f = str(tmp_path / f'seeds_{c}.pt')
+    torch.save(torch.arange(c, N, 2)[:12], f)
+    files.append(f)
+  run_workers(_w_server_client_auto, world=4, args=(files, dynamic), timeout=400)
