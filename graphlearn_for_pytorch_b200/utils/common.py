@@ -32,6 +32,29 @@ def get_free_port(host: str = '127.0.0.1') -> int:
   return port
 
 
+def get_free_port_block(n: int = 8, host: str = '127.0.0.1', tries: int = 64) -> int:
+  """First port of `n` CONSECUTIVE free ports (callers that derive `port + k` rendezvous points from one base port
+  -- sampling worker groups, per-client channels -- would otherwise collide with unrelated sockets now and then)."""
+  import random
+  rng = random.Random()
+  for _ in range(tries):
+    base = rng.randrange(20000, 60000 - n)
+    socks = []
+    try:
+      for k in range(n):
+        sk = socket.socket()
+        sk.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 0)
+        sk.bind((host, base + k))
+        socks.append(sk)
+      return base
+    except OSError:
+      continue
+    finally:
+      for sk in socks:
+        sk.close()
+  return get_free_port(host)
+
+
 def merge_dict(in_dict: Dict[Any, Any], out_dict: Dict[Any, List[Any]]):
   for k, v in in_dict.items():
     out_dict.setdefault(k, []).append(v)

@@ -65,9 +65,9 @@ def _entry(rank, world, port, fn, args, err_q):
 
 def run_workers(fn, world=2, args=(), timeout=240):
   """Spawn `world` processes running fn(rank, world, port, *args); assert clean exit codes."""
-  from graphlearn_for_pytorch_b200.utils.common import get_free_port
+  from graphlearn_for_pytorch_b200.utils.common import get_free_port_block
   ctx = mp.get_context('spawn')
-  port = get_free_port()
+  port = get_free_port_block(8)      # workers derive port+1.. for their sampling groups
   err_q = ctx.Queue()
   procs = [ctx.Process(target=_entry, args=(r, world, port, fn, args, err_q)) for r in range(world)]
   for p in procs:

@@ -38,7 +38,7 @@ def test_igbh_pipeline_single_and_distributed(tmp_path):
         '--with_feature', '0', '--edge_assign_strategy', 'by_dst'])
   for r in (0, 1):
     _run(['examples/igbh/build_partition_feature.py', '--src_path', d, '--dst_path', parts, '--partition_idx', str(r)])
-  from graphlearn_for_pytorch_b200.utils.common import get_free_port
+  from graphlearn_for_pytorch_b200.utils.common import get_free_port_block as get_free_port
   port = get_free_port()
   outs = {}
 
@@ -60,7 +60,7 @@ def test_table_examples_single_and_distributed(tmp_path):
   _run(['examples/table/data_preprocess.py', '--out', tables, '--nodes', '3000', '--edges', '30000'])
   out = _run(['examples/table/train_products_sage.py', '--tables', tables, '--epochs', '1', '--max_steps', '5'])
   assert 'train-acc' in out
-  from graphlearn_for_pytorch_b200.utils.common import get_free_port
+  from graphlearn_for_pytorch_b200.utils.common import get_free_port_block as get_free_port
   port = get_free_port()
   outs = {}
 
@@ -95,7 +95,7 @@ def _run_ranks(cmds, timeout=600):
 def test_distributed_examples_and_benchmark(tmp_path):
   """examples/distributed/* and benchmarks/bench_dist_neighbor_loader.py on a freshly partitioned graph:
   worker mode with sampling SUB-PROCESSES (needs the __main__ guards), server-client mode, ZeRO + Join."""
-  from graphlearn_for_pytorch_b200.utils.common import get_free_port
+  from graphlearn_for_pytorch_b200.utils.common import get_free_port_block as get_free_port
   parts = str(tmp_path / 'parts')
   _run(['examples/distributed/partition_dataset.py', '--out', parts, '--parts', '2', '--nodes', '4000', '--edges', '40000'])
   port = get_free_port()
@@ -139,7 +139,7 @@ def test_cluster_launcher_local_plan(tmp_path):
   import yaml
   parts = str(tmp_path / 'parts')
   _run(['examples/distributed/partition_dataset.py', '--out', parts, '--parts', '2', '--nodes', '3000', '--edges', '30000'])
-  from graphlearn_for_pytorch_b200.utils.common import get_free_port
+  from graphlearn_for_pytorch_b200.utils.common import get_free_port_block as get_free_port
   cfg = yaml.safe_load(open(os.path.join(ROOT, 'examples', 'distributed', 'dist_train_sage_config.yml')))
   cfg['master_port'] = get_free_port()
   cfg['args'] = [parts if a == '/tmp/glt_parts' else a for a in cfg['args']]
