@@ -31,6 +31,7 @@ class DistServer(object):
     self._buffer_pool: Dict[int, ShmChannel] = {}
     self._key_to_producer: Dict[str, int] = {}
     self._epoch: Dict[int, int] = {}
+    self._ready: Dict[int, threading.Event] = {}
 
   def shutdown(self):
     for pid in list(self._producer_pool.keys()):
@@ -79,28 +80,42 @@ class DistServer(object):
                                worker_options: RemoteDistSamplingWorkerOptions) -> int:
     if isinstance(sampler_input, RemoteSamplerInput):
       sampler_input = sampler_input.to_local_sampler_input(dataset=self.dataset)
+    # NB: the lock must NOT be held while the sampling workers start.  Their RPC group spans all servers, so
+    # server A blocks in init() until server B has started the workers of the SAME client; if B is meanwhile
+    # (under its lock) starting another client's workers, which in turn wait for A, the two servers deadlock.
     with self._lock:
       key = worker_options.worker_key
       if key is not None and key in self._key_to_producer:
-        return self._key_to_producer[key]
-      pid = self._cur_producer_idx
-      self._cur_producer_idx += 1
-      buf = ShmChannel(worker_options.buffer_capacity, worker_options.buffer_size)
-      ctx = get_context()
-      worker_options._set_worker_ranks(ctx)
-      prod = DistMpSamplingProducer(self.dataset, sampler_input, sampling_config, worker_options, buf)
-      prod.init()
-      self._producer_pool[pid] = prod
-      self._buffer_pool[pid] = buf
-      self._epoch[pid] = -1
-      if key is not None:
-        self._key_to_producer[key] = pid
+        pid = self._key_to_producer[key]
+        ready = self._ready.get(pid)
+      else:
+        ready = None
+        pid = self._cur_producer_idx
+        self._cur_producer_idx += 1
+        buf = ShmChannel(worker_options.buffer_capacity, worker_options.buffer_size)
+        ctx = get_context()
+        worker_options._set_worker_ranks(ctx)
+        prod = DistMpSamplingProducer(self.dataset, sampler_input, sampling_config, worker_options, buf)
+        self._producer_pool[pid] = prod
+        self._buffer_pool[pid] = buf
+        self._epoch[pid] = -1
+        self._ready[pid] = threading.Event()
+        if key is not None:
+          self._key_to_producer[key] = pid
+    if ready is not None:          # another request is (or was) creating this producer: wait until it is usable
+      ready.wait()
       return pid
+    try:
+      prod.init()
+    finally:
+      self._ready[pid].set()
+    return pid
 
   def destroy_sampling_producer(self, producer_id: int):
     with self._lock:
       prod = self._producer_pool.pop(producer_id, None)
       self._buffer_pool.pop(producer_id, None)
+      self._ready.pop(producer_id, None)
       for k, v in list(self._key_to_producer.items()):
         if v == producer_id:
           self._key_to_producer.pop(k)

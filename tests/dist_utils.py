@@ -54,6 +54,9 @@ def check_batch(b, with_edge=True):
 
 
 def _entry(rank, world, port, fn, args, err_q):
+  if os.environ.get('GLT_TEST_FAULT_TIMEOUT'):      # hang diagnosis: dump every thread's stack after N seconds
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ['GLT_TEST_FAULT_TIMEOUT']), exit=False)
   try:
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
@@ -63,6 +66,18 @@ def _entry(rank, world, port, fn, args, err_q):
     raise
 
 
+def _kill_tree(pid):
+  try:
+    import psutil
+    for c in psutil.Process(pid).children(recursive=True):
+      try:
+        c.kill()
+      except Exception:  # noqa: BLE001
+        pass
+  except Exception:  # noqa: BLE001
+    pass
+
+
 def run_workers(fn, world=2, args=(), timeout=240):
   """Spawn `world` processes running fn(rank, world, port, *args); assert clean exit codes."""
   from graphlearn_for_pytorch_b200.utils.common import get_free_port_block
@@ -70,16 +85,20 @@ def run_workers(fn, world=2, args=(), timeout=240):
   port = get_free_port_block(8)      # workers derive port+1.. for their sampling groups
   err_q = ctx.Queue()
   procs = [ctx.Process(target=_entry, args=(r, world, port, fn, args, err_q)) for r in range(world)]
+  import time
   for p in procs:
     p.start()
+  deadline = time.time() + timeout            # ONE deadline for the whole group, not one per process
   for p in procs:
-    p.join(timeout)
+    p.join(max(0.0, deadline - time.time()))
   errs = []
   while not err_q.empty():
     errs.append(err_q.get())
   for p in procs:
     if p.is_alive():
+      _kill_tree(p.pid)                        # sampling sub-processes must not outlive a stuck test
       p.terminate()
+      p.join(10)
       errs.append(('?', 'timeout'))
   assert not errs, '\n'.join(f'[rank {r}] {e}' for r, e in errs)
   assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
