@@ -93,3 +93,63 @@ def test_hgt_trains_on_hetero_batches():
       first = first if first is not None else loss.item()
       last = loss.item()
   assert last < 0.7 * first, (first, last)
+
+
+def test_transposed_gather_backward_equals_scatter_backward():
+  """Algorithm behind csrc/cuda/transpose.cu (EXPERIMENTAL kernels): the backward of the ELL mean aggregation
+  computed as an atomics-free GATHER over a transposed adjacency (sources -> targets, hop-ordered segments)
+  equals the scatter formulation the engine uses today, for every layer's hop prefix."""
+  torch.manual_seed(0)
+  cum = [0, 40, 150, 380]                       # local node ids before hop 0 / 1 / 2's new nodes
+  k = [5, 4]
+  d = 16
+  ell, deg = [], torch.zeros(cum[2], dtype=torch.int64)
+  for h in range(2):
+    rows = cum[h + 1] - cum[h]
+    e = torch.randint(-1, cum[h + 2], (rows, k[h]))
+    dg = torch.randint(0, k[h] + 1, (rows,))
+    ell.append(e); deg[cum[h]:cum[h + 1]] = dg
+  # transposed adjacency, hop 0 entries first inside every segment
+  n_src = cum[3]
+  cnt = torch.zeros(2, n_src, dtype=torch.int64)
+  for h in range(2):
+    for r in range(cum[h + 1] - cum[h]):
+      for j in range(int(deg[cum[h] + r])):
+        s = int(ell[h][r, j])
+        if s >= 0:
+          cnt[h, s] += 1
+  upto = cnt.cumsum(0)
+  off = torch.cat([torch.zeros(1, dtype=torch.int64), upto[1].cumsum(0)])
+  tgt = torch.full((int(off[-1]),), -1)
+  cur = torch.zeros(2, n_src, dtype=torch.int64)
+  for h in range(2):
+    before = upto[h - 1] if h > 0 else torch.zeros(n_src, dtype=torch.int64)
+    for r in range(cum[h + 1] - cum[h]):
+      for j in range(int(deg[cum[h] + r])):
+        s = int(ell[h][r, j])
+        if s >= 0:
+          tgt[off[s] + before[s] + cur[h, s]] = cum[h] + r
+          cur[h, s] += 1
+  for nh in (1, 2):                              # layer that aggregates over hops 0..nh-1
+    T, S = cum[nh], cum[nh + 1]
+    dA = torch.randn(T, 2 * d)                   # gradient of [mean | self]
+    # scatter formulation
+    dH = torch.zeros(S, d)
+    dH[:T] += dA[:, d:]
+    for h in range(nh):
+      for r in range(cum[h + 1] - cum[h]):
+        t = cum[h] + r
+        dg = int(deg[t])
+        for j in range(dg):
+          s = int(ell[h][r, j])
+          if s >= 0:
+            dH[s] += dA[t, :d] / dg
+    # gather formulation
+    out = torch.zeros(S, d)
+    for s in range(S):
+      acc = dA[s, d:].clone() if s < T else torch.zeros(d)
+      for e in range(int(upto[nh - 1, s])):
+        t = int(tgt[off[s] + e])
+        acc += dA[t, :d] / int(deg[t])
+      out[s] = acc
+    assert torch.allclose(out, dH, atol=1e-5), nh
