@@ -16,7 +16,7 @@ from ..loader.link_loader import get_edge_label_index
 from ..sampler import (EdgeSamplerInput, HeteroSamplerOutput, NegativeSampling, NodeSamplerInput,
                        RemoteSamplerInput, SamplerOutput, SamplingConfig, SamplingType)
 from ..typing import EdgeType, NodeType, Split, from_str, reverse_edge_type
-from ..utils.exit_status import python_exit_status
+from ..utils.exit_status import is_python_exiting
 from .dist_context import get_context
 from .dist_dataset import DistDataset
 from .dist_options import (AllDistSamplingWorkerOptions, CollocatedDistSamplingWorkerOptions,
@@ -161,7 +161,7 @@ class DistLoader(object):
 
   # ------------------------------------------------------------------ lifecycle
   def __del__(self):
-    if python_exit_status is True or python_exit_status is None:
+    if is_python_exiting():
       return
     self.shutdown()
 

@@ -1,10 +1,11 @@
-from .tensor import *
-from .common import *
-from .device import *
-from .units import *
-from .exit_status import *
-from .mixin import *
-from .singleton import *
-from .topo import *
-from .synthetic import *
-from .tracing import *
+"""Utilities: every public name of the sub-modules is re-exported here (`glt.utils.get_free_port`, ...)."""
+import importlib
+
+_SUBMODULES = ('tensor', 'common', 'device', 'units', 'exit_status', 'mixin', 'singleton', 'topo', 'synthetic', 'tracing')
+
+for _name in _SUBMODULES:
+  _mod = importlib.import_module(f'{__name__}.{_name}')
+  _public = getattr(_mod, '__all__', None) or [k for k in vars(_mod) if not k.startswith('_')]
+  for _k in _public:
+    globals()[_k] = getattr(_mod, _k)
+del _name, _mod, _public, _k
