@@ -19,6 +19,8 @@ QueueTimeoutError, QueueClosedError = _native_errors()
 
 
 class ChannelBase(ABC):
+  """A FIFO of `SampleMessage`s (dict name -> tensor) between a sampling producer and a consumer: `send`, `recv`,
+  `empty` (reference: python/channel/base.py:26-52)."""
   @abstractmethod
   def send(self, msg: SampleMessage, **kwargs):
     ...

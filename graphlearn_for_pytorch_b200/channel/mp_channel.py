@@ -7,6 +7,8 @@ from .base import ChannelBase, QueueTimeoutError, SampleMessage
 
 
 class MpChannel(ChannelBase):
+  """`torch.multiprocessing.Queue` transport (tensors travel through torch's shared-memory reducers); simple, slower
+  than `ShmChannel` (reference: python/channel/mp_channel.py:21-45)."""
   def __init__(self, capacity: int = 128, **kwargs):
     self._q = mp.get_context('spawn').Queue(maxsize=capacity)
 

@@ -11,6 +11,9 @@ from .base import ChannelBase, SampleMessage
 
 
 class RemoteReceivingChannel(ChannelBase):
+  """Client side of the server-client mode: keeps `prefetch_size` asynchronous `fetch_one_sampled_message` requests
+  in flight per server and hands the messages out in arrival order; end of epoch is signalled by the servers
+  (reference: python/channel/remote_channel.py:24-131)."""
   def __init__(self, server_rank: Union[int, List[int]], producer_id: Union[int, List[int]],
                prefetch_size: int = 4):
     self.server_rank_list = server_rank if isinstance(server_rank, list) else [server_rank]

@@ -17,6 +17,12 @@ from .reorder import sort_by_in_degree  # noqa: F401 (re-export convenience)
 
 
 class Dataset(object):
+  """Graph(s) + node / edge features + labels + splits, homogeneous or heterogeneous (dicts keyed by node / edge type).
+
+  Build it with `init_graph`, `init_node_features`, `init_edge_features`, `init_node_labels`, `init_node_split` /
+  `random_node_split`, or from a property-graph fragment with `load_vineyard`.  `edge_dir='out'` samples along CSR
+  rows (src -> dst), `'in'` along CSC columns.  Picklable across processes (`share_ipc`).
+  (Reference: python/data/dataset.py:33-450.)"""
   def __init__(self, graph=None, node_features=None, edge_features=None, node_labels=None,
                edge_dir: str = 'out', node_split=None):
     self.graph = graph

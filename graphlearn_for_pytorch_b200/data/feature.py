@@ -31,6 +31,13 @@ class DeviceGroup(object):
 
 
 class Feature(object):
+  """Feature store with a hot tier in GPU memory and a cold tier in pinned host memory.
+
+  Rows `[0, split_ratio * N)` of `feature_tensor` (order them by hotness with `sort_by_in_degree`, which also returns
+  the `id2index` map) are sharded over the GPUs of the caller's `DeviceGroup`; the rest stays in pinned (or shared,
+  page-locked in place) host memory.  `feature[ids]` is ONE gather kernel over all tiers, peer GPUs included.
+  `cpu_get(ids)` is the host-side lookup used by RPC callees.  Pickling hands GPU shards to other processes through
+  raw CUDA-IPC handles opened on the consumer's device.  (Reference: python/data/feature.py:32-283.)"""
   def __init__(self, feature_tensor: torch.Tensor, id2index: Optional[torch.Tensor] = None,
                split_ratio: float = 0.0, device_group_list: Optional[List[DeviceGroup]] = None,
                device: Optional[int] = None, with_gpu: bool = True,

@@ -47,6 +47,9 @@ def _parse_feature_column(col: np.ndarray, sep=':') -> torch.Tensor:
 
 
 class TableDataset(Dataset):
+  """`Dataset` filled from tables: edge tables `(src_id, dst_id[, weight])` and node tables `(id, feature[, label])`
+  given as parquet / CSV paths, pyarrow tables, dicts of columns or callables (reference: ODPS tables through
+  common_io, python/data/table_dataset.py:27-144)."""
   def load(self, edge_tables: Optional[Dict[EdgeType, object]] = None,
            node_tables: Optional[Dict[NodeType, object]] = None,
            graph_mode: str = 'ZERO_COPY', sort_func: Optional[Callable] = None,

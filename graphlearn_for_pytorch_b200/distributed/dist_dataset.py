@@ -18,6 +18,12 @@ from ..utils.tensor import convert_to_tensor, id2idx, share_memory, squeeze
 
 
 class DistDataset(Dataset):
+  """One partition of a partitioned dataset + the partition books that route ids to their owners.
+
+  `load(root, partition_idx)` reads the on-disk format written by the partitioners (feature caches are prepended and
+  the feature book rewritten so cached remote rows resolve locally); `load_vineyard` builds it from a property-graph
+  fragment; `from_p2p` wraps NVLink-mapped shards (no RPC on the data path).  (Reference:
+  python/distributed/dist_dataset.py:30-330.)"""
   def __init__(self, num_partitions: int = 1, partition_idx: int = 0, graph_partition=None,
                node_feature_partition=None, edge_feature_partition=None, whole_node_labels=None,
                node_pb=None, edge_pb=None, node_feat_pb=None, edge_feat_pb=None, edge_dir: str = 'out',

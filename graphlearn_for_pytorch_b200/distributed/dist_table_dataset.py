@@ -51,6 +51,9 @@ class DistTableRandomPartitioner(DistRandomPartitioner):
 
 
 class DistTableDataset(DistDataset):
+  """Every worker reads a SLICE of the node / edge tables; the workers partition the graph online together
+  (`DistTableRandomPartitioner` over RPC) and each loads its partition (reference:
+  python/distributed/dist_table_dataset.py:30-250)."""
   def load(self, num_nodes, edge_tables, node_tables=None, graph_mode: str = 'CPU', feature_with_gpu=False,
            label_col: Optional[str] = 'label', id_col: str = 'id', device=None, **kwargs):
     """Collectively partition the table slices and load this rank's partition."""

@@ -26,6 +26,10 @@ def wrap_torch_future(f: torch.futures.Future) -> asyncio.futures.Future:
 
 
 class ConcurrentEventLoop(object):
+  """An asyncio loop on its own thread with a concurrency bound: `add_task(coro, callback)` schedules, `run_task`
+  blocks for the result, `wait_all` drains.  Lets one sampler overlap the remote hops of several batches; task
+  exceptions are re-raised to the caller instead of being logged and dropped (reference:
+  python/distributed/event_loop.py:37-113)."""
   def __init__(self, concurrency: int):
     self._concurrency = concurrency
     self._sem = threading.BoundedSemaphore(concurrency)

@@ -10,6 +10,9 @@ from .link_loader import LinkLoader
 
 
 class LinkNeighborLoader(LinkLoader):
+  """Mini-batches of seed LINKS with their multi-hop neighbourhoods and (binary or triplet) negative samples;
+  batches carry `edge_label_index` / `edge_label` (binary) or `src_index` / `dst_pos_index` / `dst_neg_index`
+  (triplet) in local indices (reference: python/loader/link_neighbor_loader.py:27-170)."""
   def __init__(self, data: Dataset, num_neighbors: NumNeighbors,
                neighbor_sampler: Optional[NeighborSampler] = None, edge_label_index: InputEdges = None,
                edge_label: Optional[torch.Tensor] = None, neg_sampling: Optional[NegativeSampling] = None,

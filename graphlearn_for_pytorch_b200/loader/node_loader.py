@@ -62,6 +62,9 @@ class SeedBatcher(object):
 
 
 class NodeLoader(object):
+  """Base of the node-seeded loaders: batches seed ids (`SeedBatcher`: shuffle, drop_last, resumable position),
+  turns sampler output into PyG-shaped `Data` / `HeteroData` with features and labels attached
+  (reference: python/loader/node_loader.py:27-112)."""
   def __init__(self, data: Dataset, node_sampler: BaseSampler, input_nodes: InputNodes,
                device: torch.device = None, batch_size: int = 1, shuffle: bool = False,
                drop_last: bool = False, seed: Optional[int] = None, **kwargs):

@@ -13,6 +13,8 @@ from .node_loader import NodeLoader
 
 
 class SubGraphLoader(NodeLoader):
+  """Induced sub-graphs around batches of seed nodes (optionally after k-hop expansion); `mapping` locates the
+  seeds inside `node` (reference: python/loader/subgraph_loader.py:25-96)."""
   def __init__(self, data: Dataset, input_nodes: InputNodes, num_neighbors: Optional[NumNeighbors] = None,
                neighbor_sampler: Optional[NeighborSampler] = None, batch_size: int = 1,
                shuffle: bool = False, drop_last: bool = False, with_edge: bool = False,

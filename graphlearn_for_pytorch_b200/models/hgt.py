@@ -16,6 +16,8 @@ EdgeType = Tuple[str, str, str]
 
 
 class HGTConv(nn.Module):
+  """Heterogeneous Graph Transformer layer: per-type K/Q/V projections, per-relation attention and message
+  transforms with relation priors, softmax over the incoming edges of every target, gated skip connection."""
   def __init__(self, in_channels: Dict[str, int], out_channels: int, node_types: List[str],
                edge_types: List[EdgeType], heads: int = 4):
     super().__init__()

@@ -18,6 +18,10 @@ from .partition_book import GLTPartitionBook, PartitionBook
 
 
 class FrequencyPartitioner(PartitionerBase):
+  """Hotness-aware partitioning: `probs[p][v]` = probability that partition p's training seeds reach node v
+  (`NeighborSampler.sample_prob`); chunks of nodes go to the partition that touches them most, subject to a balance
+  budget, and every partition additionally caches the hottest remote features (`cache_memory_budget` /
+  `cache_ratio`) (reference: python/partition/frequency_partitioner.py:25-206)."""
   def __init__(self, output_dir: str, num_parts: int, num_nodes, edge_index,
                probs: Union[List[torch.Tensor], Dict[NodeType, List[torch.Tensor]]],
                node_feat=None, node_feat_dtype: torch.dtype = torch.float32, edge_feat=None,

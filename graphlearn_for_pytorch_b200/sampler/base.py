@@ -197,6 +197,8 @@ class SamplingConfig:
 
 
 class BaseSampler(ABC):
+  """Interface every sampler implements: `sample_from_nodes`, `sample_from_edges`, `subgraph`
+  (reference: python/sampler/base.py:355-411)."""
   @abstractmethod
   def sample_from_nodes(self, inputs: NodeSamplerInput, **kwargs):
     ...
@@ -218,6 +220,7 @@ class RemoteSamplerInput(ABC):
 
 
 class RemoteNodePathSamplerInput(RemoteSamplerInput):
+  """Seeds stored in a file that the SERVER can read (`torch.load(node_path)`); the client only ships the path."""
   def __init__(self, node_path: str, input_type: Optional[str] = None):
     self.node_path = node_path
     self.input_type = input_type
@@ -227,6 +230,7 @@ class RemoteNodePathSamplerInput(RemoteSamplerInput):
 
 
 class RemoteNodeSplitSamplerInput(RemoteSamplerInput):
+  """Seeds = the server-side dataset's train / valid / test split (`typing.Split`)."""
   def __init__(self, split: Split, input_type: Optional[str] = None):
     self.split = split
     self.input_type = input_type
