@@ -17,8 +17,7 @@ EdgeType = Tuple[str, str, str]
 def _segment_mean(src_feat: torch.Tensor, dst_index: torch.Tensor, n_dst: int) -> torch.Tensor:
   out = torch.zeros(n_dst, src_feat.shape[1], dtype=src_feat.dtype, device=src_feat.device)
   out.index_add_(0, dst_index, src_feat)
-  deg = torch.zeros(n_dst, dtype=src_feat.dtype, device=src_feat.device)
-  deg.index_add_(0, dst_index, torch.ones_like(dst_index, dtype=src_feat.dtype))
+  deg = torch.bincount(dst_index, minlength=n_dst).to(src_feat.dtype)
   return out / deg.clamp(min=1).unsqueeze(1)
 
 
@@ -31,6 +30,15 @@ class RelSAGEConv(nn.Module):
     self.lin_r = nn.Linear(in_dst, out, bias=False)
 
   def forward(self, x_src, x_dst, edge_index):
+    if self.lin_l.in_features > self.lin_l.out_features:
+      # the mean is linear: project the (fewer, wider) source rows first, so that the per-edge gather moves
+      # `out`-wide rows instead of `in`-wide ones (IGBH: 1024 -> 256, 4x less gather traffic); the bias is
+      # added after the aggregation so that isolated targets still get exactly lin_l(0) = b
+      proj = F.linear(x_src, self.lin_l.weight)
+      agg = _segment_mean(proj[edge_index[0]], edge_index[1], x_dst.shape[0])
+      if self.lin_l.bias is not None:
+        agg = agg + self.lin_l.bias
+      return agg + self.lin_r(x_dst)
     agg = _segment_mean(x_src[edge_index[0]], edge_index[1], x_dst.shape[0])
     return self.lin_l(agg) + self.lin_r(x_dst)
 

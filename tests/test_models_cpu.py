@@ -153,3 +153,19 @@ def test_transposed_gather_backward_equals_scatter_backward():
         acc += dA[t, :d] / int(deg[t])
       out[s] = acc
     assert torch.allclose(out, dH, atol=1e-5), nh
+
+
+def test_rel_sage_project_first_is_exact():
+  """RelSAGEConv projects before aggregating when in > out (mean is linear): same result as aggregate-first,
+  including isolated destination nodes (which must still receive the bias)."""
+  from graphlearn_for_pytorch_b200.models.rgnn import RelSAGEConv, _segment_mean
+  torch.manual_seed(0)
+  conv = RelSAGEConv(64, 16, 8)                       # in_src 64 > out 8 -> project-first path
+  x_src, x_dst = torch.randn(50, 64), torch.randn(30, 16)
+  ei = torch.stack([torch.randint(0, 50, (200,)), torch.randint(0, 25, (200,))])   # dst 25..29 isolated
+  ref = conv.lin_l(_segment_mean(x_src[ei[0]], ei[1], 30)) + conv.lin_r(x_dst)
+  assert torch.allclose(conv(x_src, x_dst, ei), ref, atol=1e-5)
+  conv2 = RelSAGEConv(8, 16, 32)                      # in < out -> aggregate-first path, same contract
+  x2 = torch.randn(50, 8)
+  ref2 = conv2.lin_l(_segment_mean(x2[ei[0]], ei[1], 30)) + conv2.lin_r(x_dst)
+  assert torch.allclose(conv2(x2, x_dst, ei), ref2, atol=1e-5)
