@@ -17,7 +17,11 @@ EdgeType = Tuple[str, str, str]
 def _segment_mean(src_feat: torch.Tensor, dst_index: torch.Tensor, n_dst: int) -> torch.Tensor:
   out = torch.zeros(n_dst, src_feat.shape[1], dtype=src_feat.dtype, device=src_feat.device)
   out.index_add_(0, dst_index, src_feat)
-  deg = torch.bincount(dst_index, minlength=n_dst).to(src_feat.dtype)
+  if dst_index.is_cuda:   # bincount synchronises with the host on CUDA (it needs max()); index_add does not
+    deg = torch.zeros(n_dst, dtype=src_feat.dtype, device=src_feat.device)
+    deg.index_add_(0, dst_index, torch.ones_like(dst_index, dtype=src_feat.dtype))
+  else:
+    deg = torch.bincount(dst_index, minlength=n_dst).to(src_feat.dtype)
   return out / deg.clamp(min=1).unsqueeze(1)
 
 
