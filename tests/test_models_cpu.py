@@ -169,3 +169,37 @@ def test_rel_sage_project_first_is_exact():
   x2 = torch.randn(50, 8)
   ref2 = conv2.lin_l(_segment_mean(x2[ei[0]], ei[1], 30)) + conv2.lin_r(x_dst)
   assert torch.allclose(conv2(x2, x_dst, ei), ref2, atol=1e-5)
+
+
+def test_graph_sage_trainer_learns_and_resumes(tmp_path):
+  """GraphSageTrainer = the engine's step API on any device: it learns a learnable labelling, evaluates, and a
+  restored state_dict continues with the same sampler stream (identical next loss)."""
+  from graphlearn_for_pytorch_b200.models import GraphSageTrainer
+  from graphlearn_for_pytorch_b200.utils.synthetic import rmat_edges
+  torch.manual_seed(1)
+  n, d, c = 3000, 16, 5
+  ei = rmat_edges(n, 15000, seed=2)
+  ei = torch.cat([ei, ei.flip(0)], 1)
+  x = torch.randn(n, d)
+  y = (x @ torch.randn(d, c)).argmax(1)
+  ds = glt.data.Dataset()
+  ds.init_graph(ei, graph_mode='CPU', num_nodes=n)
+  ds.init_node_features(x, with_gpu=False)
+
+  def make():
+    return GraphSageTrainer(ds.graph, ds.node_features, y, in_dim=d, fanouts=[5, 5], hidden=32, num_classes=c,
+                            lr=1e-2, seed=3)
+  tr = make()
+  first = None
+  for i in range(40):
+    loss = float(tr.train_step(torch.randperm(n)[:256]))
+    first = first if first is not None else loss
+  ev_loss, correct, cnt = tr.evaluate_batch(torch.arange(512))
+  assert loss < 0.8 * first and cnt == 512 and correct / cnt > 1.5 / c
+  import copy
+  state = copy.deepcopy(tr.state_dict())        # state_dict() returns live references, like nn.Module
+  seeds = torch.arange(300, 556)
+  expect = float(tr.train_step(seeds))
+  tr2 = make()
+  tr2.load_state_dict(state)
+  assert abs(float(tr2.train_step(seeds)) - expect) < 1e-5
