@@ -47,8 +47,23 @@ if args.mode == 'loader':
       opt.zero_grad(); loss.backward(); opt.step()
       tot += float(loss.detach()); correct += int((out.argmax(1) == tgt).sum()); seen += b.batch_size
     print(f'epoch {epoch}: loss {tot / len(loader):.4f} acc {correct / seen:.4f} time {time.time() - t0:.2f}s')
+elif not cuda:
+  # no GPU: the same step-level loop on the device-agnostic trainer (sampler + eager GraphSAGE + torch Adam)
+  from graphlearn_for_pytorch_b200.models import GraphSageTrainer
+  print('no CUDA device: --mode engine falls back to GraphSageTrainer (same train_step/evaluate_batch API)')
+  ds = glt.data.Dataset()
+  ds.init_graph(ei, graph_mode='CPU', directed=False)
+  ds.init_node_features(x, with_gpu=False)
+  tr = GraphSageTrainer(ds.graph, ds.node_features, y, in_dim=x.shape[1], fanouts=[15, 10, 5], hidden=256,
+                        num_classes=n_cls, device=device)
+  for epoch in range(args.epochs):
+    t0 = time.time()
+    perm = torch.randperm(train_idx.numel())
+    losses = [float(tr.train_step(train_idx[perm[i:i + args.batch]]))
+              for i in range(0, perm.numel() - args.batch + 1, args.batch)]
+    l, c, n = tr.evaluate_batch(train_idx[:args.batch])
+    print(f'epoch {epoch}: loss {sum(losses) / max(len(losses), 1):.4f} eval-acc {c / n:.4f} time {time.time() - t0:.2f}s')
 else:
-  assert cuda, 'the engine needs a GPU'
   in_dim = (x.shape[1] + 63) // 64 * 64
   feats = torch.zeros(args.nodes, in_dim, dtype=torch.bfloat16, device=device)
   feats[:, :x.shape[1]] = x.to(device).to(torch.bfloat16)

@@ -121,6 +121,8 @@ def test_distributed_examples_and_benchmark(tmp_path):
 
 @pytest.mark.parametrize('args', [
     ['examples/train_sage_products.py', '--nodes', '4000', '--edges', '40000', '--epochs', '1', '--batch', '256'],
+    ['examples/train_sage_products.py', '--mode', 'engine', '--nodes', '4000', '--edges', '40000', '--epochs', '1',
+     '--batch', '200'],
     ['examples/graph_sage_unsup.py'],
     ['examples/hetero/train_rgnn_igbh.py', '--papers', '2000', '--fanout', '4,4', '--epochs', '1', '--batch', '256'],
     ['examples/hetero/train_rgnn_igbh.py', '--papers', '2000', '--fanout', '4,4', '--epochs', '1', '--batch', '256',
@@ -128,7 +130,7 @@ def test_distributed_examples_and_benchmark(tmp_path):
     ['examples/hetero/bipartite_sage_unsup.py'],
     ['examples/feature_mp.py'],
     ['examples/seal_link_pred.py', '--links', '400', '--epochs', '2'],
-], ids=lambda a: os.path.basename(a[0]) + ('-hgt' if 'hgt' in a else ''))
+], ids=lambda a: os.path.basename(a[0]) + ('-hgt' if 'hgt' in a else '') + ('-engine' if 'engine' in a else ''))
 def test_single_process_examples(args):
   out = _run(args)
   assert 'loss' in out or 'first column' in out
