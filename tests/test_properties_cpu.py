@@ -89,3 +89,32 @@ def test_multi_hop_output_is_a_consistent_subgraph(g, k, seed):
   edge_set = set(zip(ei[0].tolist(), ei[1].tolist()))
   assert all((a, b) in edge_set for a, b in zip(src.tolist(), dst.tolist()))
   assert sum(out.num_sampled_nodes) == out.node.numel() and sum(out.num_sampled_edges) == out.row.numel()
+
+
+@settings(max_examples=15, deadline=None)
+@given(graphs(max_nodes=30, max_edges=150), st.integers(2, 4), st.sampled_from(['by_src', 'by_dst']),
+       st.integers(1, 9), st.booleans())
+def test_partitioners_cover_every_node_and_edge_exactly_once(g, parts, strategy, chunk, use_range):
+  """For ANY graph / partition count / edge-assignment strategy / chunk size: partitions are disjoint, their union
+  is the graph, edges follow the chosen endpoint's owner, feature rows travel with their ids."""
+  import tempfile
+  from graphlearn_for_pytorch_b200.partition import RandomPartitioner, RangePartitioner, load_partition
+  from graphlearn_for_pytorch_b200.utils.synthetic import id_features
+  n, ei = g
+  cls = RangePartitioner if use_range else RandomPartitioner
+  with tempfile.TemporaryDirectory() as d:
+    cls(d, parts, n, ei, node_feat=id_features(n, 4), edge_feat=id_features(max(ei.shape[1], 1), 2)[:ei.shape[1]],
+        edge_assign_strategy=strategy, chunk_size=chunk).partition()
+    nodes, edges = [], []
+    for p in range(parts):
+      _, _, gp, nf, ef, npb, epb = load_partition(d, p)
+      rows, cols = gp.edge_index
+      owner_side = rows if strategy == 'by_src' else cols
+      assert torch.all(npb[owner_side] == p)
+      assert torch.equal(ei[0][gp.eids], rows) and torch.equal(ei[1][gp.eids], cols)
+      edges += gp.eids.tolist()
+      assert torch.equal(nf.feats[:, 0].long(), nf.ids) and torch.all(npb[nf.ids] == p)
+      nodes += nf.ids.tolist()
+      if ef is not None and ef.ids.numel() > 0:
+        assert torch.equal(ef.feats[:, 0].long(), ef.ids)
+    assert sorted(nodes) == list(range(n)) and sorted(edges) == list(range(ei.shape[1]))
