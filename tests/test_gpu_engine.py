@@ -285,3 +285,32 @@ def test_gather_backward_matches_pytorch(native):
     boff, _ = eng._b_off[l - 1]
     gb_ref = params[l - 1][1].grad
     assert (eng.g32[boff:boff + n] - gb_ref).abs().max() / gb_ref.abs().max().clamp(min=1e-6) < 5e-2, f'db{l}'
+
+
+@experimental
+def test_engine_and_trainer_learn_the_same_task(native):
+  """Semantic cross-check of the fused engine against the eager GraphSageTrainer (autograd, fp32): both must drive
+  the loss of a learnable labelling down at a comparable rate on the same graph."""
+  from graphlearn_for_pytorch_b200.models import GraphSageTrainer
+  N, Fdim, C = 6000, 128, 8
+  ei, topo = rmat_csr(N, 120000, seed=3)
+  g = glt.data.Graph(topo, 'CUDA', 0)
+  torch.manual_seed(0)
+  x = torch.randn(N, Fdim, device=DEV)
+  y = (x @ torch.randn(Fdim, C, device=DEV)).argmax(1)
+  feats16 = x.to(torch.bfloat16)
+  ut = glt.data.UnifiedTensor(0, torch.bfloat16)
+  ut.append_shared_tensor(feats16)
+  eng = GraphSageEngine(g, ut._table(), y, in_dim=Fdim, num_nodes=N, fanouts=[5, 4], batch_size=256, hidden=128,
+                        num_classes=C, device=DEV, use_cuda_graph=False, seed=5, lr=1e-2)
+  ut32 = glt.data.UnifiedTensor(0, torch.float32)
+  ut32.append_shared_tensor(x)
+  tr = GraphSageTrainer(g, ut32, y, in_dim=Fdim, fanouts=[5, 4], hidden=128, num_classes=C, lr=1e-2, seed=5,
+                        device=DEV)
+  le, lt = [], []
+  for i in range(60):
+    seeds = torch.randperm(N, device=DEV)[:256]
+    le.append(float(eng.train_step(seeds).item()))
+    lt.append(float(tr.train_step(seeds)))
+  assert le[-1] < 0.7 * le[0] and lt[-1] < 0.7 * lt[0]
+  assert abs(sum(le[-10:]) - sum(lt[-10:])) / 10 < 0.35          # same ball park after 60 steps
