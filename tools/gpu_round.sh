@@ -22,7 +22,7 @@ run ncu --profile-from-start off --set full --clock-control none --import-source
 run python benchmarks/bench_sampler.py 2>/dev/null | tail -1 > $OUT/${TAG}_bench_sampler.json
 run python benchmarks/bench_feature.py 2>/dev/null | tail -1 > $OUT/${TAG}_bench_feature.json
 if [[ "${GLT_B200_EXPERIMENTAL:-0}" == "1" ]]; then
-  GLT_B200_EXPERIMENTAL=1 run python -m pytest tests/test_gpu_engine.py -q -k "transposed or gather_backward" > $OUT/${TAG}_experimental.log 2>&1
+  GLT_B200_EXPERIMENTAL=1 run python -m pytest tests/test_gpu_engine.py -q -k "transposed or gather_backward or engine_and_trainer" > $OUT/${TAG}_experimental.log 2>&1
   tail -3 $OUT/${TAG}_experimental.log
   GLT_B200_GATHER_BWD=1 run python bench.py --steps 100 --warmup 10 > $OUT/${TAG}_bench_gather_bwd.json 2> /dev/null
   tail -c 200 $OUT/${TAG}_bench_gather_bwd.json
