@@ -8,6 +8,8 @@
 // does gather -> scatter-mean -> two Linear); the aggregation here consumes the
 // feature table *in place* (local or peer HBM) like GatherTensorKernel
 // (csrc/cuda/unified_tensor.cu:47-81) but never materialises x[n_id].
+#include <cstdlib>
+
 #include "device_utils.cuh"
 
 namespace glt {
@@ -32,7 +34,7 @@ __device__ __forceinline__ const uint8_t* src_row(const SageAggArgs& a, int s) {
 }
 
 // LPR lanes cooperate on one target row; each lane owns VPL 16-byte vectors.
-template <int LPR, int VPL>
+template <int LPR, int VPL, int NB>
 __global__ void __launch_bounds__(256) k_sage_aggregate(SageAggArgs a) {
   constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31;
@@ -65,14 +67,37 @@ __global__ void __launch_bounds__(256) k_sage_aggregate(SageAggArgs a) {
         if (s >= 0) my_ptr = src_row(a, s);
       }
       const int cnt = min(LPR, dg - j0);
-      for (int jj = 0; jj < cnt; ++jj) {
-        const uint8_t* p = reinterpret_cast<const uint8_t*>(
-            __shfl_sync(gmask, reinterpret_cast<unsigned long long>(my_ptr), jj, LPR));
-        if (p == nullptr) continue;
+      if (NB == 1) {
+        for (int jj = 0; jj < cnt; ++jj) {
+          const uint8_t* p = reinterpret_cast<const uint8_t*>(
+              __shfl_sync(gmask, reinterpret_cast<unsigned long long>(my_ptr), jj, LPR));
+          if (p == nullptr) continue;
 #pragma unroll
-        for (int v = 0; v < VPL; ++v) {
-          const int c = v * LPR + gl;
-          if (c < nvec) bf16x8_accum(ld_nc_v4(p + c * 16), acc[v]);
+          for (int v = 0; v < VPL; ++v) {
+            const int c = v * LPR + gl;
+            if (c < nvec) bf16x8_accum(ld_nc_v4(p + c * 16), acc[v]);
+          }
+        }
+      } else {
+        // EXPERIMENTAL (GLT_B200_AGG_BATCH=1): NB neighbour rows in flight per lane group before accumulating
+        for (int jb = 0; jb < cnt; jb += NB) {
+          uint4 buf[NB][VPL];
+#pragma unroll
+          for (int q = 0; q < NB; ++q) {
+            const int jj = min(jb + q, LPR - 1);
+            const uint8_t* p = reinterpret_cast<const uint8_t*>(
+                __shfl_sync(gmask, reinterpret_cast<unsigned long long>(my_ptr), jj, LPR));
+            const bool ok = (jb + q < cnt) && p != nullptr;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+              const int c = v * LPR + gl;
+              buf[q][v] = (ok && c < nvec) ? ld_nc_v4(p + c * 16) : make_uint4(0, 0, 0, 0);
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < NB; ++q)
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) bf16x8_accum(buf[q][v], acc[v]);
         }
       }
     }
@@ -354,8 +379,15 @@ inline int grid_for(int64_t items, int per_block, int max_blocks = 148 * 16) {
   } while (0)
 
 void launch_sage_aggregate(const SageAggArgs& a, cudaStream_t s) {
+  static const bool batched = [] {
+    const char* e = std::getenv("GLT_B200_AGG_BATCH");
+    return e && std::atoi(e) != 0;
+  }();
   GLT_DISPATCH_WIDTH(a.d, {
-    k_sage_aggregate<LPR, VPL><<<grid_for(a.cap_targets, 8 * (32 / LPR)), 256, 0, s>>>(a);
+    if (batched && VPL <= 2)
+      k_sage_aggregate<LPR, VPL, 4><<<grid_for(a.cap_targets, 8 * (32 / LPR)), 256, 0, s>>>(a);
+    else
+      k_sage_aggregate<LPR, VPL, 1><<<grid_for(a.cap_targets, 8 * (32 / LPR)), 256, 0, s>>>(a);
   });
 }
 

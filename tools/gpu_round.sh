@@ -25,6 +25,8 @@ if [[ "${GLT_B200_EXPERIMENTAL:-0}" == "1" ]]; then
   GLT_B200_EXPERIMENTAL=1 run python -m pytest tests/test_gpu_engine.py -q -k "transposed or gather_backward or engine_and_trainer" > $OUT/${TAG}_experimental.log 2>&1
   tail -3 $OUT/${TAG}_experimental.log
   GLT_B200_GATHER_BWD=1 run python bench.py --steps 100 --warmup 10 > $OUT/${TAG}_bench_gather_bwd.json 2> /dev/null
+  GLT_B200_AGG_BATCH=1 run python -m pytest tests/test_gpu_engine.py -q -k "forward_backward" > $OUT/${TAG}_agg_batch_test.log 2>&1; tail -1 $OUT/${TAG}_agg_batch_test.log
+  GLT_B200_AGG_BATCH=1 run python bench.py --steps 100 --warmup 10 > $OUT/${TAG}_bench_agg_batch.json 2> /dev/null
   tail -c 200 $OUT/${TAG}_bench_gather_bwd.json
 fi
 echo "done: $(ls $OUT | grep -c "^${TAG}_") files"
