@@ -1,8 +1,16 @@
 """Reference arm of bench.py: the UNMODIFIED reference (installed from /root/reference into
-baseline/_ref) run through its own public API and stock code path, following its
-examples/train_sage_ogbn_products.py:95-141 (Dataset.init_graph ZERO_COPY, Feature with
-sort_by_in_degree + split_ratio 0.2, NeighborLoader([15,10,5], batch 1024, as_pyg_v1=True),
-3-layer GraphSAGE hidden 256, Adam, NLL).  Same synthetic products-shape graph as our arm.
+baseline/_ref) run through its own public API and stock code path (glt.data.Dataset + Feature +
+glt.loader.NeighborLoader), following its examples/train_sage_ogbn_products.py:95-141 (3-layer
+GraphSAGE hidden 256, NeighborLoader([15,10,5], batch 1024, as_pyg_v1=True), Adam, NLL).  Same
+synthetic products-shape graph as our arm.
+
+Pairings (bench.py --ref-config / --ref-dtype):
+  hbm   : graph_mode='CUDA', split_ratio=1.0  -- the reference's own fully HBM-resident recipe
+          (examples/train_sage_prod_with_trim.py:97,103); default, pairs with our HBM-resident arm
+  stock : graph_mode='ZERO_COPY', split_ratio=0.2 -- the products example as shipped
+  bf16  : bf16 feature storage (the reference's UnifiedTensor registers BFloat16,
+          csrc/cuda/unified_tensor.cu:129) + torch.autocast(bf16) around the model, fp32 master weights
+  fp32  : the example's stock precision
 
 PyG is not installable offline, so (a) `torch_sparse` / `torch_geometric.data` are satisfied by
 the tiny shims in baseline/shims (dependencies only), and (b) the SAGEConv layers of the example
@@ -11,6 +19,7 @@ kernels, engine or package is imported here.
 """
 import json
 import os
+import statistics
 import sys
 import time
 
@@ -46,12 +55,12 @@ def _sage_model(torch, in_dim, hidden, out_dim):
         x = self.convs[i]((x, x_target), edge_index)
         if i != len(self.convs) - 1:
           x = F.relu(x)
-      return x.log_softmax(dim=-1)
+      return x.float().log_softmax(dim=-1)
 
   return SAGE()
 
 
-def main(args, baseline_samples_per_s):
+def main(args, baseline_samples_per_s, canonical_config, metric):
   sys.path.insert(0, os.path.join(HERE, 'shims'))
   sys.path.insert(0, os.path.join(HERE, '_ref'))
   import torch
@@ -90,75 +99,122 @@ def main(args, baseline_samples_per_s):
   labels = torch.randint(0, args.classes, (N,), generator=g)
   feats = torch.randn(N, args.feat_dim, generator=g)
 
+  cfg_name, dt_name = args.ref_config, args.ref_dtype
+  graph_mode, split = ('CUDA', 1.0) if cfg_name == 'hbm' else ('ZERO_COPY', 0.2)
   ds = glt.data.Dataset()
-  ds.init_graph(edge_index=ei, graph_mode='ZERO_COPY', directed=False, device=local_rank)
-  ds.init_node_features(node_feature_data=feats, sort_func=glt.data.sort_by_in_degree, split_ratio=0.2,
-                        device_group_list=[glt.data.DeviceGroup(0, [local_rank])], device=local_rank)
+  ds.init_graph(edge_index=ei, graph_mode=graph_mode, directed=False, device=local_rank)
+  del ei
   ds.init_node_labels(node_label_data=labels)
+  node_labels = ds.node_labels.to(device)
   gp = torch.Generator(); gp.manual_seed(args.seed + 7)
   pool = torch.randperm(N, generator=gp)[rank::world]
   bs, K, W = args.batch, args.steps, args.warmup
-  need = (K + W) * bs * 2
-  reps = (need + pool.numel() - 1) // pool.numel()
-  seeds = pool.repeat(reps)[:need]
   fan = [int(x) for x in args.fanout.split(',')]
-  loader = glt.loader.NeighborLoader(ds, fan, seeds, batch_size=bs, shuffle=False, drop_last=True,
-                                     device=device, as_pyg_v1=True)
-  model = _sage_model(torch, args.feat_dim, args.hidden, args.classes).to(device)
-  if world > 1:
-    model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank])
-  opt = torch.optim.Adam(model.parameters(), lr=3e-3)
-  ds.node_labels = ds.node_labels.to(device)
-  it = iter(loader)
-  loss_host = torch.zeros(1).pin_memory()
-
-  def step():
-    batch_size, n_id, adjs = next(it)
-    adjs = [adj.to(device) for adj in adjs]
-    opt.zero_grad()
-    out = model(ds.node_features[n_id], adjs)
-    loss = F.nll_loss(out, ds.node_labels[n_id[:batch_size]])
-    loss.backward()
-    opt.step()
-    return loss
 
   def barrier():
     if world > 1:
       dist.barrier()
     torch.cuda.synchronize()
 
-  def timed(n, read_loss):
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier(); e0.record()
-    for _ in range(n):
-      loss = step()
-      if read_loss:
-        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
-    e1.record(); barrier()
-    ms = e0.elapsed_time(e1)
+  def max_ranks(ms):
     if world > 1:
       t = torch.tensor([ms], dtype=torch.float64, device=device)
       dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
     return ms
 
-  for _ in range(W):
-    step()
-  ms = timed(K, False)
-  e2e_ms = timed(K, True)
+  def measure(dtype_name, min_time):
+    """Builds Feature + loader + model for one precision and times it (same block protocol as our arm)."""
+    fdt = torch.bfloat16 if dtype_name == 'bf16' else torch.float32
+    ds.node_features = None
+    ds.init_node_features(node_feature_data=feats.to(fdt), sort_func=glt.data.sort_by_in_degree, split_ratio=split,
+                          device_group_list=[glt.data.DeviceGroup(0, [local_rank])], device=local_rank)
+    torch.manual_seed(args.seed)
+    model = _sage_model(torch, args.feat_dim, args.hidden, args.classes).to(device)
+    if world > 1:
+      model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank])
+    opt = torch.optim.Adam(model.parameters(), lr=3e-3)
+    loss_host = torch.zeros(1).pin_memory()
+    state = {'it': None, 'ep': 0}
+
+    def new_iter():
+      g2 = torch.Generator(); g2.manual_seed(1000 + state['ep']); state['ep'] += 1
+      seeds = pool[torch.randperm(pool.numel(), generator=g2)]
+      loader = glt.loader.NeighborLoader(ds, fan, seeds, batch_size=bs, shuffle=False, drop_last=True,
+                                         device=device, as_pyg_v1=True)
+      state['it'] = iter(loader)
+
+    def step(read_loss):
+      try:
+        batch_size, n_id, adjs = next(state['it'])
+      except (StopIteration, TypeError):
+        new_iter()
+        batch_size, n_id, adjs = next(state['it'])
+      adjs = [adj.to(device) for adj in adjs]
+      opt.zero_grad()
+      with torch.autocast('cuda', dtype=torch.bfloat16, enabled=(dtype_name == 'bf16')):
+        out = model(ds.node_features[n_id], adjs)
+      loss = F.nll_loss(out, node_labels[n_id[:batch_size]])
+      loss.backward()
+      opt.step()
+      if read_loss:
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+
+    def timed(read_loss):
+      blocks = []
+      while True:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier(); e0.record()
+        for _ in range(K):
+          step(read_loss)
+        e1.record(); barrier()
+        blocks.append(max_ranks(e0.elapsed_time(e1)))
+        if sum(blocks) >= min_time * 1e3 or len(blocks) >= 2000:
+          break
+      tot = sum(blocks)
+      return {'ms_per_step': tot / (len(blocks) * K), 'blocks': len(blocks), 'steps_total': len(blocks) * K,
+              'seconds': tot / 1e3, 'first_block_ms_per_step': blocks[0] / K,
+              'median_block_ms_per_step': statistics.median(blocks) / K}
+
+    new_iter()
+    for _ in range(W):
+      step(False)
+    d, e = timed(False), timed(True)
+    del model, opt
+    return d, e
+
+  dev_t, e2e_t = measure(dt_name, args.min_time)
+  arms = []
+  if not args.no_arms and dt_name == 'bf16':
+    try:
+      d2, e2 = measure('fp32', min(args.min_time, 0.5))
+      arms.append({'ref_config': cfg_name, 'dtype': 'fp32', 'value': bs * world / (d2['ms_per_step'] / 1e3),
+                   'ms_per_step': d2['ms_per_step'], 'e2e_value': bs * world / (e2['ms_per_step'] / 1e3),
+                   'e2e_ms_per_step': e2['ms_per_step'], 'timed': d2})
+    except Exception as ex:
+      arms.append({'ref_config': cfg_name, 'dtype': 'fp32', 'error': f'{type(ex).__name__}: {str(ex)[:200]}'})
   if rank == 0:
-    total = K * bs * world
-    val = total / (ms / 1e3)
+    per_step = bs * world
+    val = per_step / (dev_t['ms_per_step'] / 1e3)
+    cfg = dict(canonical_config)
+    if cfg_name != 'hbm':
+      cfg['memory_tier'] = 'ZERO_COPY topology (pinned host, UVA) + 20 % of feature rows in HBM'
+    if dt_name != 'bf16':
+      cfg['precision'] = 'fp32'
     print(json.dumps({
-      'impl': 'reference', 'metric': 'GraphSAGE ogbn-products-shape training throughput (seed nodes/s, device-timed, max over ranks)',
-      'value': val, 'unit': 'samples/s', 'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms / K,
+      'impl': 'reference', 'metric': metric,
+      'value': val, 'unit': 'samples/s', 'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': dev_t['ms_per_step'],
       'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': val / baseline_samples_per_s,
-      'dtype': 'fp32 (reference stock path)', 'data': 'synthetic',
-      'config': {'model': 'GraphSAGE-3x256-mean (plain PyTorch SAGEConv; PyG unavailable offline)',
-                 'global_batch': bs * world, 'fanout': args.fanout, 'graph_mode': 'ZERO_COPY',
-                 'feature_split_ratio': 0.2, 'loader': 'glt.loader.NeighborLoader(as_pyg_v1=True)',
-                 'parallelism': f'ddp{world}', 'deps': 'torch_sparse/torch_geometric.data shims (baseline/shims)'},
-      'e2e': {'value': total / (e2e_ms / 1e3), 'unit': 'samples/s', 'ms_per_step': e2e_ms / K,
-              'h2d_bytes_per_step': bs * 8, 'd2h_bytes_per_step': 4},
+      'dtype': 'bf16' if dt_name == 'bf16' else 'fp32', 'data': 'synthetic',
+      'config': cfg,
+      'details': {'model_code': 'plain-PyTorch SAGEConv (PyG unavailable offline), torch.autocast(bf16)' if dt_name == 'bf16'
+                  else 'plain-PyTorch SAGEConv (PyG unavailable offline), fp32',
+                  'graph_mode': graph_mode, 'feature_split_ratio': split, 'feature_dtype': dt_name,
+                  'loader': 'glt.loader.NeighborLoader(as_pyg_v1=True)', 'parallelism': f'ddp{world}',
+                  'deps': 'torch_sparse/torch_geometric.data shims (baseline/shims)'},
+      'timed': dev_t,
+      'e2e': {'value': per_step / (e2e_t['ms_per_step'] / 1e3), 'unit': 'samples/s', 'ms_per_step': e2e_t['ms_per_step'],
+              'h2d_bytes_per_step': bs * 8, 'd2h_bytes_per_step': 4, 'timed': e2e_t},
+      'arms': arms,
     }), flush=True)
   if world > 1:
     dist.destroy_process_group()

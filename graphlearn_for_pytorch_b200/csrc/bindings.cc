@@ -678,6 +678,117 @@ static void sage_fused(RowTableHandle* feat, const c10::optional<Tensor>& nodes,
   check_cuda_err("sage_fused");
 }
 
+
+// ---------------------------------------------------------------------------
+// TcGemm: a cached launch of the TMA-fed tcgen05 GEMM kernel (csrc/cuda/tc_gemm.cu) over fixed engine buffers.
+// Tensor maps are encoded once; the batch-dependent extent is read from the sampler's device counters, so
+// run() is a single static launch (CUDA-graph capturable).  Up to two problems share a launch.
+// ---------------------------------------------------------------------------
+struct TcGemm {
+  TcGemmLaunch L;
+  int device;
+  std::vector<Tensor> keep;   // keeps every operand alive
+  explicit TcGemm(int dev) : device(dev) {
+    std::memset(&L, 0, sizeof(L));
+  }
+  static int pick_bn(int64_t n) { return n % 256 == 0 ? 256 : (n % 128 == 0 ? 128 : 64); }
+  void check_bf16(const Tensor& t, const char* what) {
+    TORCH_CHECK(t.is_cuda() && t.scalar_type() == torch::kBFloat16 && t.dim() == 2 && t.stride(1) == 1 &&
+                (t.stride(0) * 2) % 16 == 0 && reinterpret_cast<uintptr_t>(t.data_ptr()) % 16 == 0,
+                "TcGemm: ", what, " must be a 2-D bf16 CUDA tensor with unit inner stride and 16-byte aligned rows");
+  }
+  void tmap(int slot, const Tensor& t, int box_cols, int box_rows) {
+    const int rc = make_tmap_bf16_2d(L.maps[slot], t.data_ptr(), t.size(0), t.size(1), t.stride(0), box_cols, box_rows);
+    TORCH_CHECK(rc == 0, "TcGemm: cuTensorMapEncodeTiled failed (rc=", rc, ")");
+    keep.push_back(t);
+  }
+  TcProblem& next() {
+    TORCH_CHECK(L.args.n_prob < 2, "TcGemm: at most two problems per launch");
+    return L.args.p[L.args.n_prob];
+  }
+  void set_dyn(TcProblem& p, const Tensor& counters, int64_t idx, int64_t cap, bool is_k) {
+    TORCH_CHECK(counters.is_cuda() && counters.scalar_type() == torch::kInt32 && idx >= 0 && idx < counters.numel());
+    p.dyn = counters.data_ptr<int32_t>();
+    p.dyn_idx = static_cast<int>(idx);
+    p.dyn_cap = static_cast<int>(cap);
+    p.dyn_is_k = is_k ? 1 : 0;
+    keep.push_back(counters);
+  }
+  // Z[rows, N] = act(A[rows, K] . W[N, K]^T + bias); rows = min(counters[dyn_idx], A.size(0))
+  void add_forward(const Tensor& A, const Tensor& W, const c10::optional<Tensor>& bias, bool relu, Tensor Z,
+                   const Tensor& counters, int64_t dyn_idx) {
+    c10::cuda::CUDAGuard guard(A.device());
+    check_bf16(A, "A"); check_bf16(W, "W"); check_bf16(Z, "Z");
+    const int64_t K = A.size(1), N = W.size(0);
+    TORCH_CHECK(W.size(1) == K && Z.size(1) == N && Z.size(0) >= A.size(0) && N % 64 == 0 && K % 8 == 0);
+    const int slot = 3 * L.args.n_prob;
+    TcProblem& p = next();
+    p.a_mn = 0; p.b_mn = 0; p.epi = 0; p.bn = pick_bn(N);
+    p.m = A.size(0); p.n = N; p.k = K;
+    set_dyn(p, counters, dyn_idx, A.size(0), false);
+    p.bias = nullptr;
+    if (bias.has_value() && bias->defined()) {
+      TORCH_CHECK(bias->scalar_type() == torch::kBFloat16 && bias->numel() == N &&
+                  reinterpret_cast<uintptr_t>(bias->data_ptr()) % 16 == 0);
+      p.bias = bias->data_ptr();
+      keep.push_back(*bias);
+    }
+    p.relu = relu ? 1 : 0;
+    tmap(slot + 0, A, 64, 128);
+    tmap(slot + 1, W, 64, p.bn);
+    tmap(slot + 2, Z, 64, 128);
+    L.max_items += static_cast<int>((A.size(0) + 127) / 128 * (N / p.bn));
+    ++L.args.n_prob;
+  }
+  // dA[rows, N] = dPre[rows, Kd] . W[Kd, N]  (W row-major = N contiguous: the MN-major B operand)
+  void add_dgrad(const Tensor& dPre, const Tensor& W, Tensor dA, const Tensor& counters, int64_t dyn_idx) {
+    c10::cuda::CUDAGuard guard(dPre.device());
+    check_bf16(dPre, "dPre"); check_bf16(W, "W"); check_bf16(dA, "dA");
+    const int64_t Kd = dPre.size(1), N = W.size(1);
+    TORCH_CHECK(W.size(0) == Kd && dA.size(1) == N && dA.size(0) >= dPre.size(0) && N % 64 == 0 && Kd % 8 == 0);
+    const int slot = 3 * L.args.n_prob;
+    TcProblem& p = next();
+    p.a_mn = 0; p.b_mn = 1; p.epi = 0; p.bn = pick_bn(N);
+    p.m = dPre.size(0); p.n = N; p.k = Kd;
+    set_dyn(p, counters, dyn_idx, dPre.size(0), false);
+    p.bias = nullptr; p.relu = 0;
+    tmap(slot + 0, dPre, 64, 128);
+    tmap(slot + 1, W, 64, 64);
+    tmap(slot + 2, dA, 64, 128);
+    L.max_items += static_cast<int>((dPre.size(0) + 127) / 128 * (N / p.bn));
+    ++L.args.n_prob;
+  }
+  // gW[M, N] += dPre[rows, M]^T . A[rows, N], rows = min(counters[dyn_idx], dPre.size(0)); fp32 split-K red-add
+  // (gW must be zeroed by the caller; dPre rows beyond the batch must be zero up to its capacity)
+  void add_wgrad(const Tensor& dPre, const Tensor& A, Tensor gW, const Tensor& counters, int64_t dyn_idx) {
+    c10::cuda::CUDAGuard guard(dPre.device());
+    check_bf16(dPre, "dPre"); check_bf16(A, "A");
+    const int64_t M = dPre.size(1), N = A.size(1);
+    TORCH_CHECK(A.size(0) >= dPre.size(0) && N % 64 == 0 && M % 8 == 0);
+    TORCH_CHECK(gW.is_cuda() && gW.scalar_type() == torch::kFloat32 && gW.dim() == 2 && gW.size(0) == M &&
+                gW.size(1) == N && gW.stride(1) == 1 && gW.stride(0) % 4 == 0 &&
+                reinterpret_cast<uintptr_t>(gW.data_ptr()) % 16 == 0, "TcGemm: gW must be fp32 [M, N], 16-byte aligned");
+    const int slot = 3 * L.args.n_prob;
+    TcProblem& p = next();
+    p.a_mn = 1; p.b_mn = 1; p.epi = 1; p.bn = pick_bn(N);
+    p.m = M; p.n = N; p.k = dPre.size(0);
+    set_dyn(p, counters, dyn_idx, dPre.size(0), true);
+    p.bias = nullptr; p.relu = 0;
+    p.out32 = gW.data_ptr<float>(); p.ld32 = static_cast<int>(gW.stride(0)); p.m_valid = static_cast<int>(M);
+    keep.push_back(gW);
+    tmap(slot + 0, dPre, 64, 64);
+    tmap(slot + 1, A, 64, 64);
+    L.max_items += 1 << 20;   // split-K fills the grid
+    ++L.args.n_prob;
+  }
+  void run() {
+    TORCH_CHECK(L.args.n_prob >= 1, "TcGemm: no problem added");
+    c10::cuda::CUDAGuard guard(static_cast<c10::DeviceIndex>(device));
+    launch_tc_gemm(L, at::cuda::getCurrentDeviceProperties()->multiProcessorCount, cur_stream());
+    check_cuda_err("tc_gemm");
+  }
+};
+
 static void enable_peer_access(int dev, int peer) {
   if (dev == peer) return;
   c10::cuda::CUDAGuard guard(dev);
@@ -952,6 +1063,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("adam", &PeerGroup::adam)
       .def_readonly("err", &PeerGroup::err)
       .def_readonly("epoch", &PeerGroup::epoch);
+  py::class_<TcGemm>(m, "TcGemm")
+      .def(py::init<int>())
+      .def("add_forward", &TcGemm::add_forward)
+      .def("add_dgrad", &TcGemm::add_dgrad)
+      .def("add_wgrad", &TcGemm::add_wgrad)
+      .def("run", &TcGemm::run);
   m.def("enable_peer_access", &enable_peer_access);
   m.def("multimem_copy", &multimem_copy);
   m.def("pack_weight", &pack_weight);

@@ -17,27 +17,35 @@ __device__ __forceinline__ uint32_t hash_slot(int64_t key, uint32_t mask) {
   return static_cast<uint32_t>(x >> 29) & mask;
 }
 
-// Insert `key`; returns the slot and whether this thread claimed it.
+constexpr uint32_t kTableFull = 0xFFFFFFFFu;
+
+// Insert `key`; returns the slot and whether this thread claimed it.  The probe sequence is bounded
+// by the table size: a full table (a batch with far more unique nodes than the calibrated arena
+// was sized for) yields kTableFull instead of spinning forever; callers drop that neighbour and
+// count it as overflow.
 __device__ __forceinline__ uint32_t table_insert(const HashTable& t, int64_t key, bool* is_new) {
   uint32_t s = hash_slot(key, t.mask);
-  while (true) {
+  *is_new = false;
+  for (uint32_t probes = 0; probes <= t.mask; ++probes) {
     unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long*>(t.keys + s),
                                         static_cast<unsigned long long>(kEmptyKey),
                                         static_cast<unsigned long long>(key));
     if (prev == static_cast<unsigned long long>(kEmptyKey)) { *is_new = true; return s; }
-    if (prev == static_cast<unsigned long long>(key)) { *is_new = false; return s; }
+    if (prev == static_cast<unsigned long long>(key)) return s;
     s = (s + 1) & t.mask;
   }
+  return kTableFull;
 }
 
 __device__ __forceinline__ int32_t table_find_slot(const HashTable& t, int64_t key) {
   uint32_t s = hash_slot(key, t.mask);
-  while (true) {
+  for (uint32_t probes = 0; probes <= t.mask; ++probes) {
     int64_t k = t.keys[s];
     if (k == key) return static_cast<int32_t>(s);
     if (k == kEmptyKey) return -1;
     s = (s + 1) & t.mask;
   }
+  return -1;
 }
 
 struct RowRef {

@@ -260,4 +260,35 @@ void launch_sage_fused(const SageFusedArgs& a, int num_sms, cudaStream_t s);
 // W [N, K] row-major bf16 -> packed swizzled image used by launch_sage_fused.
 void launch_pack_weight(const void* w, int n, int k, void* packed, cudaStream_t s);
 
+
+// ---- tc_gemm.cu (TMA-fed tcgen05 GEMMs: forward layers 2..L, dA, split-K dW) ---------------------
+struct TcProblem {
+  int a_mn, b_mn;          // operand major-ness: 0 = K-major (row-major [rows, K]), 1 = MN-major ([K rows, M/N cols])
+  int epi;                 // 0: bf16 out (+bias, +ReLU) through a TMA store; 1: fp32 red-add (split-K)
+  int bn;                  // tile width: 64 / 128 / 256, divides n
+  int m, n, k;             // static extents (capacity for the dynamic one)
+  const int32_t* dyn;      // device counters; the dynamic extent is min(dyn[dyn_idx], dyn_cap)
+  int dyn_idx, dyn_cap;
+  int dyn_is_k;            // 0: the dynamic extent is M (forward / dA); 1: it is K (dW)
+  const void* bias;        // bf16 [n] or nullptr (epi 0)
+  int relu;
+  float* out32;            // epi 1: fp32 [m_valid, ld32]
+  int ld32, m_valid;
+};
+struct TcGemmArgs {
+  int n_prob;
+  TcProblem p[2];
+};
+struct alignas(64) TcGemmLaunch {
+  unsigned char maps[6][128];   // CUtensorMap A0, B0, C0, A1, B1, C1
+  TcGemmArgs args;
+  int max_items;                // upper bound of work items (grid = min(#SMs, max_items)); 0 = #SMs
+};
+// bf16 [rows, cols] row-major (pitch ld elements) tensor map with a {box_cols = 64, box_rows} SWIZZLE_128B box.
+// Returns 0 on success (1: driver entry point unavailable, 2: encode failed).
+int make_tmap_bf16_2d(void* out_map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols,
+                      int box_rows);
+size_t tc_gemm_smem_bytes();
+void launch_tc_gemm(const TcGemmLaunch& L, int num_sms, cudaStream_t s);
+
 }  // namespace glt

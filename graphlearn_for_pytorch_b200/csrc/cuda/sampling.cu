@@ -136,7 +136,13 @@ __global__ void __launch_bounds__(256) k_sample_hop(HopArgs a) {
       }
       bool is_new = false;
       uint32_t slot = 0;
-      if (have) slot = table_insert(a.t, key, &is_new);
+      if (have) {
+        slot = table_insert(a.t, key, &is_new);
+        if (slot == kTableFull) {  // table exhausted: drop the neighbour (relabel compacts the row)
+          have = false;
+          if (a.c.overflow) atomicAdd(a.c.overflow, 1);
+        }
+      }
       // warp-aggregated local-id assignment
       const unsigned nm = __ballot_sync(0xffffffffu, is_new);
       int id_base = 0;
@@ -166,23 +172,42 @@ __global__ void __launch_bounds__(256) k_sample_hop(HopArgs a) {
 __global__ void k_relabel_hop(HopArgs a) {
   const int f_begin = a.c.cum[a.hop];
   const int n_rows = min(a.c.cum[a.hop + 1] - f_begin, a.cap_rows);
-  const int64_t n = static_cast<int64_t>(n_rows) * a.k;
   // Capacity guard (arenas may be sized from calibration instead of the worst case): the
   // next frontier holds at most cap_rows_next rows and the arena cap_nodes nodes.  Nodes past
   // the bound are dropped: their slot is poisoned (-1) so later hops treat them as absent.
   // Every thread derives the same bound from stable inputs; the cursor reset is idempotent.
   const int bound = min(min(*a.c.cursor, a.cap_nodes), a.c.cum[a.hop + 1] + a.cap_rows_next);
+  // One thread per frontier row (k <= fan-out entries, contiguous): slot -> local id, and rows that
+  // lost a neighbour (arena / table overflow) are compacted in place with deg[] and the hop's edge
+  // counter corrected, so the mean divides by the neighbours that exist and to_coo never emits -1.
   int dropped = 0;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int32_t s = a.ell[i];
-    if (s >= 0) {
-      int32_t v = a.t.vals[s];
-      if (v >= bound) { a.t.vals[s] = -1; v = -1; ++dropped; }
-      a.ell[i] = v;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += gridDim.x * blockDim.x) {
+    int32_t* row = a.ell + static_cast<int64_t>(r) * a.k;
+    int64_t* erow = a.ell_eids ? a.ell_eids + static_cast<int64_t>(r) * a.k : nullptr;
+    const int dg = min(a.deg[f_begin + r], a.k);
+    int w = 0;
+    for (int j = 0; j < dg; ++j) {
+      const int32_t s = row[j];
+      int32_t v = -1;
+      if (s >= 0) {
+        v = a.t.vals[s];
+        if (v >= bound) { a.t.vals[s] = -1; v = -1; }
+      }
+      if (v >= 0) {
+        if (w != j) { row[w] = v; if (erow) erow[w] = erow[j]; } else row[j] = v;
+        ++w;
+      }
+    }
+    if (w < dg) {
+      for (int j = w; j < dg; ++j) { row[j] = -1; if (erow) erow[j] = -1; }
+      a.deg[f_begin + r] = w;
+      dropped += dg - w;
     }
   }
-  if (dropped && a.c.overflow) atomicAdd(a.c.overflow, dropped);
+  if (dropped) {
+    if (a.c.overflow) atomicAdd(a.c.overflow, dropped);
+    atomicSub(a.c.edges + a.hop, dropped);
+  }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     a.c.cum[a.hop + 2] = bound;
     *a.c.cursor = bound;
@@ -208,7 +233,7 @@ __global__ void __launch_bounds__(1024) k_init_seeds(const int64_t* seeds, int n
     if (key < 0) { slot_of[i] = -1; continue; }
     bool is_new;
     const uint32_t s = table_insert(t, key, &is_new);
-    slot_of[i] = static_cast<int32_t>(s);
+    slot_of[i] = (s == kTableFull) ? -1 : static_cast<int32_t>(s);
     if (is_new) t.aux[s] = i;
   }
   __syncthreads();
@@ -342,7 +367,8 @@ __global__ void k_table_insert(HashTable t, const int64_t* keys, int64_t n, int6
     bool is_new = false;
     uint32_t slot = 0;
     const bool have = i < n && keys[i] >= 0;
-    if (have) slot = table_insert(t, keys[i], &is_new);
+    bool full = false;
+    if (have) { slot = table_insert(t, keys[i], &is_new); full = (slot == kTableFull); }
     const unsigned nm = __ballot_sync(0xffffffffu, is_new);
     int id_base = 0;
     if (nm) {
@@ -353,7 +379,7 @@ __global__ void k_table_insert(HashTable t, const int64_t* keys, int64_t n, int6
       const int id = id_base + __popc(nm & lanemask_lt());
       if (id < cap_nodes) { t.vals[slot] = id; nodes[id] = keys[i]; }
     }
-    if (i < n) out_slots[i] = have ? static_cast<int32_t>(slot) : -1;
+    if (i < n) out_slots[i] = (have && !full) ? static_cast<int32_t>(slot) : -1;
   }
 }
 
@@ -410,7 +436,7 @@ void launch_sample_hop(const HopArgs& a, cudaStream_t s) {
 }
 
 void launch_relabel_hop(const HopArgs& a, cudaStream_t s) {
-  k_relabel_hop<<<grid_for(static_cast<int64_t>(a.cap_rows) * a.k, 256 * 4), 256, 0, s>>>(a);
+  k_relabel_hop<<<grid_for(a.cap_rows, 256), 256, 0, s>>>(a);
 }
 
 void launch_sample_one_hop(GraphTable g, const int64_t* seeds, int n, int k, int weighted,

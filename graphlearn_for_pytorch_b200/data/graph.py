@@ -21,7 +21,7 @@ from ..utils.tensor import page_lock_in_place
 from ..ops import require_native
 from ..typing import TensorDataType
 from ..utils.tensor import convert_to_tensor, share_memory
-from ..utils.topo import coo_to_csc, coo_to_csr, ptr2ind
+from ..utils.topo import coo_to_csc, coo_to_csr, ptr2ind, rows_are_sorted, sort_csr_columns
 
 
 class Topology(object):
@@ -62,9 +62,16 @@ class Topology(object):
 
     if input_layout == layout:
       if layout == 'CSC':
-        self._indices, self._indptr = row.contiguous(), col.contiguous()
+        ind, ptr = row.contiguous(), col.contiguous()
       else:
-        self._indptr, self._indices = row.contiguous(), col.contiguous()
+        ptr, ind = row.contiguous(), col.contiguous()
+      # strict negative sampling, node2vec walks and induced sub-graphs binary-search inside a row
+      # (csrc/cuda/graph_ops.cu edge_exists, cpu_negative_sample(sorted=True)); a user-supplied
+      # compressed layout is therefore brought to the same sorted-minor-index form that the COO
+      # path produces (edge ids / weights are permuted along).
+      if ind.numel() > 1 and not rows_are_sorted(ptr, ind):
+        ptr, ind, edge_ids, edge_weights = sort_csr_columns(ptr, ind, edge_ids, edge_weights)
+      self._indptr, self._indices = ptr, ind
       self._edge_ids, self._edge_weights = edge_ids, edge_weights
       return
     if input_layout == 'CSC':

@@ -27,19 +27,26 @@ class SeedBatcher(object):
     self.epoch = 0
     self.pos = 0
     self._order = None
+    self._resumed = False
 
   def __len__(self):
     n = self.seeds.shape[0]
     return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
 
+  def _make_order(self, epoch_index: int):
+    if not self.shuffle:
+      return None
+    g = torch.Generator()
+    g.manual_seed(self.seed + epoch_index)
+    return torch.randperm(self.seeds.shape[0], generator=g)
+
   def __iter__(self):
-    n = self.seeds.shape[0]
-    if self.shuffle:
-      g = torch.Generator()
-      g.manual_seed(self.seed + self.epoch)
-      self._order = torch.randperm(n, generator=g)
-    else:
-      self._order = None
+    if self._resumed:
+      # load_state_dict() put us in the middle of epoch `self.epoch - 1`: keep the position and the
+      # permutation of THAT epoch so the resumed stream continues exactly where it stopped
+      self._resumed = False
+      return self
+    self._order = self._make_order(self.epoch)
     self.pos = 0
     self.epoch += 1
     return self
@@ -58,7 +65,15 @@ class SeedBatcher(object):
     return {'seed': self.seed, 'epoch': self.epoch, 'pos': self.pos}
 
   def load_state_dict(self, s):
+    """Restore a mid-epoch position: the permutation of the interrupted epoch (`epoch - 1`, since
+    `epoch` counts started epochs) is recomputed from the seed, and the next `iter()` continues
+    it instead of starting a new epoch."""
     self.seed, self.epoch, self.pos = s['seed'], s['epoch'], s['pos']
+    if self.epoch > 0:
+      self._order = self._make_order(self.epoch - 1)
+      self._resumed = True
+    else:
+      self._order, self._resumed = None, False
 
 
 class NodeLoader(object):

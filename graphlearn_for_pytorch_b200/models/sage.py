@@ -118,6 +118,12 @@ class GraphSageEngine(object):
       import os as _os
       use_gather_bwd = _os.environ.get('GLT_B200_GATHER_BWD', '0') == '1'
     self.use_gather_bwd = bool(use_gather_bwd)
+    # every dense contraction outside the fused layer-1 kernel runs on the TMA-fed tcgen05 GEMM kernel
+    # (csrc/cuda/tc_gemm.cu); GLT_B200_TC_GEMM=0 falls back to cuBLAS for A/B measurements
+    import os as _os2
+    self.use_tc_gemm = _os2.environ.get('GLT_B200_TC_GEMM', '1') != '0'
+    self._tc_plans = {}
+    self.library_gemms_per_step = 0
     self.peer_group = None
     self.graph = graph
     graph.lazy_init()
@@ -322,7 +328,12 @@ class GraphSageEngine(object):
   def _k(self, n):
     self._tally += n
 
+  def _lib(self, n):
+    """Counts launches that go to a vendor library (cuBLAS/cuBLASLt) instead of this repo's kernels."""
+    self._lib_tally += n
+
   _tally = 0
+  _lib_tally = 0
 
   def _ell(self, l):
     """ELL blocks + strides used by layer l: hops 0..L-l."""
@@ -338,11 +349,11 @@ class GraphSageEngine(object):
     ar.sample(self.gh, self._seeds[which], None, self.seed, 0, False, False, True, len(self._arenas))
     self._k(2 + 2 * self.L)  # table clear + init_seeds + (sample, relabel) per hop
 
-  def _forward(self):
+  def _forward(self, train: bool = True):
     nat, ar = self.nat, self.arena
     for l in range(1, self.L + 1):
       self._forward_layer(l)
-    self._forward_loss()
+    self._forward_loss(train)
 
   def _forward_layer(self, l: int):
     nat, ar = self.nat, self.arena
@@ -358,38 +369,81 @@ class GraphSageEngine(object):
       self._k(1)
     else:
       nat.sage_aggregate(feat, nodes, src_local, d, ar.counters, nh, ell, ks, ar.deg, self.A[l])
-      # library GEMM with the bias (+ ReLU) applied in the cuBLASLt epilogue: no separate
-      # elementwise pass over Z
-      if relu:
-        torch._addmm_activation(self.b(l), self.A[l], self.W(l).t(), out=self.Z[l])
-      else:
-        torch.addmm(self.b(l), self.A[l], self.W(l).t(), out=self.Z[l])
       self._k(1)
+      if self.use_tc_gemm:
+        # Z = act(A . W^T + b) on tcgen05 (TMA-fed, bias/ReLU in the TMEM epilogue, rows from the device counter)
+        self._plan('fwd', l).run()
+        self._k(1)
+      else:
+        # library GEMM with the bias (+ ReLU) applied in the cuBLASLt epilogue
+        if relu:
+          torch._addmm_activation(self.b(l), self.A[l], self.W(l).t(), out=self.Z[l])
+        else:
+          torch.addmm(self.b(l), self.A[l], self.W(l).t(), out=self.Z[l])
+        self._lib(1)
 
-  def _forward_loss(self):
+  def _forward_loss(self, train: bool = True):
     # labels[nodes[r]] is looked up inside the loss kernel (no gather launch)
     nat, ar = self.nat, self.arena
     boff, n = self._b_off[self.L - 1]
+    if train:                      # evaluation must not take part in the cross-rank gradient protocol
+      self._begin_grads()
     # the bias gradient of the last layer (column sums of dlogits) is produced by the loss kernel
     nat.softmax_nll(self.Z[self.L], self.C, None, self.labels, ar.nodes, ar.counters, self.loss,
                     self.dPre[self.L], self.correct, self.g32[boff:boff + n])
     self._k(1)
 
-  def _backward(self):
-    nat, ar = self.nat, self.arena
+  def _begin_grads(self):
+    """Runs before the first kernel that writes into the flat gradient buffer (the loss kernel produces the
+    last layer's bias gradient): peers must be done reading last step's gradients, and the split-K weight
+    gradient kernels accumulate with red.add, so the buffer starts from zero."""
     if self.peer_group is not None and len(self._peer_groups) == 1:
       self.peer_group.barrier(1)          # peers finished reading last step's gradients
       self._k(1)
+    if self.use_tc_gemm:
+      self.g32.zero_()
+      self._k(1)
+
+  def _plan(self, kind: str, l: int):
+    """Cached TcGemm launch for layer l of the current arena / gradient parity (tensor maps are encoded once)."""
+    key = (kind, l, self._cur)
+    pl = self._tc_plans.get(key)
+    if pl is not None:
+      return pl
+    nat, ar = self.nat, self.arena
+    nh = self.L - l + 1                     # counters[nh] = number of target rows of layer l
+    pl = nat.TcGemm(self.device.index)
+    if kind == 'fwd':
+      pl.add_forward(self.A[l], self.W(l), self.b(l), l < self.L, self.Z[l], ar.counters, nh)
+    else:
+      off, n, k = self._w_off[l - 1]
+      gW = self.g32[off:off + n * k].view(n, k)
+      # dW (split-K over the batch rows, fp32 red-add) and dA of the same layer share one launch
+      pl.add_wgrad(self.dPre[l], self.A[l], gW, ar.counters, nh)
+      if l > 1:
+        pl.add_dgrad(self.dPre[l], self.W(l), self.dA[l], ar.counters, nh)
+    self._tc_plans[key] = pl
+    return pl
+
+  def _backward(self):
+    nat, ar = self.nat, self.arena
     for l in range(self.L, 0, -1):
       ell, ks, nh = self._ell(l)
       off, n, k = self._w_off[l - 1]
       boff, _ = self._b_off[l - 1]
-      gW = self.g32[off:off + n * k].view(n, k)
-      # dW = dPre^T A accumulated in fp32 straight into the flat gradient buffer
-      self._mm_f32(self.dPre[l].t(), self.A[l], gW)
+      if self.use_tc_gemm:
+        self._plan('bwd', l).run()
+        self._k(1)
+      else:
+        gW = self.g32[off:off + n * k].view(n, k)
+        # dW = dPre^T A accumulated in fp32 straight into the flat gradient buffer
+        self._mm_f32(self.dPre[l].t(), self.A[l], gW)
+        self._lib(1)
+        if l > 1:
+          torch.mm(self.dPre[l], self.W(l), out=self.dA[l])
+          self._lib(1)
       # bias gradients are fused into the kernels that produce dPre (loss / relu_bwd_cast)
       if l > 1:
-        torch.mm(self.dPre[l], self.W(l), out=self.dA[l])
         pboff, pn = self._b_off[l - 2]
         if self.use_gather_bwd:
           nat.sage_gather_bwd(self.dA[l], self.dims_in[l - 1], ar, nh, self.Z[l - 1], self.dPre[l - 1],
@@ -503,9 +557,10 @@ class GraphSageEngine(object):
         if self.pipeline:
           self._sample(0)
         for _ in range(n_eager):
-          self._tally = 0
+          self._tally = self._lib_tally = 0
           self._step_eager()
           self.kernels_per_step = self._tally
+          self.library_gemms_per_step = self._lib_tally
           if self.pipeline:
             self._cur ^= 1
       torch.cuda.current_stream().wait_stream(side)
@@ -516,9 +571,10 @@ class GraphSageEngine(object):
         self._autotune_fused = False
         if self.pipeline:
           self._sample(0)
-        self._tally = 0
+        self._tally = self._lib_tally = 0
         self._step_eager()                      # re-count kernels with the chosen variants
         self.kernels_per_step = self._tally
+        self.library_gemms_per_step = self._lib_tally
         torch.cuda.synchronize()
         self._cur = 0
       self.load_state_dict(saved)
@@ -651,5 +707,5 @@ class GraphSageEngine(object):
     self.seeds_dev.fill_(-1)
     self.seeds_dev[:n].copy_(seeds)
     self._sample()
-    self._forward()
+    self._forward(train=False)
     return float(self.loss.item()), int(self.correct.item()), int(self.arena.counters[1].item())

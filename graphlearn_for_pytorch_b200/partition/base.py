@@ -258,7 +258,11 @@ def _load_graph_dir(d: str, device) -> Optional[GraphPartitionData]:
     return None
   rows = torch.load(os.path.join(d, 'rows.pt'), map_location=device)
   cols = torch.load(os.path.join(d, 'cols.pt'), map_location=device)
-  eids = torch.load(os.path.join(d, 'eids.pt'), map_location=device)
+  # eids.pt is optional (the reference's save_graph_cache only writes it with edge features,
+  # python/partition/base.py): absent = edges are numbered in file order
+  ep = os.path.join(d, 'eids.pt')
+  eids = torch.load(ep, map_location=device) if os.path.exists(ep) else \
+      torch.arange(rows.numel(), dtype=torch.int64, device=rows.device)
   wp = os.path.join(d, 'weights.pt')
   w = torch.load(wp, map_location=device) if os.path.exists(wp) else None
   return GraphPartitionData((rows, cols), eids, w)
@@ -363,7 +367,14 @@ def build_partition_feature(root_dir: str, partition_idx: int, chunk_size: int =
       _write(node_feat, torch.where(pb == partition_idx)[0], 'node_feat', None)
     if edge_feat is not None:
       g = load_graph_partition_data(os.path.join(root_dir, f'part{partition_idx}', 'graph'), 'cpu')
-      _write(edge_feat, g.eids, 'edge_feat', None)
+      if g is not None:
+        owned = g.eids
+      else:
+        # topology written with graph_caching=True (no per-partition graph dir): edge ownership
+        # comes from the stored edge partition book
+        epb = _load_pb(os.path.join(root_dir, 'edge_pb.pt'), 'cpu')
+        owned = torch.where(torch.as_tensor(epb) == partition_idx)[0]
+      _write(edge_feat, owned, 'edge_feat', None)
     return
   for nt in meta['node_types']:
     if node_feat is not None and nt in node_feat:
@@ -375,3 +386,8 @@ def build_partition_feature(root_dir: str, partition_idx: int, chunk_size: int =
       g = load_graph_partition_data(os.path.join(root_dir, f'part{partition_idx}', 'graph', as_str(et)), 'cpu')
       if g is not None:
         _write(edge_feat[et], g.eids, 'edge_feat', et)
+      else:
+        epb_path = os.path.join(root_dir, 'edge_pb', f'{as_str(et)}.pt')
+        if os.path.exists(epb_path):
+          epb = _load_pb(epb_path, 'cpu')
+          _write(edge_feat[et], torch.where(torch.as_tensor(epb) == partition_idx)[0], 'edge_feat', et)

@@ -26,7 +26,12 @@ class RangePartitioner(PartitionerBase):
 
   def _partition_node(self, ntype: Optional[NodeType] = None):
     n = self._num_nodes(ntype)
-    per = (n + self.num_parts - 1) // self.num_parts
-    pb = torch.arange(n, dtype=torch.int64) // per
-    ids = [torch.arange(p * per, min((p + 1) * per, n)) for p in range(self.num_parts)]
+    # balanced bounds floor(n*p/parts): never inverted, and empty only when n < num_parts (a
+    # partition may then own nothing; the tensor book below handles that, RangePartitionBook
+    # -- which requires non-empty ranges -- is only built by callers that checked n >= parts)
+    bounds = [(n * p) // self.num_parts for p in range(self.num_parts + 1)]
+    ids = [torch.arange(bounds[p], bounds[p + 1], dtype=torch.int64) for p in range(self.num_parts)]
+    pb = torch.empty(n, dtype=torch.int64)
+    for p in range(self.num_parts):
+      pb[bounds[p]:bounds[p + 1]] = p
     return ids, GLTPartitionBook(pb)

@@ -70,3 +70,64 @@ def synthetic_dataset_tensors(name: str = 'tiny', seed: int = 0, device='cpu',
     feats[:, shape['feat_dim']:] = 0
   labels = torch.randint(0, shape['num_classes'], (n,), device=device, generator=gen)
   return ei, feats, labels, shape
+
+
+def _rmat_chunks(num_nodes: int, num_edges: int, seed: int, device, a=0.57, b=0.19, c=0.19, chunk: int = 1 << 24):
+  """Yields the [2, n] chunks of `rmat_edges(num_nodes, num_edges, seed=seed)` one at a time (identical RNG
+  consumption, so concatenating the chunks reproduces `rmat_edges` bit for bit) without ever holding the
+  whole edge list: papers100M-shape graphs (1.6 B edges) are generated shard by shard."""
+  scale = max(1, (num_nodes - 1).bit_length())
+  gen = torch.Generator(device=device)
+  gen.manual_seed(seed)
+  done = 0
+  mult = 0x9E3779B1
+  while done < num_edges:
+    n = min(chunk, num_edges - done)
+    src = torch.zeros(n, dtype=torch.int64, device=device)
+    dst = torch.zeros(n, dtype=torch.int64, device=device)
+    for _ in range(scale):
+      r = torch.rand(n, device=device, generator=gen)
+      src = (src << 1) | (r >= a + b).to(torch.int64)
+      dst = (dst << 1) | ((r >= a) & (r < a + b) | (r >= a + b + c)).to(torch.int64)
+    ei = torch.stack([src % num_nodes, dst % num_nodes])
+    yield (ei * mult + 12345) % num_nodes
+    done += n
+
+
+def rmat_degrees(num_nodes: int, num_edges: int, seed: int = 0, device='cpu', undirected: bool = True) -> torch.Tensor:
+  """Out-degree of every node of the (optionally symmetrised) RMAT graph, streamed chunk by chunk."""
+  deg = torch.zeros(num_nodes, dtype=torch.int64, device=device)
+  for ei in _rmat_chunks(num_nodes, num_edges, seed, device):
+    deg += torch.bincount(ei[0], minlength=num_nodes)
+    if undirected:
+      deg += torch.bincount(ei[1], minlength=num_nodes)
+  return deg
+
+
+def rmat_csr_shard(num_nodes: int, num_edges: int, row_begin: int, row_end: int, seed: int = 0, device='cpu',
+                   undirected: bool = True, old2new: Optional[torch.Tensor] = None,
+                   idx_dtype=torch.int32) -> Dict[str, torch.Tensor]:
+  """CSR rows [row_begin, row_end) of the RMAT graph (after the optional id relabelling `old2new`), built
+  from streamed chunks: every rank of a partitioned run generates the same edge stream and keeps its own
+  row range only.  `num_edges` counts generated (one-direction) edges; `undirected` adds the reverse of each.
+  -> {'indptr' int64 [rows+1], 'indices' idx_dtype [nnz] column-sorted, 'row_begin', 'row_end'}."""
+  keys = []
+  n_rows = row_end - row_begin
+  for ei in _rmat_chunks(num_nodes, num_edges, seed, device):
+    if old2new is not None:
+      ei = old2new[ei]
+    for s, d in ((ei[0], ei[1]), (ei[1], ei[0])) if undirected else ((ei[0], ei[1]),):
+      m = (s >= row_begin) & (s < row_end)
+      keys.append((s[m] - row_begin) * num_nodes + d[m])        # (local row, col) packed: < 2^63 for N < 2^31
+    del ei
+  key = torch.cat(keys) if keys else torch.zeros(0, dtype=torch.int64, device=device)
+  del keys
+  key, _ = torch.sort(key)
+  rows = torch.div(key, num_nodes, rounding_mode='floor')
+  indices = (key - rows * num_nodes).to(idx_dtype)
+  del key
+  indptr = torch.zeros(n_rows + 1, dtype=torch.int64, device=device)
+  if rows.numel():
+    torch.cumsum(torch.bincount(rows, minlength=n_rows), 0, out=indptr[1:])
+  return {'indptr': indptr, 'indices': indices.contiguous(), 'eids': None, 'weights': None,
+          'row_begin': int(row_begin), 'row_end': int(row_end)}

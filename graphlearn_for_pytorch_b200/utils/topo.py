@@ -65,6 +65,19 @@ def csr_to_coo(indptr, indices):
   return ptr2ind(indptr), indices
 
 
+def rows_are_sorted(indptr: torch.Tensor, indices: torch.Tensor) -> bool:
+  """True when every row of the compressed layout lists its minor indices in ascending order
+  (O(E) vectorised check: an inversion is only allowed across a row boundary)."""
+  if indices.numel() < 2:
+    return True
+  inv = indices[1:] < indices[:-1]
+  if not bool(inv.any()):
+    return True
+  starts = torch.zeros(indices.numel() + 1, dtype=torch.bool, device=indices.device)
+  starts[indptr.to(torch.int64).clamp(max=indices.numel())] = True   # position i starts a row
+  return not bool((inv & ~starts[1:-1]).any())
+
+
 def sort_csr_columns(indptr, indices, edge_ids=None, edge_weights=None):
   """Make every CSR row column-sorted (used when the user hands in a raw CSR)."""
   row = ptr2ind(indptr)

@@ -155,6 +155,8 @@ def main():
   eng.close()
   dist.barrier()
   torch.cuda.synchronize()
+  if rank == 0:
+    print('ALL OK', flush=True)
   import threading
   t = threading.Timer(20.0, lambda: os._exit(0)); t.daemon = True; t.start()
   dist.destroy_process_group()
