@@ -114,7 +114,7 @@ def canonical_config(args, world):
     'feat_dim': args.feat_dim, 'classes': args.classes, 'optimizer': 'Adam', 'loss': 'NLL',
     'parallelism': f'dp{world}',
     'memory_tier': 'hbm-resident graph+features',
-    'precision': 'bf16 features + bf16 GEMMs, fp32 master weights',
+    'precision': 'bf16 feature storage, fp32 neighbour-mean accumulation, bf16 tensor-core GEMMs, fp32 master weights',
     'timing': 'K-step region repeated on fresh seed batches until >= min_time s; inputs larger than L2',
   }
 

@@ -417,6 +417,259 @@ struct SamplerArena {
   }
 };
 
+
+// ---------------------------------------------------------------------------
+// HeteroArena: device-resident multi-hop sampling + inducing over a heterogeneous graph (native counterpart of
+// the reference's CUDAHeteroInducer, csrc/cuda/inducer.cu:194-338, plus the per-hop orchestration of
+// python/sampler/neighbor_sampler.py:232-317).  Node types and relations are integer coded; every node type
+// owns an id table / id list / hop counters, every relation owns fixed-stride ELL blocks per hop.  One hop =
+// three launches for ALL relations together (grouped sample, per-type finalize, grouped relabel) and no host
+// synchronisation; sizes stay in `counters` until a PyG-shaped COO is requested.
+// ---------------------------------------------------------------------------
+struct HeteroArena {
+  int device, n_types, n_rel, hops;
+  bool with_edge;
+  std::vector<GraphHandle*> graphs;
+  std::vector<int64_t> key_type, nbr_type;
+  std::vector<std::vector<int64_t>> fanouts;       // [rel][hop]
+  std::vector<std::vector<int64_t>> cap_rows;      // [type][hop + 1]
+  std::vector<int64_t> cap_nodes, max_seeds;
+  std::vector<std::unique_ptr<DeviceTable>> tables;
+  Tensor all_keys;                                 // the tables' key arrays, contiguous: one memset clears them
+  Tensor counters, step, descs, type_states, seed_scratch, seed_local, deg_all;
+  std::vector<Tensor> deg;                         // [rel] views into deg_all
+  std::vector<std::vector<Tensor>> ell, ell_eids;  // [rel][hop]
+  std::vector<int> max_k, max_rows;                // per hop
+  bool any_zero_fanout = false;
+  int ctr_type_base(int t) const { return t * 8; }
+  int ctr_rel_base(int r) const { return n_types * 8 + r * 4; }
+  int ctr_overflow() const { return n_types * 8 + n_rel * 4; }
+
+  HeteroArena(int dev, int64_t n_types_, std::vector<GraphHandle*> graphs_, std::vector<int64_t> key_type_,
+              std::vector<int64_t> nbr_type_, std::vector<std::vector<int64_t>> fanouts_,
+              std::vector<int64_t> num_nodes, std::vector<int64_t> max_seeds_, bool with_edge_, int64_t seed,
+              bool weighted, bool replace, int64_t cap_limit, std::vector<std::vector<int64_t>> cap_override)
+      : device(dev), n_types(n_types_), n_rel(graphs_.size()), with_edge(with_edge_), graphs(std::move(graphs_)),
+        key_type(std::move(key_type_)), nbr_type(std::move(nbr_type_)), fanouts(std::move(fanouts_)),
+        max_seeds(std::move(max_seeds_)) {
+    c10::cuda::CUDAGuard guard(device);
+    TORCH_CHECK(n_rel >= 1 && static_cast<int>(key_type.size()) == n_rel && static_cast<int>(nbr_type.size()) == n_rel &&
+                static_cast<int>(fanouts.size()) == n_rel, "HeteroArena: one (graph, key type, nbr type, fanouts) per relation");
+    TORCH_CHECK(static_cast<int>(num_nodes.size()) == n_types && static_cast<int>(max_seeds.size()) == n_types);
+    hops = fanouts[0].size();
+    TORCH_CHECK(hops >= 1 && hops <= 4, "1..4 hops supported by the arena");
+    for (int r = 0; r < n_rel; ++r) {
+      TORCH_CHECK(static_cast<int>(fanouts[r].size()) == hops, "all relations need the same number of hops");
+      TORCH_CHECK(key_type[r] >= 0 && key_type[r] < n_types && nbr_type[r] >= 0 && nbr_type[r] < n_types);
+      TORCH_CHECK(!with_edge || graphs[r]->has_eids, "graph has no edge ids");
+      TORCH_CHECK(!weighted || graphs[r]->has_weights, "graph has no device edge weights");
+      for (int h = 0; h < hops; ++h) {
+        TORCH_CHECK(fanouts[r][h] >= 0 && fanouts[r][h] <= 512, "arena fanouts must be in [0,512]");
+        if (fanouts[r][h] == 0) any_zero_fanout = true;
+      }
+    }
+    if (cap_limit <= 0) cap_limit = INT64_MAX;
+    // frontier capacities: worst case of the fan-out recursion, bounded by the type's node count and cap_limit
+    cap_rows.assign(n_types, std::vector<int64_t>(hops + 1, 0));
+    for (int t = 0; t < n_types; ++t) cap_rows[t][0] = max_seeds[t];
+    for (int h = 0; h < hops; ++h)
+      for (int t = 0; t < n_types; ++t) {
+        int64_t rows = 0;
+        for (int r = 0; r < n_rel; ++r)
+          if (nbr_type[r] == t) rows += cap_rows[key_type[r]][h] * fanouts[r][h];
+        rows = std::min(rows, std::min(num_nodes[t] > 0 ? num_nodes[t] : INT64_MAX, cap_limit));
+        if (!cap_override.empty()) rows = std::min(rows, std::max<int64_t>(cap_override[t][h + 1], 0));
+        cap_rows[t][h + 1] = rows;
+      }
+    auto o64 = torch::TensorOptions().dtype(torch::kInt64).device(torch::kCUDA, device);
+    auto o32 = torch::TensorOptions().dtype(torch::kInt32).device(torch::kCUDA, device);
+    auto o8 = torch::TensorOptions().dtype(torch::kUInt8).device(torch::kCUDA, device);
+    counters = torch::zeros({n_types * 8 + n_rel * 4 + 8}, o32);   // [types | relations | overflow, scratch]
+    step = torch::zeros({1}, o32);
+    int32_t* cbase = counters.data_ptr<int32_t>();
+    // id tables: key arrays carved out of one buffer so a batch starts with ONE memset
+    int64_t total_slots = 0;
+    std::vector<int64_t> slots(n_types);
+    cap_nodes.assign(n_types, 0);
+    int64_t max_seed_all = 1;
+    for (int t = 0; t < n_types; ++t) {
+      int64_t cn = 0;
+      for (int h = 0; h <= hops; ++h) cn += cap_rows[t][h];
+      if (num_nodes[t] > 0) cn = std::min(cn, num_nodes[t] + max_seeds[t]);
+      cap_nodes[t] = std::max<int64_t>(cn, 16);
+      TORCH_CHECK(cap_nodes[t] < (1LL << 30), "sampler arena too large");
+      int64_t sl = 64;
+      while (sl < cap_nodes[t] * 2) sl <<= 1;
+      slots[t] = sl;
+      total_slots += sl;
+      max_seed_all = std::max(max_seed_all, max_seeds[t]);
+    }
+    all_keys = torch::full({total_slots}, -1, o64);
+    int64_t off = 0;
+    for (int t = 0; t < n_types; ++t) {
+      auto tb = std::make_unique<DeviceTable>(device, 16);   // small placeholder, re-pointed below
+      tb->cap_nodes = cap_nodes[t];
+      tb->keys = all_keys.narrow(0, off, slots[t]);
+      tb->vals = torch::zeros({slots[t]}, o32);
+      tb->aux = torch::zeros({slots[t]}, o32);
+      tb->nodes = torch::zeros({cap_nodes[t]}, o64);
+      tb->cursor = counters.narrow(0, ctr_type_base(t) + 6, 1);
+      tb->ht.keys = tb->keys.data_ptr<int64_t>();
+      tb->ht.vals = tb->vals.data_ptr<int32_t>();
+      tb->ht.aux = tb->aux.data_ptr<int32_t>();
+      tb->ht.mask = static_cast<uint32_t>(slots[t] - 1);
+      off += slots[t];
+      tables.push_back(std::move(tb));
+    }
+    seed_scratch = torch::zeros({max_seed_all}, o32);
+    seed_local = torch::zeros({n_types, max_seed_all}, o32);
+    // per-relation degree arrays (indexed by the key type's local id), one contiguous buffer
+    int64_t deg_total = 0;
+    for (int r = 0; r < n_rel; ++r) deg_total += cap_nodes[key_type[r]];
+    deg_all = torch::zeros({deg_total}, o32);
+    off = 0;
+    for (int r = 0; r < n_rel; ++r) {
+      deg.push_back(deg_all.narrow(0, off, cap_nodes[key_type[r]]));
+      off += cap_nodes[key_type[r]];
+    }
+    ell.resize(n_rel);
+    ell_eids.resize(n_rel);
+    for (int r = 0; r < n_rel; ++r)
+      for (int h = 0; h < hops; ++h) {
+        const int64_t n = cap_rows[key_type[r]][h] * fanouts[r][h];
+        ell[r].push_back(torch::full({std::max<int64_t>(n, 1)}, -1, o32));
+        ell_eids[r].push_back(with_edge ? torch::full({std::max<int64_t>(n, 1)}, -1, o64) : Tensor());
+      }
+    // static launch descriptors
+    std::vector<HopArgs> hd(static_cast<size_t>(hops) * n_rel);
+    max_k.assign(hops, 0);
+    max_rows.assign(hops, 1);
+    for (int h = 0; h < hops; ++h)
+      for (int r = 0; r < n_rel; ++r) {
+        HopArgs a{};
+        const int kt = key_type[r], nt = nbr_type[r];
+        a.g = graphs[r]->tbl;
+        a.t = tables[nt]->ht;
+        a.c.cum = cbase + ctr_type_base(kt);
+        a.c.edges = cbase + ctr_rel_base(r);
+        a.c.cursor = cbase + ctr_type_base(nt) + 6;
+        a.c.overflow = cbase + ctr_overflow();
+        a.nodes = tables[kt]->nodes.data_ptr<int64_t>();
+        a.nodes_out = tables[nt]->nodes.data_ptr<int64_t>();
+        a.ell = ell[r][h].data_ptr<int32_t>();
+        a.ell_eids = with_edge ? ell_eids[r][h].data_ptr<int64_t>() : nullptr;
+        a.deg = deg[r].data_ptr<int32_t>();
+        a.hop = h;
+        a.k = static_cast<int>(fanouts[r][h]);
+        a.cap_rows = static_cast<int>(cap_rows[kt][h]);
+        a.cap_nodes = static_cast<int>(cap_nodes[nt]);
+        a.cap_rows_next = static_cast<int>(cap_rows[nt][h + 1]);
+        a.weighted = weighted ? 1 : 0;
+        a.replace = replace ? 1 : 0;
+        a.seed = static_cast<uint64_t>(seed);
+        a.stream = static_cast<uint32_t>(h * n_rel + r);
+        a.stream_dev = step.data_ptr<int32_t>();
+        a.stream_stride = 1;   // `step` holds the Philox stream base itself (callers add hops * n_rel per batch)
+        a.bound_ptr = cbase + ctr_type_base(nt) + h + 2;
+        hd[static_cast<size_t>(h) * n_rel + r] = a;
+        if (a.k > 0) {
+          max_k[h] = std::max(max_k[h], a.k);
+          max_rows[h] = std::max(max_rows[h], a.cap_rows);
+        }
+      }
+    descs = torch::empty({static_cast<int64_t>(hd.size() * sizeof(HopArgs))}, o8);
+    cudaMemcpy(descs.data_ptr(), hd.data(), hd.size() * sizeof(HopArgs), cudaMemcpyHostToDevice);
+    std::vector<HeteroTypeState> ts(n_types);
+    for (int t = 0; t < n_types; ++t) {
+      ts[t].cum = cbase + ctr_type_base(t);
+      ts[t].cursor = cbase + ctr_type_base(t) + 6;
+      ts[t].cap_nodes = static_cast<int>(cap_nodes[t]);
+      for (int h = 0; h < 5; ++h) ts[t].cap_rows[h] = h <= hops ? static_cast<int>(cap_rows[t][h]) : 0;
+    }
+    type_states = torch::empty({static_cast<int64_t>(ts.size() * sizeof(HeteroTypeState))}, o8);
+    cudaMemcpy(type_states.data_ptr(), ts.data(), ts.size() * sizeof(HeteroTypeState), cudaMemcpyHostToDevice);
+    check_cuda_err("HeteroArena setup");
+  }
+
+  // seeds of one or more node types -> multi-hop sample of every relation; no host synchronisation
+  void sample(const std::vector<int64_t>& seed_types, const std::vector<Tensor>& seeds, int64_t step_inc) {
+    c10::cuda::CUDAGuard guard(device);
+    TORCH_CHECK(seed_types.size() == seeds.size() && !seeds.empty());
+    cudaStream_t s = cur_stream();
+    int32_t* cbase = counters.data_ptr<int32_t>();
+    cudaMemsetAsync(cbase, 0, sizeof(int32_t) * ctr_overflow(), s);          // every cum / cursor / edge counter
+    cudaMemsetAsync(all_keys.data_ptr(), 0xFF, all_keys.numel() * sizeof(int64_t), s);
+    if (any_zero_fanout) cudaMemsetAsync(deg_all.data_ptr(), 0, deg_all.numel() * sizeof(int32_t), s);
+    for (size_t i = 0; i < seeds.size(); ++i) {
+      const int t = static_cast<int>(seed_types[i]);
+      const Tensor& sd = seeds[i];
+      TORCH_CHECK(t >= 0 && t < n_types && sd.is_cuda() && sd.scalar_type() == torch::kInt64 && sd.is_contiguous());
+      TORCH_CHECK(sd.numel() <= max_seeds[t], "more seeds than the arena was built for");
+      BatchCounters c{cbase + ctr_type_base(t), cbase + ctr_overflow() + 1 /* scratch */, cbase + ctr_type_base(t) + 6,
+                      cbase + ctr_overflow()};
+      // init_seeds zeroes 4 "edge" counters: point them at scratch words that nothing else reads
+      launch_init_seeds(sd.data_ptr<int64_t>(), sd.numel(), nullptr, tables[t]->ht, tables[t]->nodes.data_ptr<int64_t>(),
+                        seed_local.data_ptr<int32_t>() + t * seed_local.size(1), seed_scratch.data_ptr<int32_t>(), c,
+                        (i == 0 && step_inc != 0) ? step.data_ptr<int32_t>() : nullptr, static_cast<int>(step_inc), s);
+    }
+    const HopArgs* d = reinterpret_cast<const HopArgs*>(descs.data_ptr());
+    const HeteroTypeState* ts = reinterpret_cast<const HeteroTypeState*>(type_states.data_ptr());
+    for (int h = 0; h < hops; ++h) {
+      launch_sample_hop_grouped(d + static_cast<size_t>(h) * n_rel, n_rel, max_k[h], max_rows[h], s);
+      launch_hetero_finalize(ts, n_types, h, s);
+      launch_relabel_hop_grouped(d + static_cast<size_t>(h) * n_rel, n_rel, max_rows[h], s);
+    }
+    check_cuda_err("hetero arena sample");
+  }
+
+  // PyG-shaped output (ONE host sync for the sizes):
+  //   nodes[t] (global ids, hop-contiguous), per relation (rows = neighbour local ids, cols = key local ids, eids),
+  //   num_sampled_nodes[t][hop], num_sampled_edges[rel][hop]
+  std::tuple<std::vector<Tensor>, std::vector<Tensor>, std::vector<Tensor>, std::vector<Tensor>,
+             std::vector<std::vector<int64_t>>, std::vector<std::vector<int64_t>>> to_coo() {
+    c10::cuda::CUDAGuard guard(device);
+    auto o64 = torch::TensorOptions().dtype(torch::kInt64).device(torch::kCUDA, device);
+    Tensor host = counters.cpu();  // sync
+    const int32_t* c = host.data_ptr<int32_t>();
+    std::vector<Tensor> nodes_out, rows_out, cols_out, eids_out;
+    std::vector<std::vector<int64_t>> nn(n_types), ne(n_rel);
+    for (int t = 0; t < n_types; ++t) {
+      const int32_t* cum = c + ctr_type_base(t);
+      for (int h = 0; h <= hops; ++h) nn[t].push_back(cum[h + 1] - cum[h]);
+      nodes_out.push_back(tables[t]->nodes.narrow(0, 0, cum[hops + 1]).clone());
+    }
+    for (int r = 0; r < n_rel; ++r) {
+      const int32_t* cum = c + ctr_type_base(key_type[r]);
+      int64_t E = 0;
+      for (int h = 0; h < hops; ++h) { ne[r].push_back(c[ctr_rel_base(r) + h]); E += c[ctr_rel_base(r) + h]; }
+      const int64_t T = cum[hops];
+      Tensor rows = torch::empty({E}, o64), cols = torch::empty({E}, o64);
+      Tensor eids = with_edge ? torch::empty({E}, o64) : Tensor();
+      if (E > 0) {
+        Tensor offs = torch::zeros({T + 1}, o64);
+        offs.narrow(0, 1, T).copy_(deg[r].narrow(0, 0, T).to(torch::kInt64).cumsum(0));
+        for (int h = 0; h < hops; ++h) {
+          if (fanouts[r][h] <= 0) continue;
+          launch_ell_to_coo(ell[r][h].data_ptr<int32_t>(), with_edge ? ell_eids[r][h].data_ptr<int64_t>() : nullptr,
+                            deg[r].data_ptr<int32_t>(), offs.data_ptr<int64_t>(),
+                            counters.data_ptr<int32_t>() + ctr_type_base(key_type[r]), h, fanouts[r][h],
+                            cap_rows[key_type[r]][h], rows.data_ptr<int64_t>(), cols.data_ptr<int64_t>(),
+                            with_edge ? eids.data_ptr<int64_t>() : nullptr, cur_stream());
+        }
+      }
+      rows_out.push_back(rows); cols_out.push_back(cols); eids_out.push_back(eids);
+    }
+    check_cuda_err("hetero to_coo");
+    return {nodes_out, rows_out, cols_out, eids_out, nn, ne};
+  }
+
+  int64_t overflow_index() const { return ctr_overflow(); }
+  Tensor seed_local_of(int64_t t) { return seed_local[t]; }
+  Tensor nodes_of(int64_t t) { return tables[t]->nodes; }
+  Tensor deg_of(int64_t r) { return deg[r]; }
+  Tensor ell_of(int64_t r, int64_t h) { return ell[r][h]; }
+};
+
 // ---------------------------------------------------------------------------
 // RowTableHandle: multi-source row store (UnifiedTensor).
 // ---------------------------------------------------------------------------
@@ -1021,6 +1274,28 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def_readonly("cap_rows", &SamplerArena::cap_rows)
       .def_readonly("cap_nodes", &SamplerArena::cap_nodes)
       .def_readonly("fanouts", &SamplerArena::fanouts);
+  py::class_<HeteroArena>(m, "HeteroArena")
+      .def(py::init<int, int64_t, std::vector<GraphHandle*>, std::vector<int64_t>, std::vector<int64_t>,
+                    std::vector<std::vector<int64_t>>, std::vector<int64_t>, std::vector<int64_t>, bool, int64_t, bool,
+                    bool, int64_t, std::vector<std::vector<int64_t>>>(),
+           py::arg("device"), py::arg("n_types"), py::arg("graphs"), py::arg("key_type"), py::arg("nbr_type"),
+           py::arg("fanouts"), py::arg("num_nodes"), py::arg("max_seeds"), py::arg("with_edge") = false,
+           py::arg("seed") = 0, py::arg("weighted") = false, py::arg("replace") = false, py::arg("cap_limit") = 0,
+           py::arg("cap_override") = std::vector<std::vector<int64_t>>{}, py::keep_alive<1, 4>())
+      .def("sample", &HeteroArena::sample, py::arg("seed_types"), py::arg("seeds"), py::arg("step_inc") = 1)
+      .def("to_coo", &HeteroArena::to_coo)
+      .def("seed_local_of", &HeteroArena::seed_local_of)
+      .def("overflow_index", &HeteroArena::overflow_index)
+      .def("nodes_of", &HeteroArena::nodes_of)
+      .def("deg_of", &HeteroArena::deg_of)
+      .def("ell_of", &HeteroArena::ell_of)
+      .def_readonly("counters", &HeteroArena::counters)
+      .def_readonly("step", &HeteroArena::step)
+      .def_readonly("cap_rows", &HeteroArena::cap_rows)
+      .def_readonly("cap_nodes", &HeteroArena::cap_nodes)
+      .def_readonly("hops", &HeteroArena::hops)
+      .def_readonly("n_types", &HeteroArena::n_types)
+      .def_readonly("n_rel", &HeteroArena::n_rel);
   py::class_<RowTableHandle>(m, "RowTableHandle")
       .def(py::init<int>())
       .def("append", &RowTableHandle::append)

@@ -84,9 +84,29 @@ struct HopArgs {
   uint64_t seed;
   uint32_t stream;
   const int32_t* stream_dev;  // optional device step counter mixed into the Philox stream
+  // --- heterogeneous graphs: frontier and neighbours belong to different node types -----------------
+  int64_t* nodes_out;         // id list of the NEIGHBOUR type (appended); nullptr = same list as `nodes`
+  const int32_t* bound_ptr;   // precomputed id bound of the neighbour type for this hop (k_hetero_finalize);
+                              // nullptr = derive it from c.cum / c.cursor (single node type)
+  uint32_t stream_stride;     // Philox stream ids consumed per device step (0 = 8, the homogeneous arena)
 };
 void launch_sample_hop(const HopArgs& a, cudaStream_t s);
 void launch_relabel_hop(const HopArgs& a, cudaStream_t s);
+
+// Heterogeneous sampling (native hetero inducer; reference csrc/cuda/inducer.cu:194-338 CUDAHeteroInducer +
+// python/sampler/neighbor_sampler.py:232-317): one GROUPED launch per hop over all relations.  `descs` is a
+// device array of `n_rel` HopArgs (blockIdx.y selects the relation; relations with k <= 0 are skipped);
+// `max_k` / `max_rows` are the maxima over the relations (template / grid selection).
+void launch_sample_hop_grouped(const HopArgs* descs, int n_rel, int max_k, int max_rows, cudaStream_t s);
+void launch_relabel_hop_grouped(const HopArgs* descs, int n_rel, int max_rows, cudaStream_t s);
+struct HeteroTypeState {
+  int32_t* cum;       // [6] of this node type
+  int32_t* cursor;
+  int cap_nodes;
+  int cap_rows[5];    // frontier capacity per hop (+ trailing entry)
+};
+// cum[hop + 2] = cursor = min(cursor, cap_nodes, cum[hop + 1] + cap_rows[hop + 1]) for every node type
+void launch_hetero_finalize(const HeteroTypeState* types, int n_types, int hop, cudaStream_t s);
 
 // One-hop API sampler (NeighborOutput): fixed-stride output, no dedup.
 void launch_sample_one_hop(GraphTable g, const int64_t* seeds, int n, int k, int weighted,

@@ -100,7 +100,7 @@ __device__ __forceinline__ void pick_positions(const GraphTable& g, const RowRef
 }
 
 template <int G, int MAXC>
-__global__ void __launch_bounds__(256) k_sample_hop(HopArgs a) {
+__device__ __forceinline__ void sample_hop_body(const HopArgs& a) {
   const int lane = threadIdx.x & 31;
   const int gl = lane % G;
   const int gw = lane / G;
@@ -111,7 +111,9 @@ __global__ void __launch_bounds__(256) k_sample_hop(HopArgs a) {
   const int warps_per_block = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5;
   // under CUDA-graph replay the host-side stream id is frozen: advance it from the device
-  const uint32_t rng_stream = a.stream + (a.stream_dev ? static_cast<uint32_t>(*a.stream_dev) * 8u : 0u);
+  const uint32_t rng_stream = a.stream + (a.stream_dev ? static_cast<uint32_t>(*a.stream_dev) *
+                                                         (a.stream_stride ? a.stream_stride : 8u) : 0u);
+  int64_t* nodes_out = a.nodes_out ? a.nodes_out : a.nodes;
   int edge_acc = 0;
   for (int base = (blockIdx.x * warps_per_block + warp) * RPW; base < n_rows;
        base += gridDim.x * warps_per_block * RPW) {
@@ -152,7 +154,7 @@ __global__ void __launch_bounds__(256) k_sample_hop(HopArgs a) {
       }
       if (is_new) {
         const int id = id_base + __popc(nm & lanemask_lt());
-        if (id < a.cap_nodes) { a.t.vals[slot] = id; a.nodes[id] = key; }
+        if (id < a.cap_nodes) { a.t.vals[slot] = id; nodes_out[id] = key; }
         else a.t.vals[slot] = -1;  // arena overflow: the node is dropped (counted by the relabel pass)
       }
       if (valid && j < a.k) {
@@ -169,14 +171,28 @@ __global__ void __launch_bounds__(256) k_sample_hop(HopArgs a) {
   if (lane == 0 && edge_acc) atomicAdd(a.c.edges + a.hop, edge_acc);
 }
 
-__global__ void k_relabel_hop(HopArgs a) {
+template <int G, int MAXC>
+__global__ void __launch_bounds__(256) k_sample_hop(HopArgs a) {
+  sample_hop_body<G, MAXC>(a);
+}
+
+// one launch for every relation of a heterogeneous hop: blockIdx.y = relation
+template <int G, int MAXC>
+__global__ void __launch_bounds__(256) k_sample_hop_grouped(const HopArgs* descs) {
+  const HopArgs& a = descs[blockIdx.y];
+  if (a.k <= 0) return;
+  sample_hop_body<G, MAXC>(a);
+}
+
+__device__ __forceinline__ void relabel_hop_body(const HopArgs& a) {
   const int f_begin = a.c.cum[a.hop];
   const int n_rows = min(a.c.cum[a.hop + 1] - f_begin, a.cap_rows);
   // Capacity guard (arenas may be sized from calibration instead of the worst case): the
   // next frontier holds at most cap_rows_next rows and the arena cap_nodes nodes.  Nodes past
   // the bound are dropped: their slot is poisoned (-1) so later hops treat them as absent.
   // Every thread derives the same bound from stable inputs; the cursor reset is idempotent.
-  const int bound = min(min(*a.c.cursor, a.cap_nodes), a.c.cum[a.hop + 1] + a.cap_rows_next);
+  const int bound = a.bound_ptr ? *a.bound_ptr
+                                : min(min(*a.c.cursor, a.cap_nodes), a.c.cum[a.hop + 1] + a.cap_rows_next);
   // One thread per frontier row (k <= fan-out entries, contiguous): slot -> local id, and rows that
   // lost a neighbour (arena / table overflow) are compacted in place with deg[] and the hop's edge
   // counter corrected, so the mean divides by the neighbours that exist and to_coo never emits -1.
@@ -208,10 +224,27 @@ __global__ void k_relabel_hop(HopArgs a) {
     if (a.c.overflow) atomicAdd(a.c.overflow, dropped);
     atomicSub(a.c.edges + a.hop, dropped);
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  if (a.bound_ptr == nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
     a.c.cum[a.hop + 2] = bound;
     *a.c.cursor = bound;
   }
+}
+
+__global__ void k_relabel_hop(HopArgs a) { relabel_hop_body(a); }
+
+__global__ void k_relabel_hop_grouped(const HopArgs* descs) {
+  const HopArgs& a = descs[blockIdx.y];
+  if (a.k <= 0) return;
+  relabel_hop_body(a);
+}
+
+__global__ void k_hetero_finalize(const HeteroTypeState* types, int n_types, int hop) {
+  const int t = threadIdx.x;
+  if (t >= n_types) return;
+  const HeteroTypeState& ty = types[t];
+  const int bound = min(min(*ty.cursor, ty.cap_nodes), ty.cum[hop + 1] + ty.cap_rows[hop + 1]);
+  ty.cum[hop + 2] = bound;
+  *ty.cursor = bound;
 }
 
 // Ordered (first-occurrence) seed insertion; single CTA, seeds are few.
@@ -437,6 +470,26 @@ void launch_sample_hop(const HopArgs& a, cudaStream_t s) {
 
 void launch_relabel_hop(const HopArgs& a, cudaStream_t s) {
   k_relabel_hop<<<grid_for(a.cap_rows, 256), 256, 0, s>>>(a);
+}
+
+void launch_sample_hop_grouped(const HopArgs* descs, int n_rel, int max_k, int max_rows, cudaStream_t s) {
+  if (n_rel <= 0 || max_k <= 0) return;
+  GLT_DISPATCH_FANOUT(max_k, {
+    const int rows_per_block = (256 / 32) * (32 / G);
+    dim3 grid(grid_for(max_rows, rows_per_block, 148 * 8), n_rel);
+    k_sample_hop_grouped<G, MAXC><<<grid, 256, 0, s>>>(descs);
+  });
+}
+
+void launch_relabel_hop_grouped(const HopArgs* descs, int n_rel, int max_rows, cudaStream_t s) {
+  if (n_rel <= 0) return;
+  dim3 grid(grid_for(max_rows, 256, 148 * 8), n_rel);
+  k_relabel_hop_grouped<<<grid, 256, 0, s>>>(descs);
+}
+
+void launch_hetero_finalize(const HeteroTypeState* types, int n_types, int hop, cudaStream_t s) {
+  if (n_types <= 0) return;
+  k_hetero_finalize<<<1, 32 * ((n_types + 31) / 32), 0, s>>>(types, n_types, hop);
 }
 
 void launch_sample_one_hop(GraphTable g, const int64_t* seeds, int n, int k, int weighted,

@@ -301,7 +301,77 @@ class NeighborSampler(BaseSampler):
       self._type_bounds[nt] = bound
     return self._type_bounds[nt] + n_seeds if self._type_bounds[nt] > 0 else None
 
+  # ------------------------------------------------------------------ native hetero arena
+  def _hetero_arena_ok(self) -> bool:
+    if not self.is_cuda or self.num_hops > 4 or self.num_hops < 1:
+      return False
+    import os
+    if os.environ.get('GLT_B200_HETERO_ARENA', '1') == '0':
+      return False
+    return all(0 <= int(k) <= 512 for v in self.num_neighbors.values() for k in v)
+
+  def _get_hetero_arena(self, seed_counts: Dict[NodeType, int]):
+    """Native device-resident hetero sampler + inducer (csrc/bindings.cc HeteroArena): node types and relations
+    are integer coded (sorted node types; relations in `self.edge_types` order so the Philox stream ids equal the
+    per-relation one-hop path), one grouped launch per hop over all relations, no host sync until to_coo()."""
+    ntypes = sorted({t for et in self.edge_types for t in self._etype_ends(et)} | set(seed_counts))
+    caps = tuple(1 << max(4, (max(int(seed_counts.get(nt, 0)), 1) - 1).bit_length()) if nt in seed_counts else 0
+                 for nt in ntypes)
+    limit = getattr(self, '_hetero_cap_limit', 1 << 22)
+    key = (caps, limit, self.with_edge)
+    if getattr(self, '_harena_key', None) != key:
+      tid = {nt: i for i, nt in enumerate(ntypes)}
+      graphs, kt, nt_, fan = [], [], [], []
+      for et in self.edge_types:
+        frm, to = self._etype_ends(et)
+        g = self.graph[et]
+        g.lazy_init()
+        graphs.append(g.graph_handler)
+        kt.append(tid[frm]); nt_.append(tid[to])
+        fan.append([int(k) for k in self.num_neighbors[et]])
+      num_nodes = [int(self._hetero_type_bound(nt, 0) or 0) for nt in ntypes]
+      weighted = bool(self.with_weight and all(h.has_weights for h in graphs))
+      self._harena = self._nat.HeteroArena(self.device.index, len(ntypes), graphs, kt, nt_, fan, num_nodes,
+                                           list(caps), self.with_edge, self.seed, weighted, bool(self.replace),
+                                           int(limit), [])
+      self._harena_key, self._harena_types, self._harena_overflow = key, ntypes, 0
+    return self._harena, self._harena_types
+
+  def _hetero_arena_sample(self, seeds_dict: Dict[NodeType, torch.Tensor]) -> HeteroSamplerOutput:
+    arena, ntypes = self._get_hetero_arena({nt: int(v.numel()) for nt, v in seeds_dict.items()})
+    tid = {nt: i for i, nt in enumerate(ntypes)}
+    stream = self._next_stream(self.num_hops * max(1, len(self.edge_types)))
+    arena.step.fill_(int(stream))
+    order = [nt for nt in seeds_dict]
+    arena.sample([tid[nt] for nt in order], [seeds_dict[nt].contiguous() for nt in order], 0)
+    nodes, rows, cols, eids, nn, ne = arena.to_coo()                  # the only host sync of the batch
+    ovf = int(arena.counters[arena.overflow_index()].item())
+    if ovf > self._harena_overflow:
+      import warnings
+      warnings.warn(f'hetero sampling arena dropped {ovf - self._harena_overflow} neighbours (frontier capacity '
+                    f'{self._hetero_cap_limit if hasattr(self, "_hetero_cap_limit") else 1 << 22} rows); '
+                    'doubling the capacity for the following batches')
+      self._hetero_cap_limit = 2 * getattr(self, '_hetero_cap_limit', 1 << 22)
+    node = {nt: nodes[i] for i, nt in enumerate(ntypes) if nodes[i].numel() > 0}
+    num_nodes = {nt: [int(x) for x in nn[i]] for i, nt in enumerate(ntypes) if nodes[i].numel() > 0}
+    row, col, edge, num_edges, out_types = {}, {}, {}, {}, []
+    for r, et in enumerate(self.edge_types):
+      key = reverse_edge_type(et) if self.edge_dir == 'out' else et
+      out_types.append(key)
+      if rows[r].numel() == 0:
+        continue
+      row[key], col[key] = rows[r], cols[r]
+      if self.with_edge:
+        edge[key] = eids[r]
+      num_edges[key] = [int(x) for x in ne[r]]
+    batch = {nt: node[nt][:num_nodes[nt][0]].clone() for nt in seeds_dict if nt in node}
+    return HeteroSamplerOutput(node=node, row=row, col=col, edge=edge if self.with_edge else None, batch=batch,
+                               num_sampled_nodes=num_nodes, num_sampled_edges=num_edges, edge_types=out_types,
+                               device=self.device)
+
   def _hetero_sample_from_nodes(self, seeds_dict: Dict[NodeType, torch.Tensor]) -> HeteroSamplerOutput:
+    if self._hetero_arena_ok():
+      return self._hetero_arena_sample({nt: v.to(self.device, dtype=torch.int64) for nt, v in seeds_dict.items()})
     n_seed_total = sum(v.numel() for v in seeds_dict.values())
     cap = self._hetero_table_cap(n_seed_total)
     tables: Dict[NodeType, IdTable] = {}

@@ -1,4 +1,6 @@
 """sm_100a kernels vs. the CPU reference ops / plain PyTorch fp32 (needs a B200)."""
+import sys
+
 import pytest
 import torch
 
@@ -285,3 +287,54 @@ def test_hetero_and_link_sampling_gpu_matches_cpu(native):
   assert eli.shape == (2, 9) and lab.tolist() == [1, 1, 1] + [0] * 6
   ns, nd = out.node[eli[0, 3:]], out.node[eli[1, 3:]]
   assert torch.all(((nd - ns) % 40 != 1) & ((nd - ns) % 40 != 2))
+
+
+def test_hetero_arena_igbh_shape_matches_cpu_sampler(native):
+  """Native grouped hetero sampler/inducer (HeteroArena) on an IGBH-shaped schema (4 node types, 7 relations,
+  3 hops, edge_dir='in'): the sampled edge SET of every relation and the node set of every type must equal the
+  CPU sampler's (same Philox streams), local ids must be hop-contiguous, and the generic per-relation device path
+  (GLT_B200_HETERO_ARENA=0) must agree as well."""
+  import os
+  sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'examples'))
+  from common import synthetic_igbh
+  edges, feats, labels, sizes = synthetic_igbh(3000, 1500, 60, 40, feat_dim=16, seed=1)
+  seeds = torch.arange(5, 3000, 11)[:200]
+  outs = {}
+  for mode in ('CPU', 'CUDA', 'CUDA-generic'):
+    ds = glt.data.Dataset(edge_dir='in')
+    ds.init_graph(edges, graph_mode='CPU' if mode == 'CPU' else 'CUDA', device=0, num_nodes=sizes)
+    s = NeighborSampler(ds.graph, [4, 3, 2], seed=9, device=None if mode == 'CPU' else DEV, edge_dir='in')
+    if mode == 'CUDA-generic':
+      os.environ['GLT_B200_HETERO_ARENA'] = '0'
+    try:
+      outs[mode] = [s.sample_from_nodes(NodeSamplerInput(seeds, 'paper')) for _ in range(2)]
+    finally:
+      os.environ.pop('GLT_B200_HETERO_ARENA', None)
+  for it in range(2):
+    a = outs['CPU'][it]
+    for other in ('CUDA', 'CUDA-generic'):
+      b = outs[other][it]
+      assert set(a.row.keys()) == set(b.row.keys()), (other, a.row.keys(), b.row.keys())
+      for nt in a.node:
+        assert set(a.node[nt].tolist()) == set(b.node[nt].cpu().tolist()), (other, nt)
+      for et in a.row:
+        st, dt = et[0], et[2]
+        ea = set(zip(a.node[st][a.row[et]].tolist(), a.node[dt][a.col[et]].tolist()))
+        eb = set(zip(b.node[st][b.row[et]].cpu().tolist(), b.node[dt][b.col[et]].cpu().tolist()))
+        assert ea == eb, (other, et, len(ea), len(eb))
+        assert a.row[et].numel() == b.row[et].numel()
+      for nt in a.node:
+        assert sum(a.num_sampled_nodes[nt]) == sum(b.num_sampled_nodes[nt]) == a.node[nt].numel()
+      assert torch.equal(a.batch['paper'], b.batch['paper'].cpu())
+  # hop-contiguity of the arena's local ids: edges of hop h only reference nodes known after hop h
+  b = outs['CUDA'][0]
+  for et, r in b.row.items():
+    st, dt = et[0], et[2]
+    ne, off = b.num_sampled_edges[et], 0
+    for h, n_e in enumerate(ne):
+      if n_e == 0:
+        continue
+      seg_r, seg_c = r[off:off + n_e], b.col[et][off:off + n_e]
+      assert int(seg_c.max()) < sum(b.num_sampled_nodes[dt][:h + 1])       # targets: frontier of hop h
+      assert int(seg_r.max()) < sum(b.num_sampled_nodes[st][:h + 2])       # sources: known after hop h
+      off += n_e
