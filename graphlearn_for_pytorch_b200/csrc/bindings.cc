@@ -617,7 +617,7 @@ struct HeteroArena {
     for (int h = 0; h < hops; ++h) {
       launch_sample_hop_grouped(d + static_cast<size_t>(h) * n_rel, n_rel, max_k[h], max_rows[h], s);
       launch_hetero_finalize(ts, n_types, h, s);
-      launch_relabel_hop_grouped(d + static_cast<size_t>(h) * n_rel, n_rel, max_rows[h], s);
+      launch_relabel_hop_grouped(d + static_cast<size_t>(h) * n_rel, n_rel, max_k[h], max_rows[h], s);
     }
     check_cuda_err("hetero arena sample");
   }
@@ -722,7 +722,8 @@ struct RowTableHandle {
     c10::cuda::CUDAGuard guard(device);
     const int64_t* map = (id2index.has_value() && id2index->defined()) ? id2index->data_ptr<int64_t>() : nullptr;
     const int32_t* nd = (n_dev.has_value() && n_dev->defined()) ? n_dev->data_ptr<int32_t>() : nullptr;
-    TORCH_CHECK(out.is_contiguous() && out.size(0) >= idx.numel());
+    TORCH_CHECK(out.dim() == 2 && out.stride(1) == 1 && out.size(0) >= idx.numel() && out.size(1) >= width &&
+                (out.stride(0) * out.element_size()) % 16 == 0, "gather_into: [rows, >= width] destination with unit inner stride");
     launch_gather_rows(tbl, idx.data_ptr<int64_t>(), map, idx.numel(), nd, out.data_ptr(),
                        out.stride(0) * out.element_size(), cur_stream(), map ? id2index->numel() : 0);
     check_cuda_err("gather_into");
@@ -794,6 +795,57 @@ static void sage_scatter_bwd(const Tensor& dA, int64_t d, const Tensor& counters
   a.dH = dH.data_ptr<float>();
   launch_sage_scatter_bwd(a, cur_stream());
   check_cuda_err("sage_scatter_bwd");
+}
+
+
+// ---- column-block variants used by the heterogeneous engine: A_t = [mean_rel1 | mean_rel2 | ... | self] ----
+static void sage_aggregate_block(RowTableHandle* feat, const c10::optional<Tensor>& nodes,
+                                 const c10::optional<Tensor>& src_local, int64_t d, const Tensor& counters,
+                                 int64_t n_hops_targets, const std::vector<Tensor>& ell,
+                                 const std::vector<int64_t>& ks, const Tensor& deg, Tensor out, int64_t mean_col) {
+  c10::cuda::CUDAGuard guard(out.device());
+  TORCH_CHECK(out.scalar_type() == torch::kBFloat16 && out.dim() == 2 && out.stride(1) == 1 &&
+              mean_col >= 0 && mean_col % 8 == 0 && mean_col + d <= out.size(1) && out.stride(0) % 8 == 0);
+  SageAggArgs a = make_agg(feat, nodes, src_local, d, counters, n_hops_targets, out.size(0), ell, ks,
+                           deg, out.data_ptr());
+  a.out_ld = static_cast<int>(out.stride(0));
+  a.mean_col = static_cast<int>(mean_col);
+  a.self_col = -1;
+  launch_sage_aggregate(a, cur_stream());
+  check_cuda_err("sage_aggregate_block");
+}
+
+static void sage_scatter_block(const Tensor& dA, int64_t d, int64_t mean_col, const Tensor& counters,
+                               int64_t n_hops_targets, const std::vector<Tensor>& ell,
+                               const std::vector<int64_t>& ks, const Tensor& deg, Tensor dH) {
+  c10::cuda::CUDAGuard guard(dA.device());
+  TORCH_CHECK(dA.scalar_type() == torch::kBFloat16 && dA.dim() == 2 && dA.stride(1) == 1 && dA.stride(0) % 8 == 0 &&
+              mean_col >= 0 && mean_col % 8 == 0 && mean_col + d <= dA.size(1));
+  TORCH_CHECK(dH.scalar_type() == torch::kFloat32 && dH.is_contiguous() && dH.size(1) == d);
+  SageScatterArgs a{};
+  a.dA = dA.data_ptr();
+  a.d = d;
+  a.cum = counters.data_ptr<int32_t>();
+  a.n_hops_targets = n_hops_targets;
+  a.cap_targets = dA.size(0);
+  fill_ell(ell, ks, a.ell, a.k);
+  a.deg = deg.data_ptr<int32_t>();
+  a.dH = dH.data_ptr<float>();
+  a.dA_ld = static_cast<int>(dA.stride(0));
+  a.mean_col = static_cast<int>(mean_col);
+  a.self_col = -1;
+  launch_sage_scatter_bwd(a, cur_stream());
+  check_cuda_err("sage_scatter_block");
+}
+
+static void add_block_f32(const Tensor& dA, int64_t col, int64_t d, const Tensor& counters, int64_t n_hops, Tensor dH) {
+  c10::cuda::CUDAGuard guard(dA.device());
+  TORCH_CHECK(dA.scalar_type() == torch::kBFloat16 && dA.dim() == 2 && dA.stride(1) == 1 && dA.stride(0) % 8 == 0 &&
+              col % 8 == 0 && col + d <= dA.size(1) && d % 8 == 0);
+  TORCH_CHECK(dH.scalar_type() == torch::kFloat32 && dH.is_contiguous() && dH.size(1) == d);
+  launch_add_block_f32(dA.data_ptr(), dA.stride(0), col, d, counters.data_ptr<int32_t>(), n_hops,
+                       std::min<int64_t>(dA.size(0), dH.size(0)), dH.data_ptr<float>(), cur_stream());
+  check_cuda_err("add_block_f32");
 }
 
 // EXPERIMENTAL atomics-free backward of the mean aggregation over the arena's transposed adjacency
@@ -1157,7 +1209,7 @@ struct PeerGroup {
                 "step_dev must be int32[2]: {steps taken, block ticket}");
     launch_adam_peer(p, param.data_ptr<float>(), m.data_ptr<float>(), v.data_ptr<float>(),
                      (p_bf16.has_value() && p_bf16->defined()) ? p_bf16->data_ptr() : nullptr, param.numel(), lr,
-                     b1, b2, eps, wd, step_dev.data_ptr<int32_t>(), gscale, cur_stream());
+                     b1, b2, eps, wd, step_dev.data_ptr<int32_t>(), gscale, cur_stream(), err.data_ptr<int32_t>());
     check_cuda_err("adam_peer");
   }
 };
@@ -1309,6 +1361,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   // ---- GraphSAGE engine ----
   m.def("sage_aggregate", &sage_aggregate);
   m.def("sage_scatter_bwd", &sage_scatter_bwd);
+  m.def("sage_aggregate_block", &sage_aggregate_block);
+  m.def("sage_scatter_block", &sage_scatter_block);
+  m.def("add_block_f32", &add_block_f32);
   m.def("relu_bwd_cast", &relu_bwd_cast);
   m.def("sage_gather_bwd", &sage_gather_bwd);
   m.def("bias_relu", &bias_relu);

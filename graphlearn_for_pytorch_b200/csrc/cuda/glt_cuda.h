@@ -98,7 +98,7 @@ void launch_relabel_hop(const HopArgs& a, cudaStream_t s);
 // device array of `n_rel` HopArgs (blockIdx.y selects the relation; relations with k <= 0 are skipped);
 // `max_k` / `max_rows` are the maxima over the relations (template / grid selection).
 void launch_sample_hop_grouped(const HopArgs* descs, int n_rel, int max_k, int max_rows, cudaStream_t s);
-void launch_relabel_hop_grouped(const HopArgs* descs, int n_rel, int max_rows, cudaStream_t s);
+void launch_relabel_hop_grouped(const HopArgs* descs, int n_rel, int max_k, int max_rows, cudaStream_t s);
 struct HeteroTypeState {
   int32_t* cum;       // [6] of this node type
   int32_t* cursor;
@@ -171,6 +171,11 @@ struct SageAggArgs {
   int k[4];
   const int32_t* deg;
   void* out;                    // bf16 [cap_targets, 2d] = [mean | self]
+  // column-block output (heterogeneous layers: A_t = [mean_rel1 | mean_rel2 | ... | self]); out_ld == 0 keeps
+  // the homogeneous layout above (out_ld = 2d, mean_col = 0, self_col = d)
+  int out_ld;                   // row pitch of `out` in elements
+  int mean_col;                 // first column of this relation's mean block
+  int self_col;                 // first column of the self block, -1 = do not write it
 };
 void launch_sage_aggregate(const SageAggArgs& a, cudaStream_t s);
 
@@ -184,8 +189,12 @@ struct SageScatterArgs {
   int k[4];
   const int32_t* deg;
   float* dH;                    // fp32 [cap_src, d], pre-zeroed
+  int dA_ld, mean_col, self_col;  // column-block input like SageAggArgs (dA_ld == 0: homogeneous [mean | self])
 };
 void launch_sage_scatter_bwd(const SageScatterArgs& a, cudaStream_t s);
+// dH[t, :] += dA[t, col : col + d] for t < cum[n_hops] (self block of a heterogeneous layer)
+void launch_add_block_f32(const void* dA, int dA_ld, int col, int d, const int32_t* cum, int n_hops, int cap,
+                          float* dH, cudaStream_t s);
 
 // ---- transpose.cu: per-batch transposed adjacency + atomics-free backward (EXPERIMENTAL) ----------
 // The forward ELL blocks are keyed by TARGET (row t lists its sampled sources).  The backward of the
@@ -259,7 +268,7 @@ struct PeerPtrs {
 void launch_peer_barrier(const PeerPtrs& p, int which, int32_t* epoch_dev, int32_t* err, cudaStream_t s);
 void launch_adam_peer(const PeerPtrs& p, float* param, float* m, float* v, void* p_bf16, int64_t n, float lr,
                       float b1, float b2, float eps, float wd, int32_t* step_dev, float gscale,
-                      cudaStream_t s);
+                      cudaStream_t s, const int32_t* err = nullptr);
 
 // ---- sage_tc.cu (tcgen05 fused gather+aggregate+GEMM) -------------------------
 struct SageFusedArgs {

@@ -58,7 +58,11 @@ __device__ __forceinline__ float4 ld_cv4(const float* p) {
 
 __global__ void __launch_bounds__(256) k_adam_peer(PeerPtrs p, float* param, float* m, float* v,
                                                    __nv_bfloat16* pb, int64_t n, float lr, float b1, float b2,
-                                                   float eps, float wd, int32_t* step_dev, float gscale) {
+                                                   float eps, float wd, int32_t* step_dev, float gscale,
+                                                   const int32_t* err) {
+  // a barrier of this step timed out (a peer died or stalled): the gradients are incomplete, so the update is
+  // skipped on every rank that saw the timeout; the host raises at its next health check (models/sage.py)
+  if (err && *reinterpret_cast<const volatile int32_t*>(err) != 0) return;
   // t = steps so far + 1; the last block to finish publishes it (see k_adam)
   const float t = static_cast<float>(*reinterpret_cast<volatile int32_t*>(step_dev) + 1);
   const float c1 = 1.f - __powf(b1, t), c2 = 1.f - __powf(b2, t);
@@ -110,12 +114,12 @@ void launch_peer_barrier(const PeerPtrs& p, int which, int32_t* epoch_dev, int32
 
 void launch_adam_peer(const PeerPtrs& p, float* param, float* m, float* v, void* p_bf16, int64_t n, float lr,
                       float b1, float b2, float eps, float wd, int32_t* step_dev, float gscale,
-                      cudaStream_t s) {
+                      cudaStream_t s, const int32_t* err) {
   int64_t blocks = ((n >> 2) + 255) / 256;
   if (blocks > 148 * 4) blocks = 148 * 4;
   if (blocks < 1) blocks = 1;
   k_adam_peer<<<static_cast<int>(blocks), 256, 0, s>>>(p, param, m, v, reinterpret_cast<__nv_bfloat16*>(p_bf16), n,
-                                                       lr, b1, b2, eps, wd, step_dev, gscale);
+                                                       lr, b1, b2, eps, wd, step_dev, gscale, err);
 }
 
 }  // namespace glt

@@ -103,15 +103,18 @@ __global__ void __launch_bounds__(256) k_sage_aggregate(SageAggArgs a) {
     }
     if (!valid) continue;
     const float inv = dg > 0 ? 1.f / static_cast<float>(dg) : 0.f;
-    uint8_t* o = reinterpret_cast<uint8_t*>(a.out) + static_cast<int64_t>(t) * a.d * 4;  // 2d bf16
-    const uint8_t* self = src_row(a, t);
+    const int ld = a.out_ld ? a.out_ld : 2 * a.d;
+    const int mcol = a.out_ld ? a.mean_col : 0;
+    const int scol = a.out_ld ? a.self_col : a.d;
+    uint8_t* o = reinterpret_cast<uint8_t*>(a.out) + static_cast<int64_t>(t) * ld * 2;
+    const uint8_t* self = scol >= 0 ? src_row(a, t) : nullptr;
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
       const int c = v * LPR + gl;
       if (c < nvec) {
-        reinterpret_cast<uint4*>(o)[c] = pack_bf16x8(acc[v], inv);
-        reinterpret_cast<uint4*>(o + a.d * 2)[c] =
-            self ? ld_nc_v4(self + c * 16) : make_uint4(0, 0, 0, 0);
+        reinterpret_cast<uint4*>(o + mcol * 2)[c] = pack_bf16x8(acc[v], inv);
+        if (scol >= 0)
+          reinterpret_cast<uint4*>(o + scol * 2)[c] = self ? ld_nc_v4(self + c * 16) : make_uint4(0, 0, 0, 0);
       }
     }
   }
@@ -138,7 +141,10 @@ __global__ void __launch_bounds__(256) k_sage_scatter_bwd(SageScatterArgs a) {
     const int dg = a.deg[t];
     const int k = a.k[l.hop];
     const int32_t* ell = a.ell[l.hop] + static_cast<int64_t>(l.row) * k;
-    const uint8_t* g = reinterpret_cast<const uint8_t*>(a.dA) + static_cast<int64_t>(t) * a.d * 4;
+    const int ld = a.dA_ld ? a.dA_ld : 2 * a.d;
+    const int mcol = a.dA_ld ? a.mean_col : 0;
+    const int scol = a.dA_ld ? a.self_col : a.d;
+    const uint8_t* g = reinterpret_cast<const uint8_t*>(a.dA) + static_cast<int64_t>(t) * ld * 2;
     const float inv = dg > 0 ? 1.f / static_cast<float>(dg) : 0.f;
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
@@ -147,11 +153,13 @@ __global__ void __launch_bounds__(256) k_sage_scatter_bwd(SageScatterArgs a) {
       float gn[8], gs[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) gn[i] = gs[i] = 0.f;
-      bf16x8_accum(reinterpret_cast<const uint4*>(g)[c], gn);
-      bf16x8_accum(reinterpret_cast<const uint4*>(g + a.d * 2)[c], gs);
+      bf16x8_accum(reinterpret_cast<const uint4*>(g + mcol * 2)[c], gn);
 #pragma unroll
       for (int i = 0; i < 8; ++i) gn[i] *= inv;
-      atomic_add8(a.dH + static_cast<int64_t>(t) * a.d + c * 8, gs);
+      if (scol >= 0) {
+        bf16x8_accum(reinterpret_cast<const uint4*>(g + scol * 2)[c], gs);
+        atomic_add8(a.dH + static_cast<int64_t>(t) * a.d + c * 8, gs);
+      }
       for (int j = 0; j < dg; ++j) {
         const int s = ell[j];
         if (s >= 0) atomic_add8(a.dH + static_cast<int64_t>(s) * a.d + c * 8, gn);
@@ -344,6 +352,26 @@ __global__ void __launch_bounds__(256) k_colsum(const __nv_bfloat16* X, const in
   }
 }
 
+__global__ void k_add_block_f32(const __nv_bfloat16* dA, int dA_ld, int col, int d, const int32_t* cum, int n_hops,
+                                int cap, float* dH) {
+  const int T = min(cum[n_hops], cap);
+  const int nvec = d >> 3;
+  const int64_t n = static_cast<int64_t>(T) * nvec;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int t = static_cast<int>(i / nvec), c = static_cast<int>(i % nvec);
+    float g[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) g[q] = 0.f;
+    bf16x8_accum(*reinterpret_cast<const uint4*>(dA + static_cast<int64_t>(t) * dA_ld + col + c * 8), g);
+    float4* o = reinterpret_cast<float4*>(dH + static_cast<int64_t>(t) * d + c * 8);
+    float4 a0 = o[0], a1 = o[1];
+    a0.x += g[0]; a0.y += g[1]; a0.z += g[2]; a0.w += g[3];
+    a1.x += g[4]; a1.y += g[5]; a1.z += g[6]; a1.w += g[7];
+    o[0] = a0; o[1] = a1;
+  }
+}
+
 __global__ void k_zero_rows(float* p, const int32_t* cum, int n_hops, int cap, int d) {
   const int T = min(cum[n_hops], cap);
   const int64_t n4 = static_cast<int64_t>(T) * d / 4;
@@ -439,6 +467,12 @@ void launch_colsum_bf16(const void* X, const int32_t* cum, int n_hops, int cap, 
   const int rpb = 256 / groups > 0 ? 256 / groups : 1;
   k_colsum<<<grid_for(cap, rpb * 8, 148 * 2), 256, sizeof(float) * rpb * d, s>>>(
       reinterpret_cast<const __nv_bfloat16*>(X), cum, n_hops, cap, d, out);
+}
+
+void launch_add_block_f32(const void* dA, int dA_ld, int col, int d, const int32_t* cum, int n_hops, int cap,
+                          float* dH, cudaStream_t s) {
+  k_add_block_f32<<<grid_for(static_cast<int64_t>(cap) * d / 8, 256), 256, 0, s>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dA), dA_ld, col, d, cum, n_hops, cap, dH);
 }
 
 void launch_zero_rows(float* p, const int32_t* cum, int n_hops, int cap, int d, cudaStream_t s) {

@@ -184,6 +184,12 @@ __global__ void __launch_bounds__(256) k_sample_hop_grouped(const HopArgs* descs
   sample_hop_body<G, MAXC>(a);
 }
 
+// G lanes per frontier row (the same group width as the sampling kernel): slot -> local id for the row's
+// entries in parallel, and rows that lost a neighbour (arena / table overflow) are compacted in place with a
+// ballot + prefix count, deg[] and the hop's edge counter corrected, so the mean divides by the neighbours that
+// exist and to_coo never emits -1.  (A thread-per-row version of this pass cost 18 us on a 1024-row frontier: 15
+// serial table reads per thread on four CTAs.)
+template <int G>
 __device__ __forceinline__ void relabel_hop_body(const HopArgs& a) {
   const int f_begin = a.c.cum[a.hop];
   const int n_rows = min(a.c.cum[a.hop + 1] - f_begin, a.cap_rows);
@@ -193,31 +199,41 @@ __device__ __forceinline__ void relabel_hop_body(const HopArgs& a) {
   // Every thread derives the same bound from stable inputs; the cursor reset is idempotent.
   const int bound = a.bound_ptr ? *a.bound_ptr
                                 : min(min(*a.c.cursor, a.cap_nodes), a.c.cum[a.hop + 1] + a.cap_rows_next);
-  // One thread per frontier row (k <= fan-out entries, contiguous): slot -> local id, and rows that
-  // lost a neighbour (arena / table overflow) are compacted in place with deg[] and the hop's edge
-  // counter corrected, so the mean divides by the neighbours that exist and to_coo never emits -1.
+  constexpr int RPW = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % G, gw = lane / G;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (gw * G));
+  const int warps_per_block = blockDim.x >> 5;
   int dropped = 0;
-  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += gridDim.x * blockDim.x) {
-    int32_t* row = a.ell + static_cast<int64_t>(r) * a.k;
-    int64_t* erow = a.ell_eids ? a.ell_eids + static_cast<int64_t>(r) * a.k : nullptr;
-    const int dg = min(a.deg[f_begin + r], a.k);
-    int w = 0;
-    for (int j = 0; j < dg; ++j) {
-      const int32_t s = row[j];
+  for (int base = (blockIdx.x * warps_per_block + (threadIdx.x >> 5)) * RPW; base < n_rows;
+       base += gridDim.x * warps_per_block * RPW) {
+    const int r = base + gw;
+    const bool valid_row = r < n_rows;
+    int32_t* row = a.ell + static_cast<int64_t>(valid_row ? r : 0) * a.k;
+    int64_t* erow = a.ell_eids ? a.ell_eids + static_cast<int64_t>(valid_row ? r : 0) * a.k : nullptr;
+    const int dg = valid_row ? min(a.deg[f_begin + r], a.k) : 0;
+    int w = 0;                                   // compacted entries written so far (uniform inside the group)
+    for (int j0 = 0; j0 < a.k; j0 += G) {        // uniform trip count across the warp
+      const int j = j0 + gl;
       int32_t v = -1;
-      if (s >= 0) {
-        v = a.t.vals[s];
-        if (v >= bound) { a.t.vals[s] = -1; v = -1; }
+      int64_t e = -1;
+      if (j < dg) {
+        const int32_t s = row[j];
+        if (s >= 0) {
+          v = a.t.vals[s];
+          if (v >= bound) { a.t.vals[s] = -1; v = -1; }
+        }
+        if (erow) e = erow[j];
       }
-      if (v >= 0) {
-        if (w != j) { row[w] = v; if (erow) erow[w] = erow[j]; } else row[j] = v;
-        ++w;
-      }
+      const unsigned m = (__ballot_sync(0xffffffffu, v >= 0) & gmask) >> (gw * G);
+      const int pos = w + __popc(m & ((1u << gl) - 1u));
+      __syncwarp();                              // every lane has read its entry before anyone overwrites the row
+      if (v >= 0) { row[pos] = v; if (erow) erow[pos] = e; }
+      w += __popc(m);
     }
-    if (w < dg) {
-      for (int j = w; j < dg; ++j) { row[j] = -1; if (erow) erow[j] = -1; }
-      a.deg[f_begin + r] = w;
-      dropped += dg - w;
+    if (w < dg) {                                // holes: blank the tail, fix the degree
+      for (int j = w + gl; j < dg; j += G) { row[j] = -1; if (erow) erow[j] = -1; }
+      if (gl == 0) { a.deg[f_begin + r] = w; dropped += dg - w; }
     }
   }
   if (dropped) {
@@ -230,12 +246,14 @@ __device__ __forceinline__ void relabel_hop_body(const HopArgs& a) {
   }
 }
 
-__global__ void k_relabel_hop(HopArgs a) { relabel_hop_body(a); }
+template <int G>
+__global__ void __launch_bounds__(256) k_relabel_hop(HopArgs a) { relabel_hop_body<G>(a); }
 
-__global__ void k_relabel_hop_grouped(const HopArgs* descs) {
+template <int G>
+__global__ void __launch_bounds__(256) k_relabel_hop_grouped(const HopArgs* descs) {
   const HopArgs& a = descs[blockIdx.y];
   if (a.k <= 0) return;
-  relabel_hop_body(a);
+  relabel_hop_body<G>(a);
 }
 
 __global__ void k_hetero_finalize(const HeteroTypeState* types, int n_types, int hop) {
@@ -468,8 +486,18 @@ void launch_sample_hop(const HopArgs& a, cudaStream_t s) {
   });
 }
 
+#define GLT_DISPATCH_GROUP(K, ...)                        \
+  do {                                                   \
+    if ((K) <= 8) { constexpr int G = 8; __VA_ARGS__; }  \
+    else if ((K) <= 16) { constexpr int G = 16; __VA_ARGS__; } \
+    else { constexpr int G = 32; __VA_ARGS__; }          \
+  } while (0)
+
 void launch_relabel_hop(const HopArgs& a, cudaStream_t s) {
-  k_relabel_hop<<<grid_for(a.cap_rows, 256), 256, 0, s>>>(a);
+  GLT_DISPATCH_GROUP(a.k, {
+    const int rows_per_block = (256 / 32) * (32 / G);
+    k_relabel_hop<G><<<grid_for(a.cap_rows, rows_per_block), 256, 0, s>>>(a);
+  });
 }
 
 void launch_sample_hop_grouped(const HopArgs* descs, int n_rel, int max_k, int max_rows, cudaStream_t s) {
@@ -481,10 +509,13 @@ void launch_sample_hop_grouped(const HopArgs* descs, int n_rel, int max_k, int m
   });
 }
 
-void launch_relabel_hop_grouped(const HopArgs* descs, int n_rel, int max_rows, cudaStream_t s) {
-  if (n_rel <= 0) return;
-  dim3 grid(grid_for(max_rows, 256, 148 * 8), n_rel);
-  k_relabel_hop_grouped<<<grid, 256, 0, s>>>(descs);
+void launch_relabel_hop_grouped(const HopArgs* descs, int n_rel, int max_k, int max_rows, cudaStream_t s) {
+  if (n_rel <= 0 || max_k <= 0) return;
+  GLT_DISPATCH_GROUP(max_k, {
+    const int rows_per_block = (256 / 32) * (32 / G);
+    dim3 grid(grid_for(max_rows, rows_per_block, 148 * 8), n_rel);
+    k_relabel_hop_grouped<G><<<grid, 256, 0, s>>>(descs);
+  });
 }
 
 void launch_hetero_finalize(const HeteroTypeState* types, int n_types, int hop, cudaStream_t s) {

@@ -107,13 +107,14 @@ class GraphSageEngine(object):
                device: Optional[torch.device] = None, group=None, use_fused: bool = True,
                use_cuda_graph: bool = True, calibration_seeds: Optional[torch.Tensor] = None,
                calibration_margin: float = 1.3, calibration_batches: int = 16, pipeline: bool = False,
-               use_peer_allreduce: bool = True, use_gather_bwd: Optional[bool] = None):
+               use_peer_allreduce: bool = True, use_gather_bwd: Optional[bool] = None,
+               check_every: int = 64, auto_regrow: bool = True):
     self.nat = require_native()
     self.pipeline = bool(pipeline)
     self.use_peer_allreduce = bool(use_peer_allreduce)
-    # EXPERIMENTAL (csrc/cuda/transpose.cu): the sampler also builds the transposed adjacency of the batch and
-    # the backward of the aggregation becomes an atomics-free gather (replaces zero_rows + scatter + relu_bwd_cast).
-    # Off by default until it has been validated on hardware; GLT_B200_GATHER_BWD=1 turns it on globally.
+    # use_gather_bwd (csrc/cuda/transpose.cu, validated on B200 in round 2): the sampler also builds the transposed
+    # adjacency of the batch and the backward of the aggregation becomes an atomics-free gather (replaces zero_rows +
+    # fp32-atomic scatter + relu_bwd_cast).  None = the measured default (GLT_B200_GATHER_BWD overrides).
     if use_gather_bwd is None:
       import os as _os
       use_gather_bwd = _os.environ.get('GLT_B200_GATHER_BWD', '0') == '1'
@@ -148,56 +149,133 @@ class GraphSageEngine(object):
     self.kernels_per_step = 0
 
     dev = self.device
+    self._num_nodes = int(num_nodes)
+    # ---- health monitoring (peer-barrier timeouts, arena overflow) without stalling the step: every
+    # `check_every` steps a tiny probe is copied to pinned memory and read one period later
+    self.check_every = int(check_every)
+    self.auto_regrow = bool(auto_regrow)
+    self.regrow_count = 0
+    self._overflow_seen = 0
+    self._probe_event = None
     with torch.cuda.device(dev):
       cap_override = []
       if calibration_seeds is not None and calibration_seeds.numel() >= self.bs:
         cap_override = self._calibrate(calibration_seeds, int(num_nodes), calibration_margin, calibration_batches)
-      # pipelined mode double-buffers the sampler state: batch i+1 is sampled on a side stream
-      # while batch i trains (the reference's sampler<->trainer producer/consumer pipeline,
-      # distributed/dist_sampling_producer.py:54-163, collapsed onto CUDA streams of one GPU)
-      n_arenas = 2 if self.pipeline else 1
-      self._arenas = [self.nat.SamplerArena(dev.index, self.bs, self.fanouts, False, int(num_nodes), cap_override)
-                      for _ in range(n_arenas)]
-      self._cur = 0
-      for p_, ar_ in enumerate(self._arenas):
-        ar_.step.fill_(p_ - n_arenas)          # disjoint Philox stream ids per arena
-        if self.use_gather_bwd and self.L >= 2:
-          ar_.enable_transpose(self.L - 1)     # layer 2 uses hops 0..L-2, deeper layers a prefix of them
       self.calibrated = bool(cap_override)
-      self.cap_rows = list(self.arena.cap_rows)           # frontier capacity per hop (+ last-hop additions)
-      # layer l (1-based) targets = nodes of hops 0..L-l
-      self.cap_T = [0] + [int(sum(self.cap_rows[:self.L - l + 1])) for l in range(1, self.L + 1)]
-      self.cap_T = [min(c, self.arena.cap_nodes) for c in self.cap_T]
       self.dims_in = [self.in_dim] + [self.hidden] * (self.L - 1)
       self.dims_out = [self.hidden] * (self.L - 1) + [self.n_out_pad]
+      self._build_buffers(cap_override)
       self._init_params()
-      bf, f32 = torch.bfloat16, torch.float32
-      self.A = [None] + [torch.zeros(self.cap_T[l], 2 * self.dims_in[l - 1], dtype=bf, device=dev)
-                         for l in range(1, self.L + 1)]
-      self.Z = [None] + [torch.zeros(self.cap_T[l], self.dims_out[l - 1], dtype=bf, device=dev)
-                         for l in range(1, self.L + 1)]
-      self.dPre = [None] + [torch.zeros(self.cap_T[l], self.dims_out[l - 1], dtype=bf, device=dev)
-                            for l in range(1, self.L + 1)]
-      self.dA = [None, None] + [torch.zeros(self.cap_T[l], 2 * self.dims_in[l - 1], dtype=bf, device=dev)
-                                for l in range(2, self.L + 1)]
-      self.dH = [None] + [torch.zeros(self.cap_T[l], self.dims_out[l - 1], dtype=f32, device=dev)
-                          for l in range(1, self.L)]
+      n_arenas = len(self._arenas)
       self._seeds = [torch.zeros(self.bs, dtype=torch.int64, device=dev) for _ in range(n_arenas)]
       self._side = torch.cuda.Stream(device=dev) if self.pipeline else None
       self._primed = False
-      self.loss = torch.zeros(1, dtype=f32, device=dev)
+      self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
       self.correct = torch.zeros(1, dtype=torch.int32, device=dev)
       self.step_dev = torch.zeros(2, dtype=torch.int32, device=dev)   # {steps taken, block ticket}
+      self._health_dev = torch.zeros(2, dtype=torch.int32, device=dev)
+      self._health_host = torch.zeros(2, dtype=torch.int32).pin_memory()
       self._autotune_fused = (use_fused == 'auto')
       self.fused_ok = [False] + [bool(use_fused and self.nat.sage_fused_supported(self.dims_in[l - 1],
                                                                                     self.dims_out[l - 1]))
                                  for l in range(1, self.L + 1)]
+      bf = torch.bfloat16
       self.w_packed = [None] + [torch.zeros(self.dims_out[l - 1] * 2 * self.dims_in[l - 1], dtype=bf, device=dev)
                                 if self.fused_ok[l] else None for l in range(1, self.L + 1)]
       self._repack()
     self._graph_fb = None
     self._graph_opt = None
     self._graph_full = None
+
+  def _build_buffers(self, cap_override):
+    """(Re)creates everything whose size depends on the arena capacities: sampler arenas, activation /
+    gradient buffers, cached GEMM launches.  Parameters and optimizer state are untouched."""
+    dev = self.device
+    bf, f32 = torch.bfloat16, torch.float32
+    # pipelined mode double-buffers the sampler state: batch i+1 is sampled on a side stream
+    # while batch i trains (the reference's sampler<->trainer producer/consumer pipeline,
+    # distributed/dist_sampling_producer.py:54-163, collapsed onto CUDA streams of one GPU)
+    n_arenas = 2 if self.pipeline else 1
+    self._arenas = [self.nat.SamplerArena(dev.index, self.bs, self.fanouts, False, self._num_nodes,
+                                          list(cap_override) if cap_override else [])
+                    for _ in range(n_arenas)]
+    self._cur = 0
+    for p_, ar_ in enumerate(self._arenas):
+      ar_.step.fill_(p_ - n_arenas)          # disjoint Philox stream ids per arena
+      if self.use_gather_bwd and self.L >= 2:
+        ar_.enable_transpose(self.L - 1)     # layer 2 uses hops 0..L-2, deeper layers a prefix of them
+    self.cap_rows = list(self.arena.cap_rows)           # frontier capacity per hop (+ last-hop additions)
+    # layer l (1-based) targets = nodes of hops 0..L-l
+    self.cap_T = [0] + [int(sum(self.cap_rows[:self.L - l + 1])) for l in range(1, self.L + 1)]
+    self.cap_T = [min(c, self.arena.cap_nodes) for c in self.cap_T]
+    self.A = [None] + [torch.zeros(self.cap_T[l], 2 * self.dims_in[l - 1], dtype=bf, device=dev)
+                       for l in range(1, self.L + 1)]
+    self.Z = [None] + [torch.zeros(self.cap_T[l], self.dims_out[l - 1], dtype=bf, device=dev)
+                       for l in range(1, self.L + 1)]
+    self.dPre = [None] + [torch.zeros(self.cap_T[l], self.dims_out[l - 1], dtype=bf, device=dev)
+                          for l in range(1, self.L + 1)]
+    self.dA = [None, None] + [torch.zeros(self.cap_T[l], 2 * self.dims_in[l - 1], dtype=bf, device=dev)
+                              for l in range(2, self.L + 1)]
+    self.dH = [None] + [torch.zeros(self.cap_T[l], self.dims_out[l - 1], dtype=f32, device=dev)
+                        for l in range(1, self.L)]
+    self._tc_plans = {}
+    self._graphs = []
+    self._graph_fb = self._graph_opt = self._graph_full = None
+
+  def regrow(self, factor: float = 1.5):
+    """Enlarge the (calibrated) arena after neighbours were dropped by the capacity guard: new per-hop
+    capacities = old x factor (bounded by the worst case), buffers and CUDA graphs are rebuilt, parameters,
+    optimizer state and the sampling position are kept.  Collective when world > 1 (every rank calls it at the
+    same step -- `_health_tick` guarantees that)."""
+    with torch.cuda.device(self.device):
+      torch.cuda.synchronize()
+      steps = [int(a.step.item()) for a in self._arenas]
+      tmp = self.nat.SamplerArena(self.device.index, self.bs, self.fanouts, False, self._num_nodes)
+      worst = list(tmp.cap_rows)
+      del tmp
+      caps = [self.bs] + [min(worst[h], (int(self.cap_rows[h] * factor) + 255) // 128 * 128)
+                          for h in range(1, self.L + 1)]
+      had_graphs = bool(getattr(self, '_graphs', None))
+      self._build_buffers(caps)
+      for a, v in zip(self._arenas, steps):
+        a.step.fill_(v)
+      self._primed = False
+      self.regrow_count += 1
+      if had_graphs:
+        self.warmup_and_capture(n_eager=1)
+
+  def _health_tick(self):
+    """Called once per train_step.  Every `check_every` steps: (1) read the probe enqueued one period ago --
+    raise if a peer barrier timed out (the Adam kernels already skipped that update), regrow the arena if
+    neighbours were dropped; (2) enqueue a new probe (max-reduced over ranks so that every rank takes the same
+    decision at the same step)."""
+    if self.check_every <= 0 or self.step_idx % self.check_every != 0:
+      return
+    if self._probe_event is not None:
+      self._probe_event.synchronize()
+      err, ovf = int(self._health_host[0]), int(self._health_host[1])
+      self._probe_event = None
+      if err != 0:
+        raise RuntimeError(f'peer barrier timed out waiting for rank {err - 1}: a peer process died or stalled; '
+                           'the optimizer updates since then were skipped')
+      if ovf > self._overflow_seen:
+        self._overflow_seen = ovf
+        if self.auto_regrow:
+          self.regrow()
+    h = self._health_dev
+    h.zero_()
+    for pg in self._peer_groups:
+      torch.maximum(h[0:1], pg.err, out=h[0:1])
+    for a in self._arenas:
+      h[1:2].add_(a.counters[12:13])
+    if self.regrow_count:
+      h[1:2].add_(self._overflow_seen)      # counters restart from zero in a rebuilt arena
+    if self.world > 1:
+      import torch.distributed as dist
+      dist.all_reduce(h, op=dist.ReduceOp.MAX, group=self.group)
+    self._health_host.copy_(h, non_blocking=True)
+    self._probe_event = torch.cuda.Event()
+    self._probe_event.record()
 
   @property
   def arena(self):
@@ -641,6 +719,7 @@ class GraphSageEngine(object):
     Pipelined engines run *sample(this batch) || train(previous batch)*: the first call only
     samples (returns None), later calls return the loss of the batch passed one call earlier;
     `flush()` trains the last pending batch."""
+    self._health_tick()
     if not self.pipeline:
       with nvtx_range('glt.engine.step'):
         self._stage_seeds(self._seeds[0], seeds)
@@ -652,7 +731,7 @@ class GraphSageEngine(object):
       self._stage_seeds(self._seeds[0], seeds)
       self._sample(0)
       self._primed = True
-      return None
+      return None if self.step_idx == 0 and self.regrow_count == 0 else self.loss
     cur = self._cur
     with nvtx_range('glt.engine.step(sample b+1 || train b)'):
       self._stage_seeds(self._seeds[1 - cur], seeds)
