@@ -53,3 +53,33 @@ def synthetic_igbh(num_papers=20_000, num_authors=10_000, num_insts=500, num_fos
   w = torch.randn(feat_dim, num_classes, generator=g)
   labels = {'paper': (feats['paper'] @ w).argmax(1)}
   return edges, feats, labels, sizes
+
+
+def synthetic_mag(num_papers=30_000, num_authors=20_000, num_insts=500, num_fields=300, feat_dim=128,
+                  num_classes=20, seed=0):
+  """OGB-MAG-shaped heterogeneous graph (paper / author / institution / field_of_study with cites, writes,
+  affiliated_with, has_topic, made undirected like T.ToUndirected(merge=True) does in the reference example
+  examples/hetero/train_hgt_mag.py:86-91).  Every node type gets dense features (the reference fills the
+  feature-less types with metapath2vec embeddings)."""
+  g = torch.Generator().manual_seed(seed)
+
+  def rnd(n_src, n_dst, n_e):
+    return torch.stack([torch.randint(0, n_src, (n_e,), generator=g), torch.randint(0, n_dst, (n_e,), generator=g)])
+  cites = rnd(num_papers, num_papers, num_papers * 6)
+  writes = rnd(num_authors, num_papers, num_papers * 3)
+  affil = rnd(num_authors, num_insts, num_authors)
+  topic = rnd(num_papers, num_fields, num_papers * 4)
+  edges = {
+    ('paper', 'cites', 'paper'): torch.cat([cites, cites.flip(0)], 1),
+    ('author', 'writes', 'paper'): writes,
+    ('paper', 'rev_writes', 'author'): writes.flip(0),
+    ('author', 'affiliated_with', 'institution'): affil,
+    ('institution', 'rev_affiliated_with', 'author'): affil.flip(0),
+    ('paper', 'has_topic', 'field_of_study'): topic,
+    ('field_of_study', 'rev_has_topic', 'paper'): topic.flip(0),
+  }
+  sizes = {'paper': num_papers, 'author': num_authors, 'institution': num_insts, 'field_of_study': num_fields}
+  feats = {t: torch.randn(n, feat_dim, generator=g) for t, n in sizes.items()}
+  w = torch.randn(feat_dim, num_classes, generator=g)
+  labels = {'paper': (feats['paper'] @ w).argmax(1)}
+  return edges, feats, labels, sizes

@@ -162,7 +162,7 @@ inline int grid_for(int64_t items, int per_block, int max_blocks = 148 * 16) {
 
 // ------------------------------------------------------------------------------------------
 template <int LPR, int VPL>
-__global__ void __launch_bounds__(256, 3) k_sage_gather_bwd(SageGatherBwdArgs a) {
+__global__ void __launch_bounds__(256, 2) k_sage_gather_bwd(SageGatherBwdArgs a) {
   extern __shared__ float s_col[];  // [d] block partial of the bias gradient
   constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31;
@@ -176,6 +176,13 @@ __global__ void __launch_bounds__(256, 3) k_sage_gather_bwd(SageGatherBwdArgs a)
   if (a.colsum)
     for (int c = threadIdx.x; c < a.d; c += blockDim.x) s_col[c] = 0.f;
   __syncthreads();
+  // per-thread running column sums of the bias gradient (a shared-memory-atomic-per-row variant was measured at
+  // 2.4x the kernel time: every row of a CTA hits the same d addresses)
+  float csum[VPL][8];
+#pragma unroll
+  for (int v = 0; v < VPL; ++v)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) csum[v][i] = 0.f;
   const uint8_t* dA = reinterpret_cast<const uint8_t*>(a.dA);
   const int64_t a_row = static_cast<int64_t>(a.d) * 4;  // bytes of one [mean | self] row
   for (int base = (blockIdx.x * wpb + (threadIdx.x >> 5)) * RPW; base < a.cap_src; base += gridDim.x * wpb * RPW) {
@@ -248,19 +255,26 @@ __global__ void __launch_bounds__(256, 3) k_sage_gather_bwd(SageGatherBwdArgs a)
       }
       const uint4 packed = pack_bf16x8(acc[v], 1.f);
       reinterpret_cast<uint4*>(o)[c] = packed;
-      if (a.colsum) {  // bias gradient: sum exactly what the GEMMs will see (bf16-rounded); shared-memory
-                       // atomics per row instead of per-thread running sums (32 registers -> one more CTA per SM)
+      if (a.colsum) {  // sum exactly what the GEMMs will see (bf16-rounded)
         float r[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) r[i] = 0.f;
         bf16x8_accum(packed, r);
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (r[i] != 0.f) atomicAdd(s_col + c * 8 + i, r[i]);
+        for (int i = 0; i < 8; ++i) csum[v][i] += r[i];
       }
     }
   }
   if (a.colsum) {
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const int c = v * LPR + gl;
+      if (c < nvec) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (csum[v][i] != 0.f) atomicAdd(s_col + c * 8 + i, csum[v][i]);
+      }
+    }
     __syncthreads();
     for (int c = threadIdx.x; c < a.d; c += blockDim.x)
       if (s_col[c] != 0.f) atomicAdd(a.colsum + c, s_col[c]);

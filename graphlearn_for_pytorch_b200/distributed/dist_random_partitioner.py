@@ -99,15 +99,38 @@ class DistRandomPartitioner(object):
 
   # ---- helpers
   def _ship(self, key: str, owners: torch.Tensor, tensors: Dict[str, torch.Tensor]):
-    """Send rows of `tensors` to their owner ranks; returns what this rank ends up with."""
+    """Send rows of `tensors` to their owner ranks; returns what this rank ends up with.
+
+    The slice is walked in chunks of `chunk_size` rows (reference python/distributed/dist_random_partitioner.py:
+    257-290, `_partition_by_chunk`): every chunk is bucketed by owner and shipped as one RPC per destination, with
+    at most `max_inflight` requests outstanding, so the peak extra memory is O(chunk_size) per destination instead
+    of a second copy of the whole slice (IGBH-scale inputs do not fit twice) and a slow receiver back-pressures
+    the sender instead of queueing everything."""
+    n = owners.numel()
+    chunk = max(int(self.chunk_size), 1)
+    max_inflight = max(2 * self.num_parts, 8)
     futs = []
-    for p in range(self.num_parts):
-      m = owners == p
-      piece = {k: v[m] for k, v in tensors.items()}
-      if p == self.rank:
-        self._mgr.add(key, piece)
-      else:
-        futs.append(rpc_request_async(self._workers[p], self._callee_id, args=(key, piece)))
+    for b in range(0, max(n, 1), chunk):
+      own = owners[b:b + chunk]
+      if own.numel() == 0:
+        break
+      # one stable sort per chunk instead of num_parts boolean masks
+      order = torch.argsort(own, stable=True)
+      counts = torch.bincount(own, minlength=self.num_parts).tolist()
+      sorted_chunk = {k: v[b:b + chunk][order] for k, v in tensors.items()}
+      off = 0
+      for p_ in range(self.num_parts):
+        c = counts[p_]
+        if c == 0:
+          continue
+        piece = {k: v[off:off + c].clone() for k, v in sorted_chunk.items()}
+        off += c
+        if p_ == self.rank:
+          self._mgr.add(key, piece)
+        else:
+          futs.append(rpc_request_async(self._workers[p_], self._callee_id, args=(key, piece)))
+          if len(futs) >= max_inflight:
+            futs.pop(0).wait()
     for f in futs:
       f.wait()
     barrier()

@@ -183,7 +183,7 @@ def _w_dist_partitioner(rank, world, port, out):
   nsl = slice(rank * N // 2, (rank + 1) * N // 2)
   d.DistRandomPartitioner(out, N, ei[:, sl], torch.arange(ei.shape[1])[sl], id_features(N, 4)[nsl],
                           torch.arange(N)[nsl], id_features(ei.shape[1], 2)[sl],
-                          torch.arange(ei.shape[1])[sl]).partition()
+                          torch.arange(ei.shape[1])[sl], chunk_size=7).partition()   # many small chunks per slice
   d.barrier()
   d.shutdown_rpc()
 
