@@ -80,6 +80,8 @@ def parse_args(argv=None):
   p.add_argument('--no-arms', action='store_true', help='skip the secondary pairings')
   p.add_argument('--min-time', type=float, default=1.0,
                  help='repeat the K-step timed region on fresh batches until this many seconds are measured')
+  p.add_argument('--feat-format', default='bf16', choices=['bf16', 'mxfp8'],
+                 help='ours/engine: feature storage (mxfp8 = e4m3 + UE8M0/32 block scales, de-quantised in the fused kernel)')
   p.add_argument('--no-fused', action='store_true')
   p.add_argument('--fused', default='auto', choices=['auto', 'on'],
                  help="'auto': time fused vs unfused layer 1 at warm-up and keep the faster")
@@ -277,7 +279,9 @@ def build_ours(args, rank, world, device, need_engine=True):
     for b0 in range(0, N, rows):      # chunked: no fp32 copy of the whole table
       b1 = min(N, b0 + rows)
       feats[b0:b1, :args.feat_dim] = torch.randn(b1 - b0, args.feat_dim, device=device, generator=g).to(torch.bfloat16)
-    ut = glt.data.UnifiedTensor(device.index, torch.bfloat16)
+    if args.feat_format == 'mxfp8':
+      feats = torch.cat([glt.data.quantize_mxfp8(feats[b0:min(N, b0 + rows)]) for b0 in range(0, N, rows)])
+    ut = glt.data.UnifiedTensor(device.index, feats.dtype)
     ut.append_shared_tensor(feats)
     table = ut._table()
     keep = (graph, ut, feats, shard)
@@ -292,6 +296,8 @@ def build_ours(args, rank, world, device, need_engine=True):
     for b0 in range(0, e - b, rows):
       b1 = min(e - b, b0 + rows)
       local[b0:b1, :args.feat_dim] = torch.randn(b1 - b0, args.feat_dim, device=device, generator=gl).to(torch.bfloat16)
+    if args.feat_format == 'mxfp8':
+      local = torch.cat([glt.data.quantize_mxfp8(local[b0:min(e - b, b0 + rows)]) for b0 in range(0, e - b, rows)])
     pf = PartitionedFeature(local, bounds, device,
                             hot_per_rank=int(args.hot_fraction * (bounds[1] - bounds[0])))
     table = pf.table
@@ -309,7 +315,7 @@ def build_ours(args, rank, world, device, need_engine=True):
                         use_fused=False if args.no_fused else (True if args.fused == 'on' else 'auto'),
                         use_cuda_graph=not args.no_graph,
                         calibration_seeds=None if args.no_calibrate else pool,
-                        pipeline=not args.no_pipeline)
+                        pipeline=not args.no_pipeline, feature_format=args.feat_format)
   eng._keep = keep
   return eng, pool
 
@@ -519,6 +525,7 @@ def run_ours(args):
         'layer1_autotune_ms': getattr(eng, 'autotune_ms', {}).get(1),
         'tcgen05_gemm_layers': getattr(eng, 'tc_gemm', None),
         'gather_backward': bool(eng.use_gather_bwd),
+        'feature_format': args.feat_format,
         'hot_feature_replica': (None if world == 1 else {'fraction': args.hot_fraction,
                                                          'fill': getattr(eng._keep[1], 'fill_mode', None)}),
         'grad_allreduce': 'peer-HBM all-reduce fused into Adam (NVLink, in-graph)' if eng.peer_group is not None

@@ -716,6 +716,18 @@ struct RowTableHandle {
     return out;
   }
 
+  // rows are MXFP8 (d e4m3 bytes + d/32 UE8M0 scales + padding to 16 bytes): dequantised bf16 [n, d]
+  Tensor gather_mxfp8(const Tensor& idx, int64_t d) {
+    c10::cuda::CUDAGuard guard(device);
+    TORCH_CHECK(dtype == torch::kUInt8 && d % 128 == 0 && width >= d + d / 32 && width % 16 == 0,
+                "gather_mxfp8: table must hold uint8 rows of d + d/32 (+pad) bytes, d a multiple of 128");
+    TORCH_CHECK(idx.is_cuda() && idx.scalar_type() == torch::kInt64 && idx.is_contiguous());
+    Tensor out = torch::empty({idx.numel(), d}, torch::TensorOptions().dtype(torch::kBFloat16).device(torch::kCUDA, device));
+    launch_gather_mxfp8(tbl, idx.data_ptr<int64_t>(), idx.numel(), d, out.data_ptr(), cur_stream());
+    check_cuda_err("gather_mxfp8");
+    return out;
+  }
+
   // static-shape gather into a caller-provided buffer with a device-side count
   void gather_into(const Tensor& idx, const c10::optional<Tensor>& id2index,
                    const c10::optional<Tensor>& n_dev, Tensor out) {
@@ -750,8 +762,10 @@ static SageAggArgs make_agg(RowTableHandle* feat, const c10::optional<Tensor>& n
     a.src_local = src_local->data_ptr();
   } else {
     TORCH_CHECK(feat != nullptr && nodes.has_value(), "layer-1 aggregation needs a feature table + nodes");
-    TORCH_CHECK(feat->dtype == torch::kBFloat16, "engine features must be bf16");
-    TORCH_CHECK(feat->width == d, "feature width mismatch");
+    TORCH_CHECK(feat->dtype == torch::kBFloat16 || feat->dtype == torch::kUInt8,
+                "engine features must be bf16 rows or MXFP8 (uint8) rows");
+    TORCH_CHECK(feat->dtype == torch::kBFloat16 ? feat->width == d : feat->width == d + 16,
+                "feature width mismatch (MXFP8 rows are d + 16 bytes)");
     a.feat = feat->tbl;
     a.nodes = nodes->data_ptr<int64_t>();
   }
@@ -772,6 +786,8 @@ static void sage_aggregate(RowTableHandle* feat, const c10::optional<Tensor>& no
                            const std::vector<int64_t>& ks, const Tensor& deg, Tensor out) {
   c10::cuda::CUDAGuard guard(out.device());
   TORCH_CHECK(out.scalar_type() == torch::kBFloat16 && out.is_contiguous() && out.size(1) == 2 * d);
+  TORCH_CHECK(feat == nullptr || (src_local.has_value() && src_local->defined()) || feat->dtype == torch::kBFloat16,
+              "the unfused aggregation kernel reads bf16 rows; MXFP8 tables go through sage_fused");
   SageAggArgs a = make_agg(feat, nodes, src_local, d, counters, n_hops_targets, out.size(0), ell, ks,
                            deg, out.data_ptr());
   launch_sage_aggregate(a, cur_stream());
@@ -883,7 +899,7 @@ static void sage_gather_bwd(const Tensor& dA, int64_t d, SamplerArena& ar, int64
 }
 
 static void relu_bwd_cast(const Tensor& dH, const Tensor& Z, const Tensor& counters, int64_t n_hops,
-                          Tensor dPre, const c10::optional<Tensor>& colsum) {
+                          Tensor dPre, const c10::optional<Tensor>& colsum, bool prezeroed) {
   c10::cuda::CUDAGuard guard(dH.device());
   TORCH_CHECK(dPre.size(0) <= dH.size(0) && dPre.size(0) <= Z.size(0) && dPre.size(1) % 8 == 0);
   TORCH_CHECK(dH.scalar_type() == torch::kFloat32 && Z.scalar_type() == torch::kBFloat16 &&
@@ -892,7 +908,8 @@ static void relu_bwd_cast(const Tensor& dH, const Tensor& Z, const Tensor& count
               Z.size(1) == dPre.size(1), "relu_bwd_cast: contiguous [rows, d] operands of equal width");
   launch_relu_bwd_cast(dH.data_ptr<float>(), Z.data_ptr(), counters.data_ptr<int32_t>(), n_hops,
                        dPre.size(0), dPre.size(1), dPre.data_ptr(),
-                       (colsum.has_value() && colsum->defined()) ? colsum->data_ptr<float>() : nullptr, cur_stream());
+                       (colsum.has_value() && colsum->defined()) ? colsum->data_ptr<float>() : nullptr, cur_stream(),
+                       prezeroed);
   check_cuda_err("relu_bwd_cast");
 }
 
@@ -908,7 +925,7 @@ static void bias_relu(Tensor Z, const Tensor& bias, const Tensor& counters, int6
 static void softmax_nll(const Tensor& logits, int64_t C, const c10::optional<Tensor>& y,
                         const c10::optional<Tensor>& labels_all, const c10::optional<Tensor>& nodes,
                         const Tensor& counters, Tensor loss, Tensor dlogits,
-                        const c10::optional<Tensor>& correct, const c10::optional<Tensor>& colsum) {
+                        const c10::optional<Tensor>& correct, const c10::optional<Tensor>& colsum, bool prezeroed) {
   c10::cuda::CUDAGuard guard(logits.device());
   TORCH_CHECK(logits.scalar_type() == torch::kBFloat16 && logits.is_contiguous());
   TORCH_CHECK(dlogits.sizes() == logits.sizes() && dlogits.is_contiguous());
@@ -921,8 +938,18 @@ static void softmax_nll(const Tensor& logits, int64_t C, const c10::optional<Ten
                      dlogits.data_ptr(),
                      (correct.has_value() && correct->defined()) ? correct->data_ptr<int32_t>() : nullptr,
                      (colsum.has_value() && colsum->defined()) ? colsum->data_ptr<float>() : nullptr,
-                     cur_stream());
+                     cur_stream(), prezeroed);
   check_cuda_err("softmax_nll");
+}
+
+static void zero_grads(Tensor g, const c10::optional<Tensor>& loss, const c10::optional<Tensor>& correct) {
+  c10::cuda::CUDAGuard guard(g.device());
+  TORCH_CHECK(g.scalar_type() == torch::kFloat32 && g.is_contiguous() &&
+              reinterpret_cast<uintptr_t>(g.data_ptr()) % 16 == 0);
+  launch_zero_grads(g.data_ptr<float>(), g.numel(),
+                    (loss.has_value() && loss->defined()) ? loss->data_ptr<float>() : nullptr,
+                    (correct.has_value() && correct->defined()) ? correct->data_ptr<int32_t>() : nullptr, cur_stream());
+  check_cuda_err("zero_grads");
 }
 
 static void colsum_bf16(const Tensor& X, const Tensor& counters, int64_t n_hops, Tensor out) {
@@ -963,6 +990,8 @@ static void sage_fused(RowTableHandle* feat, const c10::optional<Tensor>& nodes,
                        const std::vector<int64_t>& ks, const Tensor& deg, const Tensor& w_packed,
                        const Tensor& bias, bool relu, Tensor z, const c10::optional<Tensor>& a_save) {
   c10::cuda::CUDAGuard guard(z.device());
+  const bool fp8 = feat != nullptr && !(src_local.has_value() && src_local->defined()) && feat->dtype == torch::kUInt8;
+  TORCH_CHECK(!fp8 || d == 128, "the MXFP8 loader of the fused kernel supports d = 128");
   TORCH_CHECK(z.scalar_type() == torch::kBFloat16 && z.is_contiguous());
   const int64_t n_out = z.size(1);
   TORCH_CHECK(sage_fused_supported(d, n_out), "unsupported fused shape d=", d, " n_out=", n_out);
@@ -974,6 +1003,7 @@ static void sage_fused(RowTableHandle* feat, const c10::optional<Tensor>& nodes,
   f.n_out = n_out;
   f.relu = relu;
   f.z = z.data_ptr();
+  f.feat_fp8 = fp8 ? 1 : 0;
   f.a_save = nullptr;
   if (a_save.has_value() && a_save->defined()) {
     TORCH_CHECK(a_save->size(0) >= z.size(0) && a_save->size(1) == 2 * d && a_save->is_contiguous());
@@ -1356,7 +1386,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def_property_readonly("num_parts", [](const RowTableHandle& t) { return t.tbl.num_parts; })
       .def("gather", &RowTableHandle::gather, py::arg("idx"), py::arg("id2index") = py::none(),
            py::arg("out_width") = 0)
-      .def("gather_into", &RowTableHandle::gather_into);
+      .def("gather_into", &RowTableHandle::gather_into)
+      .def("gather_mxfp8", &RowTableHandle::gather_mxfp8);
 
   // ---- GraphSAGE engine ----
   m.def("sage_aggregate", &sage_aggregate);
@@ -1364,10 +1395,14 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("sage_aggregate_block", &sage_aggregate_block);
   m.def("sage_scatter_block", &sage_scatter_block);
   m.def("add_block_f32", &add_block_f32);
-  m.def("relu_bwd_cast", &relu_bwd_cast);
+  m.def("relu_bwd_cast", &relu_bwd_cast, py::arg("dH"), py::arg("Z"), py::arg("counters"), py::arg("n_hops"),
+        py::arg("dPre"), py::arg("colsum"), py::arg("prezeroed") = false);
+  m.def("zero_grads", &zero_grads);
   m.def("sage_gather_bwd", &sage_gather_bwd);
   m.def("bias_relu", &bias_relu);
-  m.def("softmax_nll", &softmax_nll);
+  m.def("softmax_nll", &softmax_nll, py::arg("logits"), py::arg("C"), py::arg("y"), py::arg("labels_all"),
+        py::arg("nodes"), py::arg("counters"), py::arg("loss"), py::arg("dlogits"), py::arg("correct"),
+        py::arg("colsum"), py::arg("prezeroed") = false);
   m.def("adam_step", &adam_step);
   m.def("colsum_bf16", &colsum_bf16);
   m.def("zero_rows", &zero_rows);

@@ -1,6 +1,7 @@
 // Device-side helpers shared by the sm_100a kernels.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp8.h>
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -11,6 +12,16 @@
 namespace glt {
 
 constexpr int64_t kEmptyKey = -1;
+
+// Programmatic dependent launch (PDL).  The kernels of a training step form one long dependency chain of short
+// launches; with the launch attribute set (launch_utils.h) the NEXT kernel's CTAs are scheduled as soon as every
+// CTA of the current grid has called pdl_trigger(), and block in pdl_wait() until the current grid has completed
+// and flushed its memory -- so launch latency, scheduling and any prologue placed before pdl_wait() overlap with
+// the tail of the predecessor.  Without the attribute both instructions are no-ops.  Rule: nothing that a
+// predecessor kernel may have written is read before pdl_wait().
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_wait(); pdl_trigger(); }
 
 __device__ __forceinline__ uint32_t hash_slot(int64_t key, uint32_t mask) {
   uint64_t x = static_cast<uint64_t>(key) * 0x9E3779B97F4A7C15ULL;
@@ -90,6 +101,31 @@ __device__ __forceinline__ uint4 ld_nc_v4(const void* p) {
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
+}
+
+__device__ __forceinline__ uint32_t ld_nc_u32(const void* p) {
+  uint32_t r;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+
+// MXFP8 (OCP microscaling: e4m3 elements, one UE8M0 power-of-two scale per 32 elements).  `v` holds 16 consecutive
+// elements of a row starting at element gl * 16, `scales` the row's first four block-scale bytes; the block of this
+// lane's elements is gl >> 1.  acc[0..16) += dequantised values.
+__device__ __forceinline__ void mxfp8x16_accum(const uint4& v, uint32_t scales, int gl, float* acc) {
+  const float s = __uint_as_float(((scales >> (8 * (gl >> 1))) & 0xFFu) << 23);   // UE8M0 byte b -> 2^(b - 127)
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const __half2_raw hr = __nv_cvt_fp8x2_to_halfraw2(static_cast<__nv_fp8x2_storage_t>((w[i] >> (16 * h)) & 0xFFFFu),
+                                                        __NV_E4M3);
+      const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&hr));
+      acc[i * 4 + h * 2] += f2.x * s;
+      acc[i * 4 + h * 2 + 1] += f2.y * s;
+    }
+  }
 }
 
 __device__ __forceinline__ void bf16x8_accum(const uint4& v, float* acc) {

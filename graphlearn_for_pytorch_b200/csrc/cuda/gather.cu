@@ -104,6 +104,35 @@ inline int grid_for(int64_t items, int per_block, int max_blocks = 148 * 16) {
   return static_cast<int>(b);
 }
 
+// 8 lanes per row, 16 e4m3 elements per lane and iteration (d multiple of 128 keeps every lane busy)
+__global__ void __launch_bounds__(256) k_gather_mxfp8(RowTable t, const int64_t* idx, int64_t n, int d,
+                                                      __nv_bfloat16* out) {
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & 7, gw = lane >> 3;
+  const int64_t wpb = blockDim.x >> 5;
+  for (int64_t base = (blockIdx.x * wpb + (threadIdx.x >> 5)) * 4; base < n;
+       base += static_cast<int64_t>(gridDim.x) * wpb * 4) {
+    const int64_t r = base + gw;
+    if (r >= n) continue;
+    const int64_t row = idx[r];
+    const uint8_t* p = row >= 0 ? row_ptr(t, row) : nullptr;
+    for (int e0 = gl * 16; e0 < d; e0 += 128) {
+      float x[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) x[i] = 0.f;
+      if (p) {
+        // scale bytes of this 128-element span: 4 consecutive bytes at d + e0 / 32 (e0 / 32 is a multiple of 4
+        // for the span start; the lane picks its block inside mxfp8x16_accum from gl)
+        const uint32_t sc = ld_nc_u32(p + d + ((e0 - gl * 16) >> 5));
+        mxfp8x16_accum(ld_nc_v4(p + e0), sc, gl, x);
+      }
+      __nv_bfloat16* o = out + r * d + e0;
+      *reinterpret_cast<uint4*>(o) = pack_bf16x8(x, 1.f);
+      *reinterpret_cast<uint4*>(o + 8) = pack_bf16x8(x + 8, 1.f);
+    }
+  }
+}
+
 }  // namespace
 
 void launch_gather_rows(RowTable t, const int64_t* idx, const int64_t* id2index, int64_t n,
@@ -172,6 +201,13 @@ void launch_gather_i64(RowTable t, const int64_t* idx, int64_t n, const int32_t*
                        int64_t* out, cudaStream_t s) {
   if (n <= 0) return;
   k_gather_i64<<<grid_for(n, 256), 256, 0, s>>>(t, idx, n, n_dev, out);
+}
+
+void launch_gather_mxfp8(RowTable t, const int64_t* idx, int64_t n, int d, void* out, cudaStream_t s) {
+  if (n <= 0) return;
+  int64_t blocks = (n + 31) / 32;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_gather_mxfp8<<<static_cast<int>(blocks), 256, 0, s>>>(t, idx, n, d, reinterpret_cast<__nv_bfloat16*>(out));
 }
 
 }  // namespace glt

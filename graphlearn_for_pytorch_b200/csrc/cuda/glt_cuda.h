@@ -154,6 +154,8 @@ void launch_gather_i64(RowTable t, const int64_t* idx, int64_t n, const int32_t*
                        int64_t* out, cudaStream_t s);
 // copy `nbytes` (multiple of 16) from local memory to an NVSwitch multicast address
 void launch_multimem_copy(const void* src, void* mc_dst, int64_t nbytes, cudaStream_t s);
+// out[i, 0..d) (bf16) = dequantised MXFP8 row idx[i] of `t` (rows of d + 16 bytes, see data/quantize.py)
+void launch_gather_mxfp8(RowTable t, const int64_t* idx, int64_t n, int d, void* out, cudaStream_t s);
 
 // ---- sage.cu (GraphSAGE engine kernels) ---------------------------------------
 struct SageAggArgs {
@@ -240,7 +242,10 @@ void launch_sage_gather_bwd(const SageGatherBwdArgs& a, cudaStream_t s);
 // dPre = (Z > 0) ? bf16(dH) : 0 for rows < cum[n_hops]; 0 beyond.
 // colsum (optional, fp32 [d]): fused bias gradient = column sums of dPre.
 void launch_relu_bwd_cast(const float* dH, const void* Z, const int32_t* cum, int n_hops, int cap,
-                          int d, void* dPre, float* colsum, cudaStream_t s);
+                          int d, void* dPre, float* colsum, cudaStream_t s, bool prezeroed = false);
+// g[0..n) = 0, *loss = 0, *correct = 0 (one launch at the start of the gradient phase; the *_prezeroed variants of
+// the kernels below then skip their own memsets, which keeps the step a pure kernel chain)
+void launch_zero_grads(float* g, int64_t n, float* loss, int32_t* correct, cudaStream_t s);
 // bias + relu epilogue over valid rows (zero beyond): Z = relu(Z + b)
 void launch_bias_relu(void* Z, const void* bias, const int32_t* cum, int n_hops, int cap, int d,
                       int relu, cudaStream_t s);
@@ -248,7 +253,7 @@ void launch_bias_relu(void* Z, const void* bias, const int32_t* cum, int n_hops,
 // labels come from y[r], or (labels_all != nullptr) from labels_all[nodes[r]].
 void launch_softmax_nll(const void* logits, int ld, int C, const int64_t* y, const int64_t* labels_all,
                         const int64_t* nodes, const int32_t* cum, int cap, float* loss, void* dlogits,
-                        int32_t* correct, float* colsum, cudaStream_t s);
+                        int32_t* correct, float* colsum, cudaStream_t s, bool prezeroed = false);
 // out[c] = sum over valid rows of X[:, c]  (d multiple of 8, d <= 2048)
 void launch_colsum_bf16(const void* X, const int32_t* cum, int n_hops, int cap, int d, float* out,
                         cudaStream_t s);
@@ -280,6 +285,7 @@ struct SageFusedArgs {
   void* z;                      // bf16 [cap_targets, N]
   void* a_save;                 // optional bf16 [cap_targets, 2d] for backward
   unsigned long long* trace;    // optional per-CTA clock64 timeline (diagnostics, see sage_fused_trace)
+  int feat_fp8;                 // 1: agg.feat rows are MXFP8 (d e4m3 bytes + d/32 UE8M0 scales, 16-byte padded)
 };
 int sage_fused_supported(int d, int n_out);
 // Copies the per-CTA timeline of the last traced launch (GLT_B200_FUSED_TRACE=1) to `host` [148*32].

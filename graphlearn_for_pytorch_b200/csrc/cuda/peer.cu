@@ -12,6 +12,7 @@
 // (examples/multi_gpu/train_sage_ogbn_papers100m.py:55); the model here is ~1.3 MB of fp32
 // gradients, far below the size where NCCL's launch + protocol latency amortises.
 #include "device_utils.cuh"
+#include "launch_utils.h"
 
 namespace glt {
 
@@ -28,6 +29,7 @@ __device__ __forceinline__ int32_t ld_acquire_sys(const int32_t* p) {
 
 // one block, >= world threads
 __global__ void k_peer_barrier(PeerPtrs p, int which, int32_t* epoch_dev, int32_t* err) {
+  pdl_enter();
   __shared__ int s_epoch;
   const int r = threadIdx.x;
   if (r == 0) s_epoch = epoch_dev[which] + 1;
@@ -60,6 +62,7 @@ __global__ void __launch_bounds__(256) k_adam_peer(PeerPtrs p, float* param, flo
                                                    __nv_bfloat16* pb, int64_t n, float lr, float b1, float b2,
                                                    float eps, float wd, int32_t* step_dev, float gscale,
                                                    const int32_t* err) {
+  pdl_enter();
   // a barrier of this step timed out (a peer died or stalled): the gradients are incomplete, so the update is
   // skipped on every rank that saw the timeout; the host raises at its next health check (models/sage.py)
   if (err && *reinterpret_cast<const volatile int32_t*>(err) != 0) return;
@@ -109,7 +112,7 @@ __global__ void __launch_bounds__(256) k_adam_peer(PeerPtrs p, float* param, flo
 }  // namespace
 
 void launch_peer_barrier(const PeerPtrs& p, int which, int32_t* epoch_dev, int32_t* err, cudaStream_t s) {
-  k_peer_barrier<<<1, 32, 0, s>>>(p, which, epoch_dev, err);
+  launch_k(k_peer_barrier, dim3(1), dim3(32), 0, s, p, which, epoch_dev, err);
 }
 
 void launch_adam_peer(const PeerPtrs& p, float* param, float* m, float* v, void* p_bf16, int64_t n, float lr,
@@ -118,8 +121,8 @@ void launch_adam_peer(const PeerPtrs& p, float* param, float* m, float* v, void*
   int64_t blocks = ((n >> 2) + 255) / 256;
   if (blocks > 148 * 4) blocks = 148 * 4;
   if (blocks < 1) blocks = 1;
-  k_adam_peer<<<static_cast<int>(blocks), 256, 0, s>>>(p, param, m, v, reinterpret_cast<__nv_bfloat16*>(p_bf16), n,
-                                                       lr, b1, b2, eps, wd, step_dev, gscale, err);
+  launch_k(k_adam_peer, dim3(static_cast<int>(blocks)), dim3(256), 0, s, p, param, m, v,
+           reinterpret_cast<__nv_bfloat16*>(p_bf16), n, lr, b1, b2, eps, wd, step_dev, gscale, err);
 }
 
 }  // namespace glt

@@ -11,6 +11,7 @@
 #include <cstdlib>
 
 #include "device_utils.cuh"
+#include "launch_utils.h"
 
 namespace glt {
 
@@ -36,6 +37,7 @@ __device__ __forceinline__ const uint8_t* src_row(const SageAggArgs& a, int s) {
 // LPR lanes cooperate on one target row; each lane owns VPL 16-byte vectors.
 template <int LPR, int VPL, int NB>
 __global__ void __launch_bounds__(256) k_sage_aggregate(SageAggArgs a) {
+  pdl_enter();
   constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31;
   const int gl = lane % LPR;
@@ -127,6 +129,7 @@ __device__ __forceinline__ void atomic_add8(float* dst, const float* v) {
 
 template <int LPR, int VPL>
 __global__ void __launch_bounds__(256) k_sage_scatter_bwd(SageScatterArgs a) {
+  pdl_enter();
   constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31;
   const int gl = lane % LPR;
@@ -171,6 +174,7 @@ __global__ void __launch_bounds__(256) k_sage_scatter_bwd(SageScatterArgs a) {
 __global__ void __launch_bounds__(256) k_relu_bwd_cast(const float* dH, const __nv_bfloat16* Z, const int32_t* cum,
                                                        int n_hops, int cap, int d, __nv_bfloat16* dPre,
                                                        float* colsum) {
+  pdl_enter();
   // colsum != nullptr: also accumulate the bias gradient (column sums of dPre).  Requires
   // d | 2048 so that a thread keeps the same 8 columns across grid-stride iterations.
   __shared__ float s_acc[256][8];
@@ -242,6 +246,7 @@ __global__ void k_softmax_nll(const __nv_bfloat16* logits, int ld, int C, const 
                               const int64_t* labels_all, const int64_t* nodes,
                               const int32_t* cum, int cap, float* loss, __nv_bfloat16* dlogits,
                               int32_t* correct, float* colsum) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   float csum[8];  // bias gradient: columns lane, lane+32, ... (ld <= 256)
 #pragma unroll
@@ -303,6 +308,7 @@ __global__ void k_softmax_nll(const __nv_bfloat16* logits, int ld, int C, const 
 __global__ void k_adam(float* p, const float* g, float* m, float* v, __nv_bfloat16* pb, int64_t n,
                        float lr, float b1, float b2, float eps, float wd, int32_t* step_dev,
                        float gscale) {
+  pdl_enter();
   const float t = static_cast<float>(*reinterpret_cast<volatile int32_t*>(step_dev) + 1);
   const float c1 = 1.f - __powf(b1, t), c2 = 1.f - __powf(b2, t);
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
@@ -354,6 +360,7 @@ __global__ void __launch_bounds__(256) k_colsum(const __nv_bfloat16* X, const in
 
 __global__ void k_add_block_f32(const __nv_bfloat16* dA, int dA_ld, int col, int d, const int32_t* cum, int n_hops,
                                 int cap, float* dH) {
+  pdl_enter();
   const int T = min(cum[n_hops], cap);
   const int nvec = d >> 3;
   const int64_t n = static_cast<int64_t>(T) * nvec;
@@ -372,7 +379,24 @@ __global__ void k_add_block_f32(const __nv_bfloat16* dA, int dA_ld, int col, int
   }
 }
 
+// start of the gradient phase of a step: flat gradient buffer, loss and #correct back to zero in one launch
+__global__ void k_zero_grads(float* g, int64_t n, float* loss, int32_t* correct) {
+  pdl_enter();
+  const int64_t n4 = n >> 2;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (blockIdx.x == 0) {
+    for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) g[i] = 0.f;
+    if (threadIdx.x == 0) {
+      if (loss) *loss = 0.f;
+      if (correct) *correct = 0;
+    }
+  }
+}
+
 __global__ void k_zero_rows(float* p, const int32_t* cum, int n_hops, int cap, int d) {
+  pdl_enter();
   const int T = min(cum[n_hops], cap);
   const int64_t n4 = static_cast<int64_t>(T) * d / 4;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
@@ -413,25 +437,25 @@ void launch_sage_aggregate(const SageAggArgs& a, cudaStream_t s) {
   }();
   GLT_DISPATCH_WIDTH(a.d, {
     if (batched && VPL <= 2)
-      k_sage_aggregate<LPR, VPL, 4><<<grid_for(a.cap_targets, 8 * (32 / LPR)), 256, 0, s>>>(a);
+      launch_k(k_sage_aggregate<LPR, VPL, 4>, dim3(grid_for(a.cap_targets, 8 * (32 / LPR))), dim3(256), 0, s, a);
     else
-      k_sage_aggregate<LPR, VPL, 1><<<grid_for(a.cap_targets, 8 * (32 / LPR)), 256, 0, s>>>(a);
+      launch_k(k_sage_aggregate<LPR, VPL, 1>, dim3(grid_for(a.cap_targets, 8 * (32 / LPR))), dim3(256), 0, s, a);
   });
 }
 
 void launch_sage_scatter_bwd(const SageScatterArgs& a, cudaStream_t s) {
   GLT_DISPATCH_WIDTH(a.d, {
-    k_sage_scatter_bwd<LPR, VPL><<<grid_for(a.cap_targets, 8 * (32 / LPR)), 256, 0, s>>>(a);
+    launch_k(k_sage_scatter_bwd<LPR, VPL>, dim3(grid_for(a.cap_targets, 8 * (32 / LPR))), dim3(256), 0, s, a);
   });
 }
 
 void launch_relu_bwd_cast(const float* dH, const void* Z, const int32_t* cum, int n_hops, int cap,
-                          int d, void* dPre, float* colsum, cudaStream_t s) {
+                          int d, void* dPre, float* colsum, cudaStream_t s, bool prezeroed) {
   if (colsum && (2048 % d != 0)) colsum = nullptr;  // caller falls back to launch_colsum_bf16
-  if (colsum) cudaMemsetAsync(colsum, 0, sizeof(float) * d, s);
-  k_relu_bwd_cast<<<grid_for(static_cast<int64_t>(cap) * d / 8, 256 * 2, 148 * 4), 256, 0, s>>>(
-      dH, reinterpret_cast<const __nv_bfloat16*>(Z), cum, n_hops, cap, d,
-      reinterpret_cast<__nv_bfloat16*>(dPre), colsum);
+  if (colsum && !prezeroed) cudaMemsetAsync(colsum, 0, sizeof(float) * d, s);
+  launch_k(k_relu_bwd_cast, dim3(grid_for(static_cast<int64_t>(cap) * d / 8, 256 * 2, 148 * 4)), dim3(256), 0, s,
+           dH, reinterpret_cast<const __nv_bfloat16*>(Z), cum, n_hops, cap, d,
+           reinterpret_cast<__nv_bfloat16*>(dPre), colsum);
 }
 
 void launch_bias_relu(void* Z, const void* bias, const int32_t* cum, int n_hops, int cap, int d,
@@ -443,21 +467,22 @@ void launch_bias_relu(void* Z, const void* bias, const int32_t* cum, int n_hops,
 
 void launch_softmax_nll(const void* logits, int ld, int C, const int64_t* y, const int64_t* labels_all,
                         const int64_t* nodes, const int32_t* cum, int cap, float* loss, void* dlogits,
-                        int32_t* correct, float* colsum, cudaStream_t s) {
+                        int32_t* correct, float* colsum, cudaStream_t s, bool prezeroed) {
   if (ld > 256) colsum = nullptr;
-  if (colsum) cudaMemsetAsync(colsum, 0, sizeof(float) * ld, s);
-  cudaMemsetAsync(loss, 0, sizeof(float), s);
-  if (correct) cudaMemsetAsync(correct, 0, sizeof(int32_t), s);
-  k_softmax_nll<<<grid_for(cap, 8), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(logits), ld,
-                                                  C, y, labels_all, nodes, cum, cap, loss,
-                                                  reinterpret_cast<__nv_bfloat16*>(dlogits), correct, colsum);
+  if (!prezeroed) {   // memset nodes would break the programmatic-launch chain: the engine zeroes these in k_zero_grads
+    if (colsum) cudaMemsetAsync(colsum, 0, sizeof(float) * ld, s);
+    cudaMemsetAsync(loss, 0, sizeof(float), s);
+    if (correct) cudaMemsetAsync(correct, 0, sizeof(int32_t), s);
+  }
+  launch_k(k_softmax_nll, dim3(grid_for(cap, 8)), dim3(256), 0, s, reinterpret_cast<const __nv_bfloat16*>(logits), ld,
+           C, y, labels_all, nodes, cum, cap, loss, reinterpret_cast<__nv_bfloat16*>(dlogits), correct, colsum);
 }
 
 void launch_adam(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr,
                  float b1, float b2, float eps, float wd, int32_t* step_dev, float gscale,
                  cudaStream_t s) {
-  k_adam<<<grid_for(n, 256, 148 * 4), 256, 0, s>>>(p, g, m, v, reinterpret_cast<__nv_bfloat16*>(p_bf16),
-                                                   n, lr, b1, b2, eps, wd, step_dev, gscale);
+  launch_k(k_adam, dim3(grid_for(n, 256, 148 * 4)), dim3(256), 0, s, p, g, m, v,
+           reinterpret_cast<__nv_bfloat16*>(p_bf16), n, lr, b1, b2, eps, wd, step_dev, gscale);
 }
 
 void launch_colsum_bf16(const void* X, const int32_t* cum, int n_hops, int cap, int d, float* out,
@@ -471,12 +496,16 @@ void launch_colsum_bf16(const void* X, const int32_t* cum, int n_hops, int cap, 
 
 void launch_add_block_f32(const void* dA, int dA_ld, int col, int d, const int32_t* cum, int n_hops, int cap,
                           float* dH, cudaStream_t s) {
-  k_add_block_f32<<<grid_for(static_cast<int64_t>(cap) * d / 8, 256), 256, 0, s>>>(
-      reinterpret_cast<const __nv_bfloat16*>(dA), dA_ld, col, d, cum, n_hops, cap, dH);
+  launch_k(k_add_block_f32, dim3(grid_for(static_cast<int64_t>(cap) * d / 8, 256)), dim3(256), 0, s,
+           reinterpret_cast<const __nv_bfloat16*>(dA), dA_ld, col, d, cum, n_hops, cap, dH);
+}
+
+void launch_zero_grads(float* g, int64_t n, float* loss, int32_t* correct, cudaStream_t s) {
+  launch_k(k_zero_grads, dim3(grid_for(n / 4 + 1, 256, 148 * 2)), dim3(256), 0, s, g, n, loss, correct);
 }
 
 void launch_zero_rows(float* p, const int32_t* cum, int n_hops, int cap, int d, cudaStream_t s) {
-  k_zero_rows<<<grid_for(static_cast<int64_t>(cap) * d / 4, 256 * 4), 256, 0, s>>>(p, cum, n_hops, cap, d);
+  launch_k(k_zero_rows, dim3(grid_for(static_cast<int64_t>(cap) * d / 4, 256 * 4)), dim3(256), 0, s, p, cum, n_hops, cap, d);
 }
 
 void launch_bf16_to_f32(const void* src, float* dst, int64_t n, cudaStream_t s) {

@@ -21,6 +21,7 @@
 //   warps 17-20 epilogue    (TMEM lane quadrant = warp_id % 4)
 #include <cstdlib>
 
+#include "launch_utils.h"
 #include "tc_utils.cuh"
 
 namespace glt {
@@ -317,7 +318,10 @@ constexpr uint32_t kNoRow = 0xFFFFFFFFu;
 // A row handle is (shard << 28) | row-inside-shard; the loaders turn it into an address with one
 // LDS from a 16-entry base table, so a table row costs 64 B instead of 128 B of pointers -- the
 // 16 KB this frees hold the epilogue's staging buffers.
-template <int NC>
+// FP8 = true: the feature table holds MXFP8 rows (d e4m3 bytes + d/32 UE8M0 block scales, padded to a multiple
+// of 16 bytes; data/quantize.py) -- the loaders move HALF the bytes per row, de-quantise in registers while they
+// reduce the neighbour mean in fp32 and still hand bf16 tiles to the tensor core (d = 128 only).
+template <int NC, bool FP8>
 __global__ void __launch_bounds__(kThreads3, 1) k_sage_fused3(SageFusedArgs f) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -351,9 +355,7 @@ __global__ void __launch_bounds__(kThreads3, 1) k_sage_fused3(SageFusedArgs f) {
   unsigned long long* tr = f.trace ? f.trace + blockIdx.x * kFusedTraceSlots : nullptr;
   if (threadIdx.x == 0) trace_at(tr, 0);
   const SageAggArgs& a = f.agg;
-  const int T = min(a.cum[a.n_hops_targets], a.cap_targets);
-  const int n_tiles = (T + kTileM - 1) / kTileM;
-  const int64_t row_bytes = static_cast<int64_t>(a.d) * 2;
+  const int64_t row_bytes = FP8 ? static_cast<int64_t>(a.feat.row_bytes) : static_cast<int64_t>(a.d) * 2;
   // Tile order.  Low tile indices hold the early hops (largest fan-out = most neighbour rows per
   // tile); a plain round-robin hands those to the same CTAs that also get a tile of the last,
   // partial wave.  The first wave is therefore dealt in reverse: the CTAs that own an extra tile
@@ -388,18 +390,24 @@ __global__ void __launch_bounds__(kThreads3, 1) k_sage_fused3(SageFusedArgs f) {
     else if (static_cast<int>(threadIdx.x) < a.feat.num_parts) b = a.feat.base[threadIdx.x];
     sts64(base_u32 + threadIdx.x * 8, reinterpret_cast<uint64_t>(b));
   }
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + (N >> 3))  // bias -> smem, 16 B per thread
-    *reinterpret_cast<uint4*>(bias_s + (threadIdx.x - 64) * 16) =
-        reinterpret_cast<const uint4*>(f.bias)[threadIdx.x - 64];
   if (warp == kResWarp0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
+  // programmatic dependent launch: barrier init, shard base table and TMEM allocation above overlap with the tail
+  // of the previous kernel; global data written by predecessors (bias, counters, ELL, rows) is only read below
+  pdl_wait();
+  pdl_trigger();
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + (N >> 3))  // bias -> smem, 16 B per thread
+    *reinterpret_cast<uint4*>(bias_s + (threadIdx.x - 64) * 16) =
+        reinterpret_cast<const uint4*>(f.bias)[threadIdx.x - 64];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int T = min(a.cum[a.n_hops_targets], a.cap_targets);
+  const int n_tiles = (T + kTileM - 1) / kTileM;
 
   if (warp < kProducerWarps) {
     // ------------------------------ loaders ------------------------------
@@ -420,6 +428,90 @@ __global__ void __launch_bounds__(kThreads3, 1) k_sage_fused3(SageFusedArgs f) {
       const uint32_t tb = tab_u32 + stage * kTabStageBytes;
       const uint32_t dgt = deg_u32 + stage * (kTileM * 4);
       bool waited = false;
+      if constexpr (FP8) {
+        static_assert(!FP8 || NC == 2, "the MXFP8 loader is written for d = 128");
+        constexpr int NF = 8;              // rows in flight per lane in the first batch (self + 7 neighbours)
+        const int cc = gl >> 2;            // bf16 K-chunk that this lane's 16 elements fall into
+        const int vv = (gl & 3) * 2;       // first of the two 16-byte bf16 vectors inside that chunk
+#pragma unroll 1
+        for (int q = 0; q < RPG; ++q) {
+          const int r = group + q * (kTileM / RPG);
+          const int t = tile * kTileM + r;
+          const int dg = lds32(dgt + r * 4);
+          const uint32_t trow = tb + r * 64;
+          const int sw = r & 15;
+          const uint32_t arow = a_u32 + r * kChunkBytes;
+          const uint32_t o0 = ((vv ^ (r & 7)) << 4), o1 = (((vv + 1) ^ (r & 7)) << 4);
+          uint8_t* save = (t < T && f.a_save)
+                              ? reinterpret_cast<uint8_t*>(f.a_save) + static_cast<int64_t>(t) * a.d * 4 + gl * 32
+                              : nullptr;
+          const int dgt_ = min(dg, kKP);
+          float acc[16];
+          {
+            uint4 v[NF];
+            uint32_t sc[NF];
+#pragma unroll
+            for (int jj = 0; jj < NF; ++jj) {
+              const uint8_t* p = nullptr;
+              if (jj <= dgt_) p = row_addr(static_cast<uint32_t>(lds32(trow + ((((jj + 15) & 15) ^ sw) << 2))));
+              v[jj] = p ? ld_nc_v4(p + gl * 16) : make_uint4(0, 0, 0, 0);
+              sc[jj] = p ? ld_nc_u32(p + a.d) : 0u;
+            }
+            if (!waited) { mbar_wait(bar_a_empty, (it & 1) ^ 1); waited = true; }
+            {  // the row itself -> bf16 -> "self" half of the A tile
+              float x[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) x[i] = 0.f;
+              mxfp8x16_accum(v[0], sc[0], gl, x);
+              const uint4 s0 = pack_bf16x8(x, 1.f), s1 = pack_bf16x8(x + 8, 1.f);
+              sts128(arow + (NC + cc) * kAChunkTile + o0, s0);
+              sts128(arow + (NC + cc) * kAChunkTile + o1, s1);
+              if (save) {
+                *reinterpret_cast<uint4*>(save + a.d * 2) = s0;
+                *reinterpret_cast<uint4*>(save + a.d * 2 + 16) = s1;
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+#pragma unroll
+            for (int jj = 1; jj < NF; ++jj) mxfp8x16_accum(v[jj], sc[jj], gl, acc);
+          }
+          if (dgt_ > NF - 1) {             // neighbours 7..14 in one more batch
+            uint4 v[NF];
+            uint32_t sc[NF];
+#pragma unroll
+            for (int jj = 0; jj < NF; ++jj) {
+              const int j = NF - 1 + jj;
+              const uint8_t* p = nullptr;
+              if (j < dgt_) p = row_addr(static_cast<uint32_t>(lds32(trow + ((j ^ sw) << 2))));
+              v[jj] = p ? ld_nc_v4(p + gl * 16) : make_uint4(0, 0, 0, 0);
+              sc[jj] = p ? ld_nc_u32(p + a.d) : 0u;
+            }
+#pragma unroll
+            for (int jj = 0; jj < NF; ++jj) mxfp8x16_accum(v[jj], sc[jj], gl, acc);
+          }
+          if (dg > kKP) {  // rows wider than the table (fan-out > 15): chase the rest here
+            const HopLoc2 l = locate2(a.cum, a.n_hops_targets, t);
+            const int32_t* ellrow = a.ell[l.hop] + static_cast<int64_t>(l.row) * a.k[l.hop];
+#pragma unroll 1
+            for (int j = kKP; j < dg; ++j) {
+              const int sidx = __ldg(ellrow + j);
+              if (sidx < 0) continue;
+              const uint8_t* p = src_row2(a, sidx);
+              mxfp8x16_accum(ld_nc_v4(p + gl * 16), ld_nc_u32(p + a.d), gl, acc);
+            }
+          }
+          const float inv = dg > 0 ? 1.f / static_cast<float>(dg) : 0.f;
+          const uint4 m0 = pack_bf16x8(acc, inv), m1 = pack_bf16x8(acc + 8, inv);
+          sts128(arow + cc * kAChunkTile + o0, m0);
+          sts128(arow + cc * kAChunkTile + o1, m1);
+          if (save) {
+            *reinterpret_cast<uint4*>(save) = m0;
+            *reinterpret_cast<uint4*>(save + 16) = m1;
+          }
+          if (threadIdx.x == 0 && q == 0) trace_at(tr, 4 + 7 * it + 2);
+        }
+      } else {
 #pragma unroll 1
       for (int q = 0; q < RPG; ++q) {
         const int r = group + q * (kTileM / RPG);
@@ -498,6 +590,7 @@ __global__ void __launch_bounds__(kThreads3, 1) k_sage_fused3(SageFusedArgs f) {
         }
         if (threadIdx.x == 0 && q == 0) trace_at(tr, 4 + 7 * it + 2);
       }
+      }  // !FP8
       __syncwarp();
       if (threadIdx.x == 0) trace_at(tr, 4 + 7 * it + 3);
       if (lane == 0) mbar_arrive(bar_p_empty0 + 8 * stage);  // table stage may be refilled
@@ -695,6 +788,7 @@ __global__ void __launch_bounds__(kThreads3, 1) k_sage_fused3(SageFusedArgs f) {
 // W [N, K] row-major bf16 -> [K/64][N][64] with the SWIZZLE_128B XOR applied, so
 // the kernel can bulk-copy it verbatim into 1024-B aligned shared memory.
 __global__ void k_pack_weight(const __nv_bfloat16* w, int n, int k, __nv_bfloat16* out) {
+  pdl_enter();
   const int64_t total = static_cast<int64_t>(n) * k / 8;  // 16-byte vectors
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -768,10 +862,19 @@ static void launch_fused_nc(const SageFusedArgs& a_in, int grid, cudaStream_t s)
       a.trace = sym[dev];
     }
   }
+  if (a.feat_fp8) {
+    // MXFP8 feature rows: only the decoupled (v3) kernel has the de-quantising loader, d = 128
+    if constexpr (NC == 2) {
+      const size_t smem = fused3_smem_bytes(a.agg.d, a.n_out);
+      cudaFuncSetAttribute(k_sage_fused3<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      launch_k(k_sage_fused3<2, true>, dim3(grid), dim3(kThreads3), smem, s, a);
+    }
+    return;
+  }
   if (fused_version(a.agg.d, a.n_out) == 3 && handles_fit(a.agg)) {
     const size_t smem = fused3_smem_bytes(a.agg.d, a.n_out);
-    cudaFuncSetAttribute(k_sage_fused3<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    k_sage_fused3<NC><<<grid, kThreads3, smem, s>>>(a);
+    cudaFuncSetAttribute(k_sage_fused3<NC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    launch_k(k_sage_fused3<NC, false>, dim3(grid), dim3(kThreads3), smem, s, a);
   } else {
     const size_t smem = fused_smem_bytes(a.agg.d, a.n_out);
     cudaFuncSetAttribute(k_sage_fused<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
@@ -795,8 +898,8 @@ void launch_pack_weight(const void* w, int n, int k, void* packed, cudaStream_t 
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > 1184) blocks = 1184;
   if (blocks < 1) blocks = 1;
-  k_pack_weight<<<blocks, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(w), n, k,
-                                       reinterpret_cast<__nv_bfloat16*>(packed));
+  launch_k(k_pack_weight, dim3(blocks), dim3(256), 0, s, reinterpret_cast<const __nv_bfloat16*>(w), n, k,
+           reinterpret_cast<__nv_bfloat16*>(packed));
 }
 
 }  // namespace glt

@@ -17,6 +17,7 @@
 #include <climits>
 
 #include "device_utils.cuh"
+#include "launch_utils.h"
 
 namespace glt {
 
@@ -173,12 +174,14 @@ __device__ __forceinline__ void sample_hop_body(const HopArgs& a) {
 
 template <int G, int MAXC>
 __global__ void __launch_bounds__(256) k_sample_hop(HopArgs a) {
+  pdl_enter();
   sample_hop_body<G, MAXC>(a);
 }
 
 // one launch for every relation of a heterogeneous hop: blockIdx.y = relation
 template <int G, int MAXC>
 __global__ void __launch_bounds__(256) k_sample_hop_grouped(const HopArgs* descs) {
+  pdl_enter();
   const HopArgs& a = descs[blockIdx.y];
   if (a.k <= 0) return;
   sample_hop_body<G, MAXC>(a);
@@ -247,16 +250,21 @@ __device__ __forceinline__ void relabel_hop_body(const HopArgs& a) {
 }
 
 template <int G>
-__global__ void __launch_bounds__(256) k_relabel_hop(HopArgs a) { relabel_hop_body<G>(a); }
+__global__ void __launch_bounds__(256) k_relabel_hop(HopArgs a) {
+  pdl_enter();
+  relabel_hop_body<G>(a);
+}
 
 template <int G>
 __global__ void __launch_bounds__(256) k_relabel_hop_grouped(const HopArgs* descs) {
+  pdl_enter();
   const HopArgs& a = descs[blockIdx.y];
   if (a.k <= 0) return;
   relabel_hop_body<G>(a);
 }
 
 __global__ void k_hetero_finalize(const HeteroTypeState* types, int n_types, int hop) {
+  pdl_enter();
   const int t = threadIdx.x;
   if (t >= n_types) return;
   const HeteroTypeState& ty = types[t];
@@ -271,6 +279,7 @@ __global__ void __launch_bounds__(1024) k_init_seeds(const int64_t* seeds, int n
                                                      int64_t* nodes, int32_t* seed_local,
                                                      int32_t* slot_of, BatchCounters c, int max_hops,
                                                      int32_t* step_dev, int step_inc) {
+  pdl_enter();
   __shared__ int s_warp[32];
   __shared__ int s_running;
   // first kernel of a batch: advance the device-side Philox step here instead of paying a
@@ -466,8 +475,8 @@ void launch_table_clear(HashTable t, cudaStream_t s) {
 void launch_init_seeds(const int64_t* seeds, int n_seeds, const int32_t* n_seeds_dev, HashTable t,
                        int64_t* nodes, int32_t* seed_local, int32_t* scratch, BatchCounters c,
                        int32_t* step_dev, int step_inc, cudaStream_t s) {
-  k_init_seeds<<<1, 1024, 0, s>>>(seeds, n_seeds, n_seeds_dev, t, nodes, seed_local, scratch, c, 4, step_dev,
-                                  step_inc);
+  launch_k(k_init_seeds, dim3(1), dim3(1024), 0, s, seeds, n_seeds, n_seeds_dev, t, nodes, seed_local, scratch, c, 4,
+           step_dev, step_inc);
 }
 
 #define GLT_DISPATCH_FANOUT(K, ...)                                  \
@@ -482,7 +491,7 @@ void launch_init_seeds(const int64_t* seeds, int n_seeds, const int32_t* n_seeds
 void launch_sample_hop(const HopArgs& a, cudaStream_t s) {
   GLT_DISPATCH_FANOUT(a.k, {
     const int rows_per_block = (256 / 32) * (32 / G);
-    k_sample_hop<G, MAXC><<<grid_for(a.cap_rows, rows_per_block), 256, 0, s>>>(a);
+    launch_k(k_sample_hop<G, MAXC>, dim3(grid_for(a.cap_rows, rows_per_block)), dim3(256), 0, s, a);
   });
 }
 
@@ -496,7 +505,7 @@ void launch_sample_hop(const HopArgs& a, cudaStream_t s) {
 void launch_relabel_hop(const HopArgs& a, cudaStream_t s) {
   GLT_DISPATCH_GROUP(a.k, {
     const int rows_per_block = (256 / 32) * (32 / G);
-    k_relabel_hop<G><<<grid_for(a.cap_rows, rows_per_block), 256, 0, s>>>(a);
+    launch_k(k_relabel_hop<G>, dim3(grid_for(a.cap_rows, rows_per_block)), dim3(256), 0, s, a);
   });
 }
 
@@ -505,7 +514,7 @@ void launch_sample_hop_grouped(const HopArgs* descs, int n_rel, int max_k, int m
   GLT_DISPATCH_FANOUT(max_k, {
     const int rows_per_block = (256 / 32) * (32 / G);
     dim3 grid(grid_for(max_rows, rows_per_block, 148 * 8), n_rel);
-    k_sample_hop_grouped<G, MAXC><<<grid, 256, 0, s>>>(descs);
+    launch_k(k_sample_hop_grouped<G, MAXC>, grid, dim3(256), 0, s, descs);
   });
 }
 
@@ -514,13 +523,13 @@ void launch_relabel_hop_grouped(const HopArgs* descs, int n_rel, int max_k, int 
   GLT_DISPATCH_GROUP(max_k, {
     const int rows_per_block = (256 / 32) * (32 / G);
     dim3 grid(grid_for(max_rows, rows_per_block, 148 * 8), n_rel);
-    k_relabel_hop_grouped<G><<<grid, 256, 0, s>>>(descs);
+    launch_k(k_relabel_hop_grouped<G>, grid, dim3(256), 0, s, descs);
   });
 }
 
 void launch_hetero_finalize(const HeteroTypeState* types, int n_types, int hop, cudaStream_t s) {
   if (n_types <= 0) return;
-  k_hetero_finalize<<<1, 32 * ((n_types + 31) / 32), 0, s>>>(types, n_types, hop);
+  launch_k(k_hetero_finalize, dim3(1), dim3(32 * ((n_types + 31) / 32)), 0, s, types, n_types, hop);
 }
 
 void launch_sample_one_hop(GraphTable g, const int64_t* seeds, int n, int k, int weighted,

@@ -24,6 +24,7 @@
 #include <cstring>
 #include <mutex>
 
+#include "launch_utils.h"
 #include "tc_utils.cuh"
 
 namespace glt {
@@ -131,6 +132,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above (barrier init, tensor-map prefetch, TMEM allocation) overlapped with the tail of the previous
+  // kernel; from here on the predecessor's results (counters, operands) are read
+  pdl_wait();
+  pdl_trigger();
 
   // identical on every thread: work decomposition from the device counters
   const int share = g.n_prob > 1 ? max(1, static_cast<int>(gridDim.x) / 2) : static_cast<int>(gridDim.x);
@@ -347,7 +352,7 @@ void launch_tc_gemm(const TcGemmLaunch& L, int num_sms, cudaStream_t s) {
   int grid = num_sms;
   if (L.max_items > 0 && L.max_items < grid) grid = L.max_items;
   const CUtensorMap* m = reinterpret_cast<const CUtensorMap*>(L.maps);
-  k_tc_gemm<<<grid, kGemmThreads, kGemmSmem, s>>>(m[0], m[1], m[2], m[3], m[4], m[5], L.args);
+  launch_k(k_tc_gemm, dim3(grid), dim3(kGemmThreads), kGemmSmem, s, m[0], m[1], m[2], m[3], m[4], m[5], L.args);
 }
 
 }  // namespace glt

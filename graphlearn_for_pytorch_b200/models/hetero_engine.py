@@ -272,10 +272,10 @@ class HeteroSageEngine(object):
     if self.peer_group is not None:
       self.peer_group.barrier(1)            # peers finished reading last step's gradients
       self._k()
-    self.g32.zero_()
+    nat.zero_grads(self.g32, self.loss, self.correct)
     boff, n = self._b_off[(self.L, st)]
     nat.softmax_nll(self.Z[self.L][st], self.C, None, self.labels, ar.nodes_of(st), self._ctr[st], self.loss,
-                    self.dPre[self.L][st], self.correct, self.g32[boff:boff + n])
+                    self.dPre[self.L][st], self.correct, self.g32[boff:boff + n], True)
     self._k(2)
 
   def _backward(self):
@@ -303,7 +303,7 @@ class HeteroSageEngine(object):
       for s in self.targets[l - 1]:
         boff, n = self._b_off[(l - 1, s)]
         nat.relu_bwd_cast(self.dH[l - 1][s], self.Z[l - 1][s], self._ctr[s], nh + 1, self.dPre[l - 1][s],
-                          self.g32[boff:boff + n])
+                          self.g32[boff:boff + n], True)
         self._k()
 
   def _optimizer(self):

@@ -108,8 +108,15 @@ class GraphSageEngine(object):
                use_cuda_graph: bool = True, calibration_seeds: Optional[torch.Tensor] = None,
                calibration_margin: float = 1.3, calibration_batches: int = 16, pipeline: bool = False,
                use_peer_allreduce: bool = True, use_gather_bwd: Optional[bool] = None,
-               check_every: int = 64, auto_regrow: bool = True):
+               check_every: int = 64, auto_regrow: bool = True, feature_format: str = 'bf16'):
     self.nat = require_native()
+    # 'mxfp8': `feature_table` holds data.quantize_mxfp8 rows (uint8, in_dim + 16 bytes); the fused layer-1 kernel
+    # de-quantises in its loaders (half the gather bytes), so the fused path is mandatory for that format
+    assert feature_format in ('bf16', 'mxfp8')
+    self.feature_format = feature_format
+    if feature_format == 'mxfp8':
+      assert int(in_dim) == 128, 'MXFP8 features: in_dim must be 128'
+      use_fused = True
     self.pipeline = bool(pipeline)
     self.use_peer_allreduce = bool(use_peer_allreduce)
     # use_gather_bwd (csrc/cuda/transpose.cu, validated on B200 in round 2): the sampler also builds the transposed
@@ -183,6 +190,8 @@ class GraphSageEngine(object):
       self.w_packed = [None] + [torch.zeros(self.dims_out[l - 1] * 2 * self.dims_in[l - 1], dtype=bf, device=dev)
                                 if self.fused_ok[l] else None for l in range(1, self.L + 1)]
       self._repack()
+      if self.feature_format == 'mxfp8' and not self.fused_ok[1]:
+        raise RuntimeError('MXFP8 features need the fused layer-1 kernel (in_dim 128, hidden multiple of 32, <= 256)')
     self._graph_fb = None
     self._graph_opt = None
     self._graph_full = None
@@ -468,7 +477,7 @@ class GraphSageEngine(object):
       self._begin_grads()
     # the bias gradient of the last layer (column sums of dlogits) is produced by the loss kernel
     nat.softmax_nll(self.Z[self.L], self.C, None, self.labels, ar.nodes, ar.counters, self.loss,
-                    self.dPre[self.L], self.correct, self.g32[boff:boff + n])
+                    self.dPre[self.L], self.correct, self.g32[boff:boff + n], train)
     self._k(1)
 
   def _begin_grads(self):
@@ -478,9 +487,10 @@ class GraphSageEngine(object):
     if self.peer_group is not None and len(self._peer_groups) == 1:
       self.peer_group.barrier(1)          # peers finished reading last step's gradients
       self._k(1)
-    if self.use_tc_gemm:
-      self.g32.zero_()
-      self._k(1)
+    # one launch zeroes the flat gradient buffer, the loss and the #correct counter; the kernels that accumulate
+    # into them then skip their own memsets (memset nodes would cut the programmatic-launch chain of the step)
+    self.nat.zero_grads(self.g32, self.loss, self.correct)
+    self._k(1)
 
   def _plan(self, kind: str, l: int):
     """Cached TcGemm launch for layer l of the current arena / gradient parity (tensor maps are encoded once)."""
@@ -531,7 +541,7 @@ class GraphSageEngine(object):
         nat.zero_rows(self.dH[l - 1], ar.counters, nh + 1)
         nat.sage_scatter_bwd(self.dA[l], self.dims_in[l - 1], ar.counters, nh, ell, ks, ar.deg, self.dH[l - 1])
         nat.relu_bwd_cast(self.dH[l - 1], self.Z[l - 1], ar.counters, nh + 1, self.dPre[l - 1],
-                          self.g32[pboff:pboff + pn])
+                          self.g32[pboff:pboff + pn], True)
         self._k(3)
 
   _f32_mode = None
