@@ -18,14 +18,48 @@ p.add_argument('--rows', type=int, default=2_449_029)
 p.add_argument('--dim', type=int, default=128)
 p.add_argument('--ids', type=int, default=400_000, help='rows gathered per lookup (~unique nodes of one batch)')
 p.add_argument('--iters', type=int, default=50)
+p.add_argument('--impl', default='ours', choices=['ours', 'reference'],
+               help="'reference': the unmodified reference (baseline/_ref) Feature on the same box")
 args = p.parse_args()
+if args.impl == 'reference':
+  ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  sys.path.insert(0, os.path.join(ROOT, 'baseline', 'shims'))
+  sys.path.insert(0, os.path.join(ROOT, 'baseline', '_ref'))
+  try:
+    import graphlearn_torch as rglt
+    dev = torch.device('cuda', 0)
+    results = []
+    for dtype in (torch.float32, torch.bfloat16):
+      full = torch.randn(args.rows, args.dim).to(dtype)
+      for ratio in (1.0, 0.2, 0.0):
+        feat = rglt.data.Feature(full, split_ratio=ratio, device_group_list=[rglt.data.DeviceGroup(0, [0])], device=0)
+        gen = torch.Generator(device=dev); gen.manual_seed(0)
+        ids = [torch.randint(0, args.rows, (args.ids,), device=dev, generator=gen) for _ in range(args.iters + 3)]
+        for i in ids[:3]:
+          feat[i]
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in ids[3:]:
+          out = feat[i]
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.iters
+        results.append({'dtype': str(dtype), 'split_ratio': ratio, 'ms': ms,
+                        'GB_per_s': out.numel() * out.element_size() / (ms / 1e3) / 2 ** 30})
+        del feat
+    print(json.dumps({'impl': 'reference', 'metric': 'feature lookup GB/s', 'rows_per_lookup': args.ids, 'dim': args.dim,
+                      'results': results}))
+  except Exception as ex:  # noqa: BLE001
+    print(json.dumps({'impl': 'reference', 'unavailable': f'{type(ex).__name__}: {str(ex)[:300]}'}))
+  sys.exit(0)
 dev = torch.device('cuda', 0)
 results = []
 for dtype in (torch.float32, torch.bfloat16):
   full = torch.randn(args.rows, args.dim).to(dtype)
   for ratio in (1.0, 0.2, 0.0):
     feat = glt.data.Feature(full, split_ratio=ratio, device=0, dtype=dtype)
-    ids = [torch.randint(0, args.rows, (args.ids,), device=dev) for _ in range(args.iters + 3)]
+    gen = torch.Generator(device=dev); gen.manual_seed(0)
+    ids = [torch.randint(0, args.rows, (args.ids,), device=dev, generator=gen) for _ in range(args.iters + 3)]
     for i in ids[:3]:
       feat[i]
     torch.cuda.synchronize()
@@ -38,5 +72,5 @@ for dtype in (torch.float32, torch.bfloat16):
     gbs = out.numel() * out.element_size() / (ms / 1e3) / 2 ** 30
     results.append({'dtype': str(dtype), 'split_ratio': ratio, 'ms': ms, 'GB_per_s': gbs})
     del feat
-print(json.dumps({'metric': 'feature lookup GB/s', 'rows_per_lookup': args.ids, 'dim': args.dim,
+print(json.dumps({'impl': 'ours', 'metric': 'feature lookup GB/s', 'rows_per_lookup': args.ids, 'dim': args.dim,
                   'results': results, 'reference_published_A100_GB_per_s_derived': 11.1}))

@@ -40,6 +40,7 @@ p.add_argument('--steps', type=int, default=30)
 p.add_argument('--warmup', type=int, default=3)
 p.add_argument('--model', default='rsage')
 p.add_argument('--cap-limit', type=int, default=1 << 21)
+p.add_argument('--device-gen', action='store_true', help='generate the graph / feature shards on the GPU')
 args = p.parse_args()
 rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
 local = int(os.environ.get('LOCAL_RANK', 0))
@@ -56,6 +57,39 @@ def igbh_graph():
   from common import synthetic_igbh
   return synthetic_igbh(args.papers, args.papers // 2, max(args.papers // 400, 8), max(args.papers // 1000, 8),
                         feat_dim=args.feat_dim, num_classes=args.classes)
+
+
+def igbh_graph_device():
+  """Same schema generated ON THE DEVICE for large shapes (>= millions of papers, multi-GPU): every rank draws the
+  same edge lists (same seed), features are generated per rank for its own row range only, labels are random
+  (throughput runs).  -> (edges on device, feature shard generator, labels, sizes)."""
+  n = {'paper': args.papers, 'author': args.papers // 2, 'institute': max(args.papers // 400, 8),
+       'fos': max(args.papers // 1000, 8)}
+  g = torch.Generator(device=dev)
+  g.manual_seed(0)
+
+  def rnd(ns, nd, e):
+    return torch.stack([torch.randint(0, ns, (e,), device=dev, generator=g),
+                        torch.randint(0, nd, (e,), device=dev, generator=g)])
+  cites = rnd(n['paper'], n['paper'], n['paper'] * 8)
+  written = rnd(n['paper'], n['author'], n['paper'] * 3)
+  affil = rnd(n['author'], n['institute'], n['author'] * 2)
+  topic = rnd(n['paper'], n['fos'], n['paper'] * 2)
+  edges = {('paper', 'cites', 'paper'): torch.cat([cites, cites.flip(0)], 1),
+           ('paper', 'written_by', 'author'): written, ('author', 'rev_written_by', 'paper'): written.flip(0),
+           ('author', 'affiliated_to', 'institute'): affil, ('institute', 'rev_affiliated_to', 'author'): affil.flip(0),
+           ('paper', 'topic', 'fos'): topic, ('fos', 'rev_topic', 'paper'): topic.flip(0)}
+
+  def feat_shard(nt, lo, hi):
+    gg = torch.Generator(device=dev)
+    gg.manual_seed(100 + rank * 7 + sorted(n).index(nt))
+    out = torch.empty(hi - lo, args.feat_dim, dtype=torch.bfloat16, device=dev)
+    for b0 in range(0, hi - lo, 1 << 20):
+      b1 = min(hi - lo, b0 + (1 << 20))
+      out[b0:b1] = torch.randn(b1 - b0, args.feat_dim, device=dev, generator=gg).to(torch.bfloat16)
+    return out
+  labels = {'paper': torch.randint(0, args.classes, (n['paper'],), device=dev, generator=g)}
+  return edges, feat_shard, labels, n
 
 
 def timed(step):
@@ -155,22 +189,31 @@ def run_ours():
   from graphlearn_for_pytorch_b200.models import RGNN, HeteroSageEngine
   from graphlearn_for_pytorch_b200.parallel import PartitionedFeature, partition_hetero_graph
   from graphlearn_for_pytorch_b200.sampler import NeighborSampler, NodeSamplerInput
-  edges, feats, labels, sizes = igbh_graph()
+  device_gen = args.device_gen or world > 1 or args.papers >= 2_000_000
+  if device_gen:
+    edges, feat_shard, labels, sizes = igbh_graph_device()
+  else:
+    edges, feats, labels, sizes = igbh_graph()
+    feat_shard = lambda nt, lo, hi: feats[nt][lo:hi].to(dev).to(torch.bfloat16)   # noqa: E731
   edge_dir = 'in'
-  topos = {et: glt.data.Topology(ei.to(dev), layout='CSC', num_nodes=sizes[et[2]]) for et, ei in edges.items()}
+  topos = {}
+  for et in list(edges):
+    topos[et] = glt.data.Topology(edges.pop(et).to(dev), layout='CSC', num_nodes=sizes[et[2]])
+  torch.cuda.empty_cache()
   if world > 1:
     graphs, bounds, keep = partition_hetero_graph(topos, sizes, rank, world, dev, edge_dir)
-    fstore = {nt: PartitionedFeature(feats[nt][bounds[nt][rank]:bounds[nt][rank + 1]].to(dev).to(torch.bfloat16),
-                                     bounds[nt], dev) for nt in sizes}
+    fstore = {nt: PartitionedFeature(feat_shard(nt, bounds[nt][rank], bounds[nt][rank + 1]), bounds[nt], dev)
+              for nt in sizes}
     tables = {nt: f.table for nt, f in fstore.items()}
   else:
     graphs = {et: glt.data.Graph(t, 'CUDA', local) for et, t in topos.items()}
     fstore, tables = {}, {}
     for nt in sizes:
       ut = glt.data.UnifiedTensor(local, torch.bfloat16)
-      ut.append_shared_tensor(feats[nt].to(dev).to(torch.bfloat16))
+      ut.append_shared_tensor(feat_shard(nt, 0, sizes[nt]))
       fstore[nt], tables[nt] = ut, ut._table()
   del topos
+  torch.cuda.empty_cache()
   y = labels['paper'].to(dev)
   pool = torch.randperm(args.papers, generator=torch.Generator().manual_seed(3))[rank::world].to(dev)
 

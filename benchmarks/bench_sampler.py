@@ -24,7 +24,42 @@ p.add_argument('--batch', type=int, default=1024)
 p.add_argument('--fanout', default='15,10,5')
 p.add_argument('--iters', type=int, default=100)
 p.add_argument('--mode', default='CUDA', choices=['CUDA', 'ZERO_COPY'])
+p.add_argument('--impl', default='ours', choices=['ours', 'reference'],
+               help="'reference': the unmodified reference (baseline/_ref) NeighborSampler on the same box and graph")
 args = p.parse_args()
+
+if args.impl == 'reference':
+  # reference benchmarks/api/bench_sampler.py:27-54, same synthetic graph, same seeds, device-timed
+  ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  sys.path.insert(0, os.path.join(ROOT, 'baseline', 'shims'))
+  sys.path.insert(0, os.path.join(ROOT, 'baseline', '_ref'))
+  try:
+    import graphlearn_torch as rglt
+    dev = torch.device('cuda', 0)
+    ei = rmat_edges(args.nodes, args.edges // 2, seed=0, device=dev)
+    ei = torch.cat([ei, ei.flip(0)], 1).cpu()
+    csr = rglt.data.Topology(ei, input_layout='COO')
+    g = rglt.data.Graph(csr, args.mode, 0)
+    fan = [int(v) for v in args.fanout.split(',')]
+    sampler = rglt.sampler.NeighborSampler(g, fan, device=dev)
+    gen = torch.Generator(device=dev); gen.manual_seed(0)
+    seeds = [torch.randint(0, args.nodes, (args.batch,), device=dev, generator=gen) for _ in range(args.iters + 5)]
+    for sd in seeds[:5]:
+      sampler.sample_from_nodes(sd)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    edges = 0
+    e0.record()
+    for sd in seeds[5:]:
+      edges += sampler.sample_from_nodes(sd).row.numel()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    print(json.dumps({'impl': 'reference', 'metric': 'sampled edges/s', 'graph_mode': args.mode, 'batch': args.batch,
+                      'fanout': fan, 'edges_per_batch': edges / args.iters, 'api_M_edges_per_s': edges / ms / 1e3,
+                      'api_ms_per_batch': ms / args.iters}))
+  except Exception as ex:  # noqa: BLE001
+    print(json.dumps({'impl': 'reference', 'unavailable': f'{type(ex).__name__}: {str(ex)[:300]}'}))
+  sys.exit(0)
 
 dev = torch.device('cuda', 0)
 ei = rmat_edges(args.nodes, args.edges // 2, seed=0, device=dev)
@@ -34,7 +69,8 @@ del ei
 graph = glt.data.Graph(topo, args.mode, 0)
 fan = [int(v) for v in args.fanout.split(',')]
 sampler = NeighborSampler(graph, fan, device=dev, seed=1)
-seeds = [torch.randint(0, args.nodes, (args.batch,), device=dev) for _ in range(args.iters + 5)]
+gen = torch.Generator(device=dev); gen.manual_seed(0)
+seeds = [torch.randint(0, args.nodes, (args.batch,), device=dev, generator=gen) for _ in range(args.iters + 5)]
 for s in seeds[:5]:
   sampler.sample_from_nodes(s)
 torch.cuda.synchronize()
@@ -52,7 +88,7 @@ for i, s in enumerate(seeds[5:]):
   arena.sample(h, s, None, 1, i * 8, False, False, False)
 e1.record(); torch.cuda.synchronize()
 arena_ms = e0.elapsed_time(e1)
-print(json.dumps({'metric': 'sampled edges/s', 'graph_mode': args.mode, 'batch': args.batch, 'fanout': fan,
+print(json.dumps({'impl': 'ours', 'metric': 'sampled edges/s', 'graph_mode': args.mode, 'batch': args.batch, 'fanout': fan,
                   'edges_per_batch': edges / args.iters,
                   'api_M_edges_per_s': edges / api_ms / 1e3, 'api_ms_per_batch': api_ms / args.iters,
                   'arena_M_edges_per_s': edges / arena_ms / 1e3, 'arena_ms_per_batch': arena_ms / args.iters,

@@ -15,9 +15,9 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import graphlearn_for_pytorch_b200 as glt  # noqa: E402
-from graphlearn_for_pytorch_b200.parallel import PartitionedGraph, range_bounds, shard_topology  # noqa: E402
+from graphlearn_for_pytorch_b200.parallel import PartitionedGraph, range_bounds  # noqa: E402
 from graphlearn_for_pytorch_b200.sampler import NeighborSampler, NodeSamplerInput, RandomNegativeSampler  # noqa: E402
-from graphlearn_for_pytorch_b200.utils.synthetic import rmat_edges  # noqa: E402
+from graphlearn_for_pytorch_b200.utils.synthetic import rmat_csr_shard  # noqa: E402
 
 p = argparse.ArgumentParser()
 p.add_argument('--nodes', type=int, default=10_000_000)
@@ -32,18 +32,18 @@ torch.cuda.set_device(local)
 dev = torch.device('cuda', local)
 if world > 1:
   dist.init_process_group('nccl', device_id=dev)
-ei = rmat_edges(args.nodes, args.edges, seed=0, device=dev)
-topo = glt.data.Topology(ei, layout='CSR', num_nodes=args.nodes)
-del ei
-if world > 1:
-  bounds = range_bounds(args.nodes, world)
-  pg = PartitionedGraph(shard_topology(topo, bounds, rank, dev), bounds, dev)
-  graph = pg.graph
-  graph._col_count = args.nodes
-else:
-  graph = glt.data.Graph(topo, 'CUDA', local)
-del topo
+# every rank streams the same RMAT edge sequence and keeps its own row range only (1 B directed edges never exist as
+# one edge list); `--edges` counts DIRECTED edges of the symmetrised graph like the other benchmarks
+bounds = range_bounds(args.nodes, world)
+shard = rmat_csr_shard(args.nodes, args.edges // 2, bounds[rank], bounds[rank + 1], seed=0, device=dev, undirected=True)
 torch.cuda.empty_cache()
+if world > 1:
+  pg = PartitionedGraph(shard, bounds, dev)
+  graph = pg.graph
+else:
+  graph = glt.data.Graph.from_shards([shard], local)
+graph._col_count = args.nodes
+local_edges = int(shard['indices'].numel())
 fan = [int(v) for v in args.fanout.split(',')]
 sampler = NeighborSampler(graph, fan, device=dev, with_edge=False, seed=1)
 neg = RandomNegativeSampler(graph, 'CUDA', seed=2)
@@ -80,7 +80,7 @@ ms_s, sub_edges = timed(sub, args.iters)
 ms_n, n_neg = timed(negs, args.iters)
 if rank == 0:
   print(json.dumps({'metric': 'SEAL subgraph + negative sampling', 'n_gpus': world, 'nodes': args.nodes,
-                    'edges': args.edges, 'links_per_s': args.iters * args.links * world / (ms_s / 1e3),
+                    'edges': args.edges, 'edges_on_rank0': local_edges, 'links_per_s': args.iters * args.links * world / (ms_s / 1e3),
                     'induced_edges_per_batch': sub_edges / args.iters, 'ms_per_subgraph_batch': ms_s / args.iters,
                     'strict_negatives_M_per_s': n_neg * world / ms_n / 1e3}))
 if world > 1:

@@ -349,6 +349,9 @@ struct SamplerArena {
     return BatchCounters{c, c + 6, table->cursor.data_ptr<int32_t>(), c + 12};
   }
 
+  bool deterministic = false;   // re-assign every hop's new local ids in ascending global-id order
+  Tensor det_tmp;
+
   void sample(GraphHandle& g, const Tensor& seeds, const c10::optional<Tensor>& n_dev, int64_t seed,
               int64_t stream_base, bool weighted, bool replace, bool use_dev_step, int64_t step_inc) {
     c10::cuda::CUDAGuard guard(device);
@@ -383,6 +386,13 @@ struct SamplerArena {
       a.stream = static_cast<uint32_t>(stream_base + h);
       a.stream_dev = use_dev_step ? step.data_ptr<int32_t>() : nullptr;
       launch_sample_hop(a, s);
+      if (deterministic) {
+        if (!det_tmp.defined())
+          det_tmp = torch::empty({cap_nodes}, torch::TensorOptions().dtype(torch::kInt64).device(torch::kCUDA, device));
+        launch_det_keys(a, det_tmp.data_ptr<int64_t>(), s);
+        Tensor sorted = std::get<0>(torch::sort(det_tmp));
+        launch_det_assign(a, sorted.data_ptr<int64_t>(), s);
+      }
       launch_relabel_hop(a, s);
     }
     if (tr_hops > 0) build_transpose(s);
@@ -1347,6 +1357,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def_readonly("seed_local", &SamplerArena::seed_local)
       .def_readonly("step", &SamplerArena::step)
       .def("enable_transpose", &SamplerArena::enable_transpose)
+      .def_readwrite("deterministic", &SamplerArena::deterministic)
       .def_readonly("tr_hops", &SamplerArena::tr_hops)
       .def_readonly("tr_off", &SamplerArena::tr_off)
       .def_readonly("tr_cnt", &SamplerArena::tr_cnt)
@@ -1398,6 +1409,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("relu_bwd_cast", &relu_bwd_cast, py::arg("dH"), py::arg("Z"), py::arg("counters"), py::arg("n_hops"),
         py::arg("dPre"), py::arg("colsum"), py::arg("prezeroed") = false);
   m.def("zero_grads", &zero_grads);
+  m.def("set_pdl", [](bool on) { return set_pdl(on ? 1 : 0) != 0; });
   m.def("sage_gather_bwd", &sage_gather_bwd);
   m.def("bias_relu", &bias_relu);
   m.def("softmax_nll", &softmax_nll, py::arg("logits"), py::arg("C"), py::arg("y"), py::arg("labels_all"),

@@ -92,6 +92,9 @@ struct HopArgs {
 };
 void launch_sample_hop(const HopArgs& a, cudaStream_t s);
 void launch_relabel_hop(const HopArgs& a, cudaStream_t s);
+// deterministic local-id order of a hop's new nodes (see sampling.cu): keys -> (caller sorts tmp) -> assign
+void launch_det_keys(const HopArgs& a, int64_t* tmp, cudaStream_t s);
+void launch_det_assign(const HopArgs& a, const int64_t* sorted, cudaStream_t s);
 
 // Heterogeneous sampling (native hetero inducer; reference csrc/cuda/inducer.cu:194-338 CUDAHeteroInducer +
 // python/sampler/neighbor_sampler.py:232-317): one GROUPED launch per hop over all relations.  `descs` is a
@@ -324,6 +327,8 @@ struct alignas(64) TcGemmLaunch {
 int make_tmap_bf16_2d(void* out_map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols,
                       int box_rows);
 size_t tc_gemm_smem_bytes();
+// programmatic-dependent-launch switch (launch_utils.h); returns the previous value
+int set_pdl(int on);
 void launch_tc_gemm(const TcGemmLaunch& L, int num_sms, cudaStream_t s);
 
 }  // namespace glt

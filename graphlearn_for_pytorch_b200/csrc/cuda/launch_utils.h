@@ -8,13 +8,12 @@
 
 namespace glt {
 
-inline bool pdl_enabled() {
-  static const bool on = [] {
-    const char* e = std::getenv("GLT_B200_PDL");
-    return e ? std::atoi(e) != 0 : true;
-  }();
-  return on;
-}
+// Process-wide switch (default: GLT_B200_PDL, on).  Read at every launch, so a caller can turn it off around the
+// capture of a CUDA graph: measured on B200, programmatic edges speed up single-stream chains (hetero engine, the
+// unpipelined step: -3 %) but cost ~2 % when two streams interleave kernels (sample || train), because early-launched
+// dependents hold SM slots that the other stream's kernels could have used.
+int& pdl_flag();
+inline bool pdl_enabled() { return pdl_flag() != 0; }
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,

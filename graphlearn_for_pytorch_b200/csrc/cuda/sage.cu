@@ -419,6 +419,14 @@ inline int grid_for(int64_t items, int per_block, int max_blocks = 148 * 16) {
 
 }  // namespace
 
+int& pdl_flag() {
+  static int flag = [] {
+    const char* e = std::getenv("GLT_B200_PDL");
+    return e ? (std::atoi(e) != 0 ? 1 : 0) : 1;
+  }();
+  return flag;
+}
+
 #define GLT_DISPATCH_WIDTH(D, ...)                                            \
   do {                                                                        \
     const int nvec_ = (D) / 8;                                                \
@@ -429,6 +437,12 @@ inline int grid_for(int64_t items, int per_block, int max_blocks = 148 * 16) {
     else if (nvec_ <= 64) { constexpr int LPR = 32, VPL = 2; __VA_ARGS__; }   \
     else { constexpr int LPR = 32, VPL = 4; __VA_ARGS__; }                    \
   } while (0)
+
+int set_pdl(int on) {
+  const int old = pdl_flag();
+  pdl_flag() = on ? 1 : 0;
+  return old;
+}
 
 void launch_sage_aggregate(const SageAggArgs& a, cudaStream_t s) {
   static const bool batched = [] {

@@ -273,6 +273,36 @@ __global__ void k_hetero_finalize(const HeteroTypeState* types, int n_types, int
   *ty.cursor = bound;
 }
 
+// ---- deterministic local-id order (opt-in) -------------------------------------------------------------
+// The sampling kernel hands out the local ids of a hop's NEW nodes with an atomic cursor, i.e. in arrival order,
+// which varies from run to run.  With the option on, the new ids of every hop are re-assigned in ascending
+// global-id order between the sampling and the relabel pass:
+//   k_det_keys    tmp[i] = nodes[i] for the hop's new range [cum[hop+1], min(cursor, cap)), +inf elsewhere
+//   (device sort of tmp; static size = arena capacity)
+//   k_det_assign  nodes[start + j] = sorted[j]; vals[slot(sorted[j])] = start + j
+// The relabel pass then maps slots to the new ids as usual.
+__global__ void k_det_keys(const int64_t* nodes, const int32_t* cum, const int32_t* cursor, int hop, int cap_nodes,
+                           int64_t* tmp) {
+  pdl_enter();
+  const int start = cum[hop + 1];
+  const int end = min(*cursor, cap_nodes);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cap_nodes; i += gridDim.x * blockDim.x)
+    tmp[i] = (i >= start && i < end) ? nodes[i] : INT64_MAX;
+}
+
+__global__ void k_det_assign(HashTable t, int64_t* nodes, const int32_t* cum, const int32_t* cursor, int hop,
+                             int cap_nodes, const int64_t* sorted) {
+  pdl_enter();
+  const int start = cum[hop + 1];
+  const int n_new = min(*cursor, cap_nodes) - start;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_new; j += gridDim.x * blockDim.x) {
+    const int64_t key = sorted[j];
+    nodes[start + j] = key;
+    const int32_t slot = table_find_slot(t, key);
+    if (slot >= 0) t.vals[slot] = start + j;
+  }
+}
+
 // Ordered (first-occurrence) seed insertion; single CTA, seeds are few.
 __global__ void __launch_bounds__(1024) k_init_seeds(const int64_t* seeds, int n_host,
                                                      const int32_t* n_dev, HashTable t,
@@ -501,6 +531,16 @@ void launch_sample_hop(const HopArgs& a, cudaStream_t s) {
     else if ((K) <= 16) { constexpr int G = 16; __VA_ARGS__; } \
     else { constexpr int G = 32; __VA_ARGS__; }          \
   } while (0)
+
+void launch_det_keys(const HopArgs& a, int64_t* tmp, cudaStream_t s) {
+  launch_k(k_det_keys, dim3(grid_for(a.cap_nodes, 256)), dim3(256), 0, s, static_cast<const int64_t*>(a.nodes),
+           static_cast<const int32_t*>(a.c.cum), static_cast<const int32_t*>(a.c.cursor), a.hop, a.cap_nodes, tmp);
+}
+
+void launch_det_assign(const HopArgs& a, const int64_t* sorted, cudaStream_t s) {
+  launch_k(k_det_assign, dim3(grid_for(a.cap_rows_next, 256)), dim3(256), 0, s, a.t, a.nodes,
+           static_cast<const int32_t*>(a.c.cum), static_cast<const int32_t*>(a.c.cursor), a.hop, a.cap_nodes, sorted);
+}
 
 void launch_relabel_hop(const HopArgs& a, cudaStream_t s) {
   GLT_DISPATCH_GROUP(a.k, {

@@ -162,7 +162,7 @@ inline int grid_for(int64_t items, int per_block, int max_blocks = 148 * 16) {
 
 // ------------------------------------------------------------------------------------------
 template <int LPR, int VPL>
-__global__ void __launch_bounds__(256, 2) k_sage_gather_bwd(SageGatherBwdArgs a) {
+__global__ void __launch_bounds__(256) k_sage_gather_bwd(SageGatherBwdArgs a) {
   extern __shared__ float s_col[];  // [d] block partial of the bias gradient
   constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31;
@@ -297,19 +297,19 @@ void launch_build_transpose(const TransposeArgs& a, cudaStream_t s) {
     k_tr_fill<<<grid_for(static_cast<int64_t>(a.cap_rows[h]) * a.k[h], 256 * 4), 256, 0, s>>>(a, h);
 }
 
-// Lane-group width of the gather backward.  Most source rows have one or two incoming edges, so a row is a chain
-// of dependent loads (segment extent -> target id -> target degree -> gradient row) with very little streaming:
-// the kernel is latency bound and wants MANY ROWS in flight per warp rather than wide rows.  8 lanes x up to 4
-// vectors per lane keeps 4 rows per warp in flight for the 256-wide hidden layers (measured with 32 lanes per
-// row: 65 us for 54 k rows, twice the atomics path it was meant to replace).
+// Lane-group width of the gather backward.  Measured on B200 (products shape, 54 k source rows x 256, 66 k in-edges):
+// 32 lanes per row = 65 us for the layer-2 launch; 8 lanes x 4 vectors (4 rows per warp in flight) was slower still
+// (pipelined step 0.435 ms vs 0.268 ms), as was accumulating the bias column sums with shared-memory atomics.  The
+// fp32-atomic scatter path (zero_rows + sage_scatter_bwd + relu_bwd_cast = 39 us for the same layer) therefore stays
+// the engine default; this kernel is kept, tested, behind use_gather_bwd / GLT_B200_GATHER_BWD=1.
 #define GLT_DISPATCH_WIDTH_T(D, ...)                                          \
   do {                                                                        \
     const int nvec_ = (D) / 8;                                                \
     if (nvec_ <= 4) { constexpr int LPR = 4, VPL = 1; __VA_ARGS__; }          \
     else if (nvec_ <= 8) { constexpr int LPR = 8, VPL = 1; __VA_ARGS__; }     \
-    else if (nvec_ <= 16) { constexpr int LPR = 8, VPL = 2; __VA_ARGS__; }    \
-    else if (nvec_ <= 32) { constexpr int LPR = 8, VPL = 4; __VA_ARGS__; }    \
-    else if (nvec_ <= 64) { constexpr int LPR = 16, VPL = 4; __VA_ARGS__; }   \
+    else if (nvec_ <= 16) { constexpr int LPR = 16, VPL = 1; __VA_ARGS__; }   \
+    else if (nvec_ <= 32) { constexpr int LPR = 32, VPL = 1; __VA_ARGS__; }   \
+    else if (nvec_ <= 64) { constexpr int LPR = 32, VPL = 2; __VA_ARGS__; }   \
     else { constexpr int LPR = 32, VPL = 4; __VA_ARGS__; }                    \
   } while (0)
 

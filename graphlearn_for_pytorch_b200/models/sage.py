@@ -108,7 +108,8 @@ class GraphSageEngine(object):
                use_cuda_graph: bool = True, calibration_seeds: Optional[torch.Tensor] = None,
                calibration_margin: float = 1.3, calibration_batches: int = 16, pipeline: bool = False,
                use_peer_allreduce: bool = True, use_gather_bwd: Optional[bool] = None,
-               check_every: int = 64, auto_regrow: bool = True, feature_format: str = 'bf16'):
+               check_every: int = 64, auto_regrow: bool = True, feature_format: str = 'bf16',
+               deterministic_sampling: bool = False):
     self.nat = require_native()
     # 'mxfp8': `feature_table` holds data.quantize_mxfp8 rows (uint8, in_dim + 16 bytes); the fused layer-1 kernel
     # de-quantises in its loaders (half the gather bytes), so the fused path is mandatory for that format
@@ -118,6 +119,7 @@ class GraphSageEngine(object):
       assert int(in_dim) == 128, 'MXFP8 features: in_dim must be 128'
       use_fused = True
     self.pipeline = bool(pipeline)
+    self.deterministic_sampling = bool(deterministic_sampling)
     self.use_peer_allreduce = bool(use_peer_allreduce)
     # use_gather_bwd (csrc/cuda/transpose.cu, validated on B200 in round 2): the sampler also builds the transposed
     # adjacency of the batch and the backward of the aggregation becomes an atomics-free gather (replaces zero_rows +
@@ -211,6 +213,7 @@ class GraphSageEngine(object):
     self._cur = 0
     for p_, ar_ in enumerate(self._arenas):
       ar_.step.fill_(p_ - n_arenas)          # disjoint Philox stream ids per arena
+      ar_.deterministic = self.deterministic_sampling   # local ids of a hop in ascending global-id order
       if self.use_gather_bwd and self.L >= 2:
         ar_.enable_transpose(self.L - 1)     # layer 2 uses hops 0..L-2, deeper layers a prefix of them
     self.cap_rows = list(self.arena.cap_rows)           # frontier capacity per hop (+ last-hop additions)
@@ -670,6 +673,9 @@ class GraphSageEngine(object):
       self._graphs = []
       if not self.use_cuda_graph:
         return
+      # programmatic dependent launch helps single-stream chains and costs ~2 % when the sampling and training
+      # streams interleave (measured, csrc/cuda/launch_utils.h): captured without it in pipelined mode
+      prev_pdl = self.nat.set_pdl(not self.pipeline) if hasattr(self.nat, 'set_pdl') else None
       # capturing NCCL collectives works but makes process-group teardown hang on this stack
       # (measured: bench exit blocked until the timeout), so it is opt-in for world > 1
       single = self.world == 1 or self.peer_group is not None or \
@@ -693,6 +699,8 @@ class GraphSageEngine(object):
             self._optimizer()
         self._graphs.append((g, None if single else g_opt))
       torch.cuda.synchronize()
+      if prev_pdl is not None:
+        self.nat.set_pdl(prev_pdl)
       self.load_state_dict(saved)
       self._cur, self._primed = 0, False
       self._graph_fb = self._graphs[0][0]

@@ -44,8 +44,12 @@ class NeighborSampler(BaseSampler):
   def __init__(self, graph: Union[Graph, Dict[EdgeType, Graph]], num_neighbors: Optional[NumNeighbors] = None,
                device: Optional[torch.device] = None, with_edge: bool = False, with_neg: bool = False,
                with_weight: bool = False, strategy: str = 'random', edge_dir: str = 'out',
-               seed: Optional[int] = None, replace: bool = False):
+               seed: Optional[int] = None, replace: bool = False, deterministic: bool = False):
     self.graph = graph
+    # deterministic=True: the GPU arena re-assigns the local ids of every hop's new nodes in ascending global-id
+    # order (one device sort per hop), so two runs with the same seed return identical tensors, not just identical
+    # sets (default: arrival order of the sampling warps)
+    self.deterministic = bool(deterministic)
     self.num_neighbors = num_neighbors
     self.with_edge = with_edge
     self.with_neg = with_neg
@@ -199,6 +203,7 @@ class NeighborSampler(BaseSampler):
       n_nodes = max(self.graph.row_count, self.graph.col_count)
       self._arena = self._nat.SamplerArena(self.device.index, cap, list(self.num_neighbors),
                                            self.with_edge, int(n_nodes))
+      self._arena.deterministic = self.deterministic
       self._arena_key = key
     return self._arena
 

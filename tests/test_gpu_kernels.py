@@ -338,3 +338,26 @@ def test_hetero_arena_igbh_shape_matches_cpu_sampler(native):
       assert int(seg_c.max()) < sum(b.num_sampled_nodes[dt][:h + 1])       # targets: frontier of hop h
       assert int(seg_r.max()) < sum(b.num_sampled_nodes[st][:h + 2])       # sources: known after hop h
       off += n_e
+
+
+def test_deterministic_local_id_order(native):
+  """deterministic=True: the local ids of every hop's new nodes are assigned in ascending global-id order, so two
+  independent samplers with the same seed return IDENTICAL tensors (node order, COO), and every hop's slice of
+  `node` is sorted; the sampled structure still equals the CPU sampler's."""
+  ei, topo = rmat_csr(20000, 400000, seed=7)
+  seeds = torch.randperm(20000)[:700]
+  outs = []
+  for _ in range(2):
+    g = glt.data.Graph(topo, 'CUDA', 0)
+    s = NeighborSampler(g, [7, 5, 3], device=DEV, seed=11, deterministic=True)
+    outs.append([s.sample_from_nodes(NodeSamplerInput(seeds)) for _ in range(2)])
+  for a, b in zip(outs[0], outs[1]):
+    assert torch.equal(a.node, b.node) and torch.equal(a.row, b.row) and torch.equal(a.col, b.col)
+    off = a.num_sampled_nodes[0]
+    for n in a.num_sampled_nodes[1:]:
+      seg = a.node[off:off + n]
+      assert bool((seg[1:] > seg[:-1]).all())
+      off += n
+  cpu = NeighborSampler(glt.data.Graph(topo, 'CPU'), [7, 5, 3], seed=11).sample_from_nodes(NodeSamplerInput(seeds))
+  a = outs[0][0]
+  assert canonical_edges(cpu) == canonical_edges(a)
