@@ -1134,6 +1134,63 @@ struct TcGemm {
   }
 };
 
+
+// ---------------------------------------------------------------------------
+// TcGemmMx: block-scaled MXFP8 forward GEMM (csrc/cuda/tc_gemm_mx.cu).  A / W are e4m3 bytes [rows, K]; sfa / sfb are
+// the UE8M0 scales packed into the tensor core's 512-byte block layout (data/quantize.py pack_mx_scale_blocks).
+// ---------------------------------------------------------------------------
+struct TcGemmMx {
+  alignas(64) unsigned char maps[3][128];
+  TcMxArgs a{};
+  int device;
+  std::vector<Tensor> keep;
+  TcGemmMx(int dev, const Tensor& A, const Tensor& sfa, const Tensor& W, const Tensor& sfb,
+           const c10::optional<Tensor>& bias, bool relu, Tensor Z, const c10::optional<Tensor>& counters,
+           int64_t dyn_idx) : device(dev) {
+    c10::cuda::CUDAGuard guard(static_cast<c10::DeviceIndex>(dev));
+    auto ok8 = [](const Tensor& t) {
+      return t.is_cuda() && t.scalar_type() == torch::kUInt8 && t.dim() == 2 && t.stride(1) == 1 && t.stride(0) % 16 == 0 &&
+             reinterpret_cast<uintptr_t>(t.data_ptr()) % 16 == 0;
+    };
+    TORCH_CHECK(ok8(A) && ok8(W), "TcGemmMx: A / W must be uint8 (e4m3) [rows, K] CUDA tensors, 16-byte aligned rows");
+    const int64_t M = A.size(0), K = A.size(1), N = W.size(0);
+    TORCH_CHECK(W.size(1) == K && K % 128 == 0 && N % 128 == 0 && M >= 128, "TcGemmMx: K, N multiples of 128, M >= 128");
+    TORCH_CHECK(Z.is_cuda() && Z.scalar_type() == torch::kBFloat16 && Z.dim() == 2 && Z.size(0) >= M && Z.size(1) == N &&
+                Z.stride(1) == 1);
+    const int64_t mb = (M + 127) / 128, kb = K / 128;
+    TORCH_CHECK(sfa.is_cuda() && sfa.scalar_type() == torch::kUInt8 && sfa.is_contiguous() && sfa.numel() == mb * kb * 512,
+                "TcGemmMx: sfa must hold ceil(M/128) * K/128 blocks of 512 bytes");
+    TORCH_CHECK(sfb.is_cuda() && sfb.scalar_type() == torch::kUInt8 && sfb.is_contiguous() && sfb.numel() == (N / 128) * kb * 512,
+                "TcGemmMx: sfb must hold N/128 * K/128 blocks of 512 bytes");
+    a.m = M; a.n = N; a.k = K;
+    a.bn = N % 256 == 0 ? 256 : 128;
+    a.dyn = nullptr; a.dyn_idx = 0;
+    if (counters.has_value() && counters->defined()) {
+      TORCH_CHECK(counters->scalar_type() == torch::kInt32 && dyn_idx >= 0 && dyn_idx < counters->numel());
+      a.dyn = counters->data_ptr<int32_t>();
+      a.dyn_idx = static_cast<int>(dyn_idx);
+      keep.push_back(*counters);
+    }
+    a.sfa = sfa.data_ptr(); a.sfb = sfb.data_ptr();
+    a.bias = nullptr;
+    if (bias.has_value() && bias->defined()) {
+      TORCH_CHECK(bias->scalar_type() == torch::kBFloat16 && bias->numel() == N);
+      a.bias = bias->data_ptr();
+      keep.push_back(*bias);
+    }
+    a.relu = relu ? 1 : 0;
+    TORCH_CHECK(make_tmap_u8_2d(maps[0], A.data_ptr(), M, K, A.stride(0), 128, 128) == 0, "tensor map A");
+    TORCH_CHECK(make_tmap_u8_2d(maps[1], W.data_ptr(), N, K, W.stride(0), 128, a.bn) == 0, "tensor map W");
+    TORCH_CHECK(make_tmap_bf16_2d(maps[2], Z.data_ptr(), Z.size(0), N, Z.stride(0), 64, 128) == 0, "tensor map Z");
+    keep.insert(keep.end(), {A, sfa, W, sfb, Z});
+  }
+  void run() {
+    c10::cuda::CUDAGuard guard(static_cast<c10::DeviceIndex>(device));
+    launch_tc_gemm_mx(maps, a, at::cuda::getCurrentDeviceProperties()->multiProcessorCount, cur_stream());
+    check_cuda_err("tc_gemm_mx");
+  }
+};
+
 static void enable_peer_access(int dev, int peer) {
   if (dev == peer) return;
   c10::cuda::CUDAGuard guard(dev);
@@ -1440,6 +1497,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("adam", &PeerGroup::adam)
       .def_readonly("err", &PeerGroup::err)
       .def_readonly("epoch", &PeerGroup::epoch);
+  py::class_<TcGemmMx>(m, "TcGemmMx")
+      .def(py::init<int, const Tensor&, const Tensor&, const Tensor&, const Tensor&, const c10::optional<Tensor>&, bool,
+                    Tensor, const c10::optional<Tensor>&, int64_t>(),
+           py::arg("device"), py::arg("A"), py::arg("sfa"), py::arg("W"), py::arg("sfb"), py::arg("bias") = py::none(),
+           py::arg("relu") = false, py::arg("Z"), py::arg("counters") = py::none(), py::arg("dyn_idx") = 0)
+      .def("run", &TcGemmMx::run);
   py::class_<TcGemm>(m, "TcGemm")
       .def(py::init<int>())
       .def("add_forward", &TcGemm::add_forward)

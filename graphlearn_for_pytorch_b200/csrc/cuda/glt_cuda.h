@@ -326,7 +326,23 @@ struct alignas(64) TcGemmLaunch {
 // Returns 0 on success (1: driver entry point unavailable, 2: encode failed).
 int make_tmap_bf16_2d(void* out_map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols,
                       int box_rows);
+// uint8 (e4m3) [rows, cols] row-major tensor map with a {box_cols = 128 bytes, box_rows} SWIZZLE_128B box
+int make_tmap_u8_2d(void* out_map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols,
+                    int box_rows);
 size_t tc_gemm_smem_bytes();
+
+// ---- tc_gemm_mx.cu (block-scaled MXFP8 forward GEMM, tcgen05.mma.kind::mxf8f6f4.block_scale) -----------------
+struct TcMxArgs {
+  int m, n, k;              // rows of A (capacity), rows of W, contraction length (multiple of 128)
+  int bn;                   // 128 or 256, divides n
+  const int32_t* dyn;       // optional device counter for the valid rows of A
+  int dyn_idx;
+  const void* sfa;          // packed UE8M0 scale blocks of A: [ceil(m/128)][k/128][512 B]
+  const void* sfb;          // packed UE8M0 scale blocks of W: [n/128][k/128][512 B]
+  const void* bias;         // bf16 [n] or nullptr
+  int relu;
+};
+void launch_tc_gemm_mx(const void* maps3, const TcMxArgs& a, int num_sms, cudaStream_t s);
 // programmatic-dependent-launch switch (launch_utils.h); returns the previous value
 int set_pdl(int on);
 void launch_tc_gemm(const TcGemmLaunch& L, int num_sms, cudaStream_t s);

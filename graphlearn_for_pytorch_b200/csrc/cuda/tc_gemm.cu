@@ -340,6 +340,21 @@ int make_tmap_bf16_2d(void* out_map, const void* base, int64_t rows, int64_t col
   return r == CUDA_SUCCESS ? 0 : 2;
 }
 
+int make_tmap_u8_2d(void* out_map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols,
+                    int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return 1;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(reinterpret_cast<CUtensorMap*>(out_map), CU_TENSOR_MAP_DATA_TYPE_UINT8, 2,
+                        const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 2;
+}
+
 size_t tc_gemm_smem_bytes() { return kGemmSmem; }
 
 void launch_tc_gemm(const TcGemmLaunch& L, int num_sms, cudaStream_t s) {

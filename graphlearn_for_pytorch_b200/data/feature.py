@@ -70,14 +70,16 @@ class Feature(object):
     return out if len(tail) == 1 else out.view(ids.numel(), *tail)
 
   def cpu_get(self, ids: torch.Tensor) -> torch.Tensor:
-    """Host-side lookup (used by the RPC callee in multi-node mode)."""
+    """Host-side lookup (used by the RPC callee in multi-node mode).  When the host copy of the tensor was
+    released (a consumer process that only received the GPU shards + the cold host part over IPC), the rows are
+    gathered through the unified table on the device and copied back."""
     ids = ids.to('cpu', dtype=torch.int64)
-    idx = self.id2index[ids] if self.id2index is not None else ids
-    src = self.feature_tensor if self.feature_tensor is not None else self._cpu_full()
-    return src[idx]
-
-  def _cpu_full(self):
-    raise RuntimeError('host copy of the feature tensor was released; use __getitem__')
+    if self.feature_tensor is not None:
+      idx = self.id2index[ids] if self.id2index is not None else ids
+      return self.feature_tensor[idx]
+    if not self.with_gpu:
+      raise RuntimeError('feature tensor is not available in this process')
+    return self.__getitem__(ids).cpu()
 
   # ------------------------------------------------------------------ init
   def _check_and_set_device(self):

@@ -119,6 +119,8 @@ class GraphSageEngine(object):
       assert int(in_dim) == 128, 'MXFP8 features: in_dim must be 128'
       use_fused = True
     self.pipeline = bool(pipeline)
+    import os as _os3
+    self.overlap_wgrad = _os3.environ.get('GLT_B200_OVERLAP_WGRAD', '1') != '0'
     self.deterministic_sampling = bool(deterministic_sampling)
     self.use_peer_allreduce = bool(use_peer_allreduce)
     # use_gather_bwd (csrc/cuda/transpose.cu, validated on B200 in round 2): the sampler also builds the transposed
@@ -178,6 +180,7 @@ class GraphSageEngine(object):
       n_arenas = len(self._arenas)
       self._seeds = [torch.zeros(self.bs, dtype=torch.int64, device=dev) for _ in range(n_arenas)]
       self._side = torch.cuda.Stream(device=dev) if self.pipeline else None
+      self._aux = torch.cuda.Stream(device=dev)      # weight gradients + zero fills, off the critical chain
       self._primed = False
       self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
       self.correct = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -509,22 +512,56 @@ class GraphSageEngine(object):
     else:
       off, n, k = self._w_off[l - 1]
       gW = self.g32[off:off + n * k].view(n, k)
-      # dW (split-K over the batch rows, fp32 red-add) and dA of the same layer share one launch
-      pl.add_wgrad(self.dPre[l], self.A[l], gW, ar.counters, nh)
-      if l > 1:
+      # 'bwd': dW (split-K over the batch rows, fp32 red-add) and dA of the same layer share one launch;
+      # 'wgrad' / 'dgrad': the two halves as separate launches (overlap_wgrad: dW leaves the critical chain)
+      if kind in ('bwd', 'wgrad'):
+        pl.add_wgrad(self.dPre[l], self.A[l], gW, ar.counters, nh)
+      if l > 1 and kind in ('bwd', 'dgrad'):
         pl.add_dgrad(self.dPre[l], self.W(l), self.dA[l], ar.counters, nh)
     self._tc_plans[key] = pl
     return pl
 
   def _backward(self):
     nat, ar = self.nat, self.arena
+    overlap = self.overlap_wgrad and self.use_tc_gemm and not self.use_gather_bwd and self.L > 1
+    main = torch.cuda.current_stream()
+    if overlap:
+      # Only dA -> scatter -> ReLU-mask feeds the next layer; the weight gradients are consumed by Adam alone.  They
+      # run on an auxiliary stream (forked after dPre[l] exists, joined before the optimizer) together with the
+      # zero-fill of the fp32 scatter targets, so the critical chain per layer is dgrad -> scatter -> cast.
+      aux = self._aux
+      aux.wait_stream(main)
+      with torch.cuda.stream(aux):
+        for l in range(self.L, 1, -1):
+          nat.zero_rows(self.dH[l - 1], ar.counters, self.L - l + 2)
+        self._k(self.L - 1)
+      ev_zero = torch.cuda.Event()
+      ev_zero.record(aux)
     for l in range(self.L, 0, -1):
       ell, ks, nh = self._ell(l)
       off, n, k = self._w_off[l - 1]
       boff, _ = self._b_off[l - 1]
+      if overlap and l > 1:
+        ev = torch.cuda.Event()
+        ev.record(main)                     # dPre[l] (and everything before it) is complete
+        with torch.cuda.stream(aux):
+          aux.wait_event(ev)
+          self._plan('wgrad', l).run()
+        self._plan('dgrad', l).run()
+        self._k(2)
+        pboff, pn = self._b_off[l - 2]
+        if l == self.L:
+          main.wait_event(ev_zero)
+        nat.sage_scatter_bwd(self.dA[l], self.dims_in[l - 1], ar.counters, nh, ell, ks, ar.deg, self.dH[l - 1])
+        nat.relu_bwd_cast(self.dH[l - 1], self.Z[l - 1], ar.counters, nh + 1, self.dPre[l - 1],
+                          self.g32[pboff:pboff + pn], True)
+        self._k(2)
+        continue
       if self.use_tc_gemm:
-        self._plan('bwd', l).run()
+        self._plan('wgrad' if overlap else 'bwd', l).run()
         self._k(1)
+        if overlap:
+          main.wait_stream(aux)             # join: every weight gradient is in the flat buffer
       else:
         gW = self.g32[off:off + n * k].view(n, k)
         # dW = dPre^T A accumulated in fp32 straight into the flat gradient buffer

@@ -138,3 +138,30 @@ def test_tc_gemm_inside_cuda_graph(native):
   torch.cuda.synchronize()
   ref = A.float() @ W.float().t()
   assert torch.allclose(Z.float(), ref, rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize('M,T,K,N,relu', [(512, 512, 256, 256, False), (1000, 900, 512, 128, True), (4096, 4000, 1024, 512, False)])
+def test_tc_block_scaled_mxfp8_gemm_matches_dequantised_fp32(native, M, T, K, N, relu):
+  """tcgen05.mma.kind::mxf8f6f4.block_scale: e4m3 operands with UE8M0 scales per 32 K-elements; the result must
+  equal the fp32 product of the DE-QUANTISED operands (the quantisation error itself is not part of the kernel)."""
+  from graphlearn_for_pytorch_b200.data import dequantize_mxfp8, pack_mx_scale_blocks, quantize_mxfp8, quantize_mxfp8_parts
+  dev = torch.device('cuda', 0)
+  g = torch.Generator(device=dev); g.manual_seed(5)
+  A = torch.randn(M, K, device=dev, generator=g) * (0.1 + 4 * torch.rand(M, 1, device=dev, generator=g))
+  W = torch.randn(N, K, device=dev, generator=g) * 0.05
+  b = _rand((N,), dev, seed=9)
+  Aq, Asf = quantize_mxfp8_parts(A)
+  Wq, Wsf = quantize_mxfp8_parts(W)
+  Ad = dequantize_mxfp8(quantize_mxfp8(A), K)
+  Wd = dequantize_mxfp8(quantize_mxfp8(W), K)
+  Z = torch.full((M, N), 7.0, dtype=torch.bfloat16, device=dev)
+  c = _counters(dev, 1, T)
+  pl = native.TcGemmMx(0, Aq, pack_mx_scale_blocks(Asf), Wq, pack_mx_scale_blocks(Wsf), b, relu, Z, c, 1)
+  pl.run()
+  torch.cuda.synchronize()
+  ref = Ad[:T] @ Wd.t() + b.float()
+  if relu:
+    ref = ref.relu()
+  err = float((Z[:T].float() - ref).abs().max())
+  scale = max(1.0, float(ref.abs().max()))
+  assert err <= 1.5e-2 * scale, (err, scale)

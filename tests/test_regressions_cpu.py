@@ -68,3 +68,48 @@ def test_graph_cache_without_eids_loads(glt, tmp_path):
   torch.save(torch.tensor([1, 2, 0]), d / 'cols.pt')
   g = load_graph_partition_data(str(d), torch.device('cpu'))
   assert torch.equal(g.eids, torch.arange(3))
+
+
+def test_streamed_rmat_shard_equals_full_build(glt):
+  """utils.synthetic.rmat_csr_shard / rmat_degrees (used by bench.py for papers100M-shape graphs) reproduce the rows
+  of the full COO -> CSR build without materialising the edge list, with and without an id relabelling."""
+  from graphlearn_for_pytorch_b200.parallel import hotness_balanced_order
+  from graphlearn_for_pytorch_b200.utils.synthetic import rmat_csr_shard, rmat_degrees, rmat_edges
+  N, E = 3000, 25000
+  ei = rmat_edges(N, E, seed=3)
+  full = torch.cat([ei, ei.flip(0)], 1)
+  deg = rmat_degrees(N, E, seed=3)
+  assert torch.equal(deg, torch.bincount(full[0], minlength=N))
+  old2new, bounds = hotness_balanced_order(deg, 3)
+  for relabel in (None, old2new):
+    edges = full if relabel is None else relabel[full]
+    topo = glt.data.Topology(edges, layout='CSR', num_nodes=N)
+    b = [0, 1000, 2000, 3000] if relabel is None else bounds
+    for r in range(3):
+      sh = rmat_csr_shard(N, E, b[r], b[r + 1], seed=3, old2new=relabel)
+      lo, hi = int(topo.indptr[b[r]]), int(topo.indptr[b[r + 1]])
+      assert torch.equal(sh['indptr'], topo.indptr[b[r]:b[r + 1] + 1] - lo)
+      assert torch.equal(sh['indices'].long(), topo.indices[lo:hi])
+
+
+def test_mxfp8_quantiser_roundtrip_and_layout():
+  from graphlearn_for_pytorch_b200.data import dequantize_mxfp8, mxfp8_row_bytes, quantize_mxfp8
+  g = torch.Generator().manual_seed(0)
+  x = torch.randn(500, 128, generator=g) * (0.01 + 10 * torch.rand(500, 1, generator=g))
+  x[7] = 0
+  q = quantize_mxfp8(x)
+  assert q.dtype == torch.uint8 and q.shape == (500, mxfp8_row_bytes(128)) and mxfp8_row_bytes(128) == 144
+  assert bool((q[:, 132:] == 0).all())                       # padding bytes
+  y = dequantize_mxfp8(q, 128)
+  assert float(y[7].abs().max()) == 0.0
+  # e4m3 keeps 3 mantissa bits: every element is within 2^-4 of its block maximum
+  blk = x.view(500, 4, 32)
+  err = (y.view(500, 4, 32) - blk).abs() / blk.abs().amax(2, keepdim=True).clamp(min=1e-30)
+  assert float(err.max()) <= 0.0625 + 1e-6
+  # scales are powers of two chosen as the smallest that keep the block inside +-448
+  e = q[:, 128:132].float() - 127
+  amax = blk.abs().amax(2)
+  ok = amax > 0
+  assert bool(((amax / torch.exp2(e))[ok] <= 448.0).all()) and bool(((amax / torch.exp2(e - 1))[ok] > 448.0).all())
+  # bf16 input quantises like its fp32 value
+  assert torch.equal(quantize_mxfp8(x.to(torch.bfloat16)), quantize_mxfp8(x.to(torch.bfloat16).float()))

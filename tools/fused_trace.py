@@ -1,6 +1,8 @@
 """In-situ timeline of the fused layer-1 kernel (GLT_B200_FUSED_TRACE=1).
 
   GLT_B200_FUSED_TRACE=1 python tools/fused_trace.py [--steps 30] > profiles/fused_trace.txt
+  GLT_B200_FUSED_TRACE=1 python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 \
+      tools/fused_trace.py --gpus 8 > profiles/fused_trace_8gpu.txt        # rows resolved over NVLink: rank 0's timeline
 
 Runs the bench engine (pipelined, CUDA graphs, a different seed batch every step, i.e. the real
 cache state), then reads the per-CTA clock64 stamps written by the last launch and prints, per tile
@@ -25,9 +27,9 @@ def main():
   a, rest = ap.parse_known_args()
   sys.argv = [sys.argv[0]] + rest + ['--fused', 'on']
   args = bench.parse_args()
-  device = torch.device('cuda', 0)
-  torch.cuda.set_device(device)
-  eng, pool = bench.build_ours(args, 0, 1, device)
+  rank, world, local_rank = bench.setup_dist(args)
+  device = torch.device('cuda', local_rank)
+  eng, pool = bench.build_ours(args, rank, world, device)
   eng.warmup_and_capture(n_eager=2)
   bs = args.batch
   nb = pool.numel() // bs
@@ -37,6 +39,15 @@ def main():
   torch.cuda.synchronize()
   from graphlearn_for_pytorch_b200.ops import require_native
   tr = require_native().sage_fused_trace().double()
+  if world > 1:
+    import torch.distributed as dist
+    dist.barrier()
+  if rank != 0:
+    eng.close()
+    if world > 1:
+      os._exit(0)
+    return
+  print(f'# fused layer-1 kernel timeline, rank 0 of {world} GPU(s) (remote rows are read from peer HBM over NVLink)')
   start = tr[:, 0:1]
   used = tr[:, 0] > 0
   rel = (tr - start) / a.mhz  # us
@@ -54,6 +65,9 @@ def main():
         row.append(f'{n} {v.mean():.2f}/{v.max():.2f}')
       print(f'   tile {i}: ' + ' | '.join(row))
   eng.close()
+  if world > 1:
+    sys.stdout.flush()
+    os._exit(0)
 
 
 if __name__ == '__main__':
