@@ -46,7 +46,8 @@ def _sage_model(torch, in_dim, hidden, out_dim):
       agg.index_add_(0, dst, xs[src])
       deg = torch.zeros(x_dst.shape[0], dtype=torch.float32, device=xs.device)
       deg.index_add_(0, dst, torch.ones_like(dst, dtype=torch.float32))
-      return self.lin_l(agg / deg.clamp(min=1).unsqueeze(1)) + self.lin_r(x_dst)
+      mean = (agg / deg.clamp(min=1).unsqueeze(1)).to(self.lin_l.weight.dtype)   # no-op unless the model is pure bf16
+      return self.lin_l(mean) + self.lin_r(x_dst.to(self.lin_r.weight.dtype) if not torch.is_autocast_enabled() else x_dst)
 
   class SAGE(nn.Module):
     def __init__(self):
@@ -126,14 +127,18 @@ def main(args, baseline_samples_per_s, canonical_config, metric):
       dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
     return ms
 
-  def measure(dtype_name, min_time):
-    """Builds Feature + loader + model for one precision and times it (same block protocol as our arm)."""
+  def measure(dtype_name, min_time, pure=False):
+    """Builds Feature + loader + model for one precision and times it (same block protocol as our arm).
+    bf16 comes in two recipes: torch.autocast around an fp32 model (casts per call), or `pure`: the model itself
+    in bf16 (no per-call weight casts; torch Adam on bf16 parameters) -- the faster one is the headline."""
     fdt = torch.bfloat16 if dtype_name == 'bf16' else torch.float32
     ds.node_features = None
     ds.init_node_features(node_feature_data=feats.to(fdt), sort_func=glt.data.sort_by_in_degree, split_ratio=split,
                           device_group_list=[glt.data.DeviceGroup(0, [local_rank])], device=local_rank)
     torch.manual_seed(args.seed)
     model = _sage_model(torch, args.feat_dim, args.hidden, args.classes).to(device)
+    if pure:
+      model = model.to(torch.bfloat16)
     if world > 1:
       model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank])
     opt = torch.optim.Adam(model.parameters(), lr=3e-3)
@@ -155,7 +160,7 @@ def main(args, baseline_samples_per_s, canonical_config, metric):
         batch_size, n_id, adjs = next(state['it'])
       adjs = [adj.to(device) for adj in adjs]
       opt.zero_grad()
-      with torch.autocast('cuda', dtype=torch.bfloat16, enabled=(dtype_name == 'bf16')):
+      with torch.autocast('cuda', dtype=torch.bfloat16, enabled=(dtype_name == 'bf16' and not pure)):
         out = model(ds.node_features[n_id], adjs)
       loss = F.nll_loss(out, node_labels[n_id[:batch_size]])
       loss.backward()
@@ -186,8 +191,25 @@ def main(args, baseline_samples_per_s, canonical_config, metric):
     del model, opt
     return d, e
 
-  dev_t, e2e_t = measure(dt_name, args.min_time)
   arms = []
+  recipe = 'fp32'
+  if dt_name == 'bf16':
+    # two bf16 recipes; the FASTER one is the headline of this arm, the other is listed under "arms"
+    cand = {}
+    for name, pure in (('bf16-autocast', False), ('bf16-pure', True)):
+      try:
+        cand[name] = measure('bf16', args.min_time, pure=pure)
+      except Exception as ex:
+        arms.append({'ref_config': cfg_name, 'dtype': name, 'error': f'{type(ex).__name__}: {str(ex)[:200]}'})
+    recipe = min(cand, key=lambda k: cand[k][0]['ms_per_step'])
+    dev_t, e2e_t = cand[recipe]
+    for name, (d2, e2) in cand.items():
+      if name != recipe:
+        arms.append({'ref_config': cfg_name, 'dtype': name, 'value': bs * world / (d2['ms_per_step'] / 1e3),
+                     'ms_per_step': d2['ms_per_step'], 'e2e_value': bs * world / (e2['ms_per_step'] / 1e3),
+                     'e2e_ms_per_step': e2['ms_per_step'], 'timed': d2})
+  else:
+    dev_t, e2e_t = measure(dt_name, args.min_time)
   if not args.no_arms and dt_name == 'bf16':
     try:
       d2, e2 = measure('fp32', min(args.min_time, 0.5))
@@ -210,7 +232,8 @@ def main(args, baseline_samples_per_s, canonical_config, metric):
       'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': val / baseline_samples_per_s,
       'dtype': 'bf16' if dt_name == 'bf16' else 'fp32', 'data': 'synthetic',
       'config': cfg,
-      'details': {'model_code': 'plain-PyTorch SAGEConv (PyG unavailable offline), torch.autocast(bf16)' if dt_name == 'bf16'
+      'details': {'model_code': f'plain-PyTorch SAGEConv (PyG unavailable offline), recipe {recipe} (fastest bf16 recipe of '
+                                'this run: autocast around an fp32 model vs the model itself in bf16)' if dt_name == 'bf16'
                   else 'plain-PyTorch SAGEConv (PyG unavailable offline), fp32',
                   'graph_mode': graph_mode, 'feature_split_ratio': split, 'feature_dtype': dt_name,
                   'loader': 'glt.loader.NeighborLoader(as_pyg_v1=True)', 'parallelism': f'ddp{world}',
