@@ -28,13 +28,14 @@ if args.impl == 'reference':
   try:
     import graphlearn_torch as rglt
     dev = torch.device('cuda', 0)
-    results = []
+    results, held = [], []
     for dtype in (torch.float32, torch.bfloat16):
       full = torch.randn(args.rows, args.dim).to(dtype)
       for ratio in (1.0, 0.2, 0.0):
         # a fresh host tensor per Feature: the reference page-locks (cudaHostRegister) the cold part in place and
         # fails on memory that an earlier Feature already registered
-        feat = rglt.data.Feature(full.clone(), split_ratio=ratio, device_group_list=[rglt.data.DeviceGroup(0, [0])], device=0)
+        held.append(full.clone())   # kept alive: a freed-and-reused host block would still be registered
+        feat = rglt.data.Feature(held[-1], split_ratio=ratio, device_group_list=[rglt.data.DeviceGroup(0, [0])], device=0)
         gen = torch.Generator(device=dev); gen.manual_seed(0)
         ids = [torch.randint(0, args.rows, (args.ids,), device=dev, generator=gen) for _ in range(args.iters + 3)]
         for i in ids[:3]:

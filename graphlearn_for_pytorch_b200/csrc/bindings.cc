@@ -686,6 +686,7 @@ struct HeteroArena {
 struct RowTableHandle {
   RowTable tbl{};
   std::vector<Tensor> keep;
+  unsigned local_mask = 0;   // bit p: part p is memory of `device` itself (not a peer GPU's HBM / pinned host)
   int device;
   torch::ScalarType dtype = torch::kFloat32;
   int64_t width = 0;
@@ -704,6 +705,14 @@ struct RowTableHandle {
     TORCH_CHECK(part.scalar_type() == dtype, "dtype mismatch between parts");
     TORCH_CHECK((part.dim() > 1 ? w : 1) == width || part.size(0) == 0, "row width mismatch");
     tbl.base[tbl.num_parts] = part.size(0) > 0 ? dev_ptr(part) : nullptr;
+    if (part.size(0) > 0 && part.is_cuda()) {
+      cudaPointerAttributes at{};
+      if (cudaPointerGetAttributes(&at, part.data_ptr()) == cudaSuccess && at.type == cudaMemoryTypeDevice &&
+          at.device == device)
+        local_mask |= 1u << tbl.num_parts;
+      else
+        cudaGetLastError();
+    }
     tbl.row_begin[tbl.num_parts + 1] = tbl.row_begin[tbl.num_parts] + part.size(0);
     tbl.num_parts++;
     keep.push_back(part);
@@ -1014,6 +1023,9 @@ static void sage_fused(RowTableHandle* feat, const c10::optional<Tensor>& nodes,
   f.relu = relu;
   f.z = z.data_ptr();
   f.feat_fp8 = fp8 ? 1 : 0;
+  static const bool l2pf = [] { const char* e = std::getenv("GLT_B200_L2_PREFETCH"); return e ? std::atoi(e) != 0 : true; }();
+  f.l2_prefetch = (l2pf && feat != nullptr && !(src_local.has_value() && src_local->defined())) ? 1 : 0;
+  f.local_mask = feat != nullptr ? feat->local_mask : 0u;
   f.a_save = nullptr;
   if (a_save.has_value() && a_save->defined()) {
     TORCH_CHECK(a_save->size(0) >= z.size(0) && a_save->size(1) == 2 * d && a_save->is_contiguous());

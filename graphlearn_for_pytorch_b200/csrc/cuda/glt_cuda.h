@@ -289,6 +289,8 @@ struct SageFusedArgs {
   void* a_save;                 // optional bf16 [cap_targets, 2d] for backward
   unsigned long long* trace;    // optional per-CTA clock64 timeline (diagnostics, see sage_fused_trace)
   int feat_fp8;                 // 1: agg.feat rows are MXFP8 (d e4m3 bytes + d/32 UE8M0 scales, 16-byte padded)
+  int l2_prefetch;              // resolver warps prefetch next tile's local feature rows into L2
+  unsigned local_mask;          // bit p set: part p of agg.feat lives in this GPU's HBM (prefetchable into its L2)
 };
 int sage_fused_supported(int d, int n_out);
 // Copies the per-CTA timeline of the last traced launch (GLT_B200_FUSED_TRACE=1) to `host` [148*32].

@@ -644,9 +644,28 @@ __global__ void __launch_bounds__(kThreads3, 1) k_sage_fused3(SageFusedArgs f) {
         int64_t gid[kKP];
 #pragma unroll
         for (int j = 0; j < kKP; ++j) gid[j] = (j < dg && sidx[j] >= 0) ? __ldg(a.nodes + sidx[j]) : -1;
+        // The loaders will want these rows one tile (~7 us) from now: pull the LOCAL ones from DRAM into L2 already
+        // (the loader's three dependent batches per row then cost L2 latency instead of DRAM latency).  Peer rows
+        // are skipped: peer memory is not cached in the local L2.
+        uint32_t hnd[kKP + 1];
 #pragma unroll
-        for (int j = 0; j < kKP; ++j) sts32(trow + ((j ^ sw) << 2), static_cast<int32_t>(handle_of(gid[j])));
-        sts32(trow + ((15 ^ sw) << 2), static_cast<int32_t>(handle_of(self_gid)));
+        for (int j = 0; j < kKP; ++j) hnd[j] = handle_of(gid[j]);
+        hnd[kKP] = handle_of(self_gid);
+        if (f.l2_prefetch) {
+#pragma unroll
+          for (int j = 0; j <= kKP; ++j) {
+            const uint32_t h = hnd[j];
+            if (h != kNoRow && ((f.local_mask >> (h >> 28)) & 1u)) {
+              const uint8_t* p = reinterpret_cast<const uint8_t*>(a.feat.base[h >> 28]) +
+                                 static_cast<int64_t>(h & 0x0FFFFFFFu) * row_bytes;
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+              if (row_bytes > 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 128));
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < kKP; ++j) sts32(trow + ((j ^ sw) << 2), static_cast<int32_t>(hnd[j]));
+        sts32(trow + ((15 ^ sw) << 2), static_cast<int32_t>(hnd[kKP]));
       }
       sts32(deg_u32 + (stage * kTileM + r) * 4, dg);
     };

@@ -120,7 +120,9 @@ class GraphSageEngine(object):
       use_fused = True
     self.pipeline = bool(pipeline)
     import os as _os3
-    self.overlap_wgrad = _os3.environ.get('GLT_B200_OVERLAP_WGRAD', '1') != '0'
+    # measured on B200 (profiles/): running the weight-gradient GEMMs and the zero fills on an auxiliary stream LOSES 3 %
+    # (0.245 vs 0.237 ms/step): the extra CTAs compete with the critical dgrad -> scatter -> cast chain.  Kept as an option.
+    self.overlap_wgrad = _os3.environ.get('GLT_B200_OVERLAP_WGRAD', '0') != '0'
     self.deterministic_sampling = bool(deterministic_sampling)
     self.use_peer_allreduce = bool(use_peer_allreduce)
     # use_gather_bwd (csrc/cuda/transpose.cu, validated on B200 in round 2): the sampler also builds the transposed
