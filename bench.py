@@ -526,6 +526,7 @@ def run_ours(args):
         'tcgen05_gemm_layers': getattr(eng, 'tc_gemm', None),
         'gather_backward': bool(eng.use_gather_bwd),
         'feature_format': args.feat_format,
+        'remote_rows_staged_on_sampling_stream': bool(getattr(eng, 'stage_remote', False)),
         'hot_feature_replica': (None if world == 1 else {'fraction': args.hot_fraction,
                                                          'fill': getattr(eng._keep[1], 'fill_mode', None)}),
         'grad_allreduce': 'peer-HBM all-reduce fused into Adam (NVLink, in-graph)' if eng.peer_group is not None

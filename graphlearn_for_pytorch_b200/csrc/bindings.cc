@@ -735,6 +735,18 @@ struct RowTableHandle {
     return out;
   }
 
+  // copy the rows of the batch's nodes that are NOT in this GPU's HBM into xcache[local id] (see launch_stage_remote_rows)
+  void stage_remote_rows(const Tensor& nodes, const Tensor& counters, int64_t n_idx, Tensor xcache) {
+    c10::cuda::CUDAGuard guard(device);
+    TORCH_CHECK(nodes.is_cuda() && nodes.scalar_type() == torch::kInt64 && nodes.is_contiguous());
+    TORCH_CHECK(xcache.is_cuda() && xcache.is_contiguous() &&
+                xcache.numel() * xcache.element_size() >= nodes.numel() * tbl.row_bytes && tbl.row_bytes % 16 == 0);
+    launch_stage_remote_rows(tbl, local_mask, nodes.data_ptr<int64_t>(), counters.data_ptr<int32_t>(), n_idx,
+                             nodes.numel(), xcache.data_ptr(), cur_stream());
+    check_cuda_err("stage_remote_rows");
+  }
+  bool all_local() const { return local_mask == ((tbl.num_parts >= 32) ? ~0u : ((1u << tbl.num_parts) - 1u)); }
+
   // rows are MXFP8 (d e4m3 bytes + d/32 UE8M0 scales + padding to 16 bytes): dequantised bf16 [n, d]
   Tensor gather_mxfp8(const Tensor& idx, int64_t d) {
     c10::cuda::CUDAGuard guard(device);
@@ -1007,7 +1019,8 @@ static void sage_fused(RowTableHandle* feat, const c10::optional<Tensor>& nodes,
                        const c10::optional<Tensor>& src_local, int64_t d, const Tensor& counters,
                        int64_t n_hops_targets, const std::vector<Tensor>& ell,
                        const std::vector<int64_t>& ks, const Tensor& deg, const Tensor& w_packed,
-                       const Tensor& bias, bool relu, Tensor z, const c10::optional<Tensor>& a_save) {
+                       const Tensor& bias, bool relu, Tensor z, const c10::optional<Tensor>& a_save,
+                       const c10::optional<Tensor>& xcache) {
   c10::cuda::CUDAGuard guard(z.device());
   const bool fp8 = feat != nullptr && !(src_local.has_value() && src_local->defined()) && feat->dtype == torch::kUInt8;
   TORCH_CHECK(!fp8 || d == 128, "the MXFP8 loader of the fused kernel supports d = 128");
@@ -1026,6 +1039,19 @@ static void sage_fused(RowTableHandle* feat, const c10::optional<Tensor>& nodes,
   static const bool l2pf = [] { const char* e = std::getenv("GLT_B200_L2_PREFETCH"); return e ? std::atoi(e) != 0 : true; }();
   f.l2_prefetch = (l2pf && feat != nullptr && !(src_local.has_value() && src_local->defined())) ? 1 : 0;
   f.local_mask = feat != nullptr ? feat->local_mask : 0u;
+  f.xcache = nullptr;
+  f.cache_part = -1;
+  if (feat != nullptr && xcache.has_value() && xcache->defined()) {
+    // remote rows of the batch were staged into `xcache` (indexed by local node id): reuse a remote part's slot
+    for (int p = 0; p < feat->tbl.num_parts; ++p)
+      if (!((feat->local_mask >> p) & 1u)) { f.cache_part = p; break; }
+    if (f.cache_part >= 0) {
+      TORCH_CHECK(xcache->is_cuda() && xcache->is_contiguous() &&
+                  xcache->numel() * xcache->element_size() >= static_cast<int64_t>(nodes->numel()) * feat->tbl.row_bytes,
+                  "sage_fused: xcache must hold one feature row per arena node");
+      f.xcache = xcache->data_ptr();
+    }
+  }
   f.a_save = nullptr;
   if (a_save.has_value() && a_save->defined()) {
     TORCH_CHECK(a_save->size(0) >= z.size(0) && a_save->size(1) == 2 * d && a_save->is_contiguous());
@@ -1467,7 +1493,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("gather", &RowTableHandle::gather, py::arg("idx"), py::arg("id2index") = py::none(),
            py::arg("out_width") = 0)
       .def("gather_into", &RowTableHandle::gather_into)
-      .def("gather_mxfp8", &RowTableHandle::gather_mxfp8);
+      .def("gather_mxfp8", &RowTableHandle::gather_mxfp8)
+      .def("stage_remote_rows", &RowTableHandle::stage_remote_rows)
+      .def("all_local", &RowTableHandle::all_local);
 
   // ---- GraphSAGE engine ----
   m.def("sage_aggregate", &sage_aggregate);
@@ -1487,7 +1515,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("adam_step", &adam_step);
   m.def("colsum_bf16", &colsum_bf16);
   m.def("zero_rows", &zero_rows);
-  m.def("sage_fused", &sage_fused);
+  m.def("sage_fused", &sage_fused, py::arg("feat"), py::arg("nodes"), py::arg("src_local"), py::arg("d"),
+        py::arg("counters"), py::arg("n_hops_targets"), py::arg("ell"), py::arg("ks"), py::arg("deg"),
+        py::arg("w_packed"), py::arg("bias"), py::arg("relu"), py::arg("z"), py::arg("a_save") = py::none(),
+        py::arg("xcache") = py::none());
   m.def("sage_fused_supported", &sage_fused_supported);
   m.def("sage_fused_trace", []() {
     // [148, 32] int64 clock64 timeline of the last fused launch made with GLT_B200_FUSED_TRACE=1

@@ -159,6 +159,11 @@ void launch_gather_i64(RowTable t, const int64_t* idx, int64_t n, const int32_t*
 void launch_multimem_copy(const void* src, void* mc_dst, int64_t nbytes, cudaStream_t s);
 // out[i, 0..d) (bf16) = dequantised MXFP8 row idx[i] of `t` (rows of d + 16 bytes, see data/quantize.py)
 void launch_gather_mxfp8(RowTable t, const int64_t* idx, int64_t n, int d, void* out, cudaStream_t s);
+// xcache[s, :] = row nodes[s] of `t` for every local id s < cum[n_idx] whose row is NOT in a part of `local_mask`
+// (peer HBM / host): one bulk, bandwidth-efficient pass over the batch's unique remote rows (each is needed ~2.5x by
+// the layer-1 kernel), run on the sampling stream one batch ahead of the training step.
+void launch_stage_remote_rows(RowTable t, unsigned local_mask, const int64_t* nodes, const int32_t* cum, int n_idx,
+                              int cap_nodes, void* xcache, cudaStream_t s);
 
 // ---- sage.cu (GraphSAGE engine kernels) ---------------------------------------
 struct SageAggArgs {
@@ -291,6 +296,11 @@ struct SageFusedArgs {
   int feat_fp8;                 // 1: agg.feat rows are MXFP8 (d e4m3 bytes + d/32 UE8M0 scales, 16-byte padded)
   int l2_prefetch;              // resolver warps prefetch next tile's local feature rows into L2
   unsigned local_mask;          // bit p set: part p of agg.feat lives in this GPU's HBM (prefetchable into its L2)
+  // Staged remote rows: rows of the batch's nodes that live in PEER HBM, copied once per batch (on the sampling
+  // stream, launch_stage_remote_rows) into a local buffer indexed by the node's LOCAL id.  nullptr = read peers in
+  // place.  cache_part: index of a non-local part whose handle slot is reused for the cache.
+  const void* xcache;
+  int cache_part;
 };
 int sage_fused_supported(int d, int n_out);
 // Copies the per-CTA timeline of the last traced launch (GLT_B200_FUSED_TRACE=1) to `host` [148*32].

@@ -388,6 +388,8 @@ __global__ void __launch_bounds__(kThreads3, 1) k_sage_fused3(SageFusedArgs f) {
       b = reinterpret_cast<const uint8_t*>(a.src_local) +
           static_cast<int64_t>(threadIdx.x) * (int64_t(1) << 28) * row_bytes;
     else if (static_cast<int>(threadIdx.x) < a.feat.num_parts) b = a.feat.base[threadIdx.x];
+    // staged remote rows (see SageFusedArgs::xcache): the slot of one (never referenced) remote part points at the cache
+    if (f.xcache && static_cast<int>(threadIdx.x) == f.cache_part) b = f.xcache;
     sts64(base_u32 + threadIdx.x * 8, reinterpret_cast<uint64_t>(b));
   }
   if (warp == kResWarp0) {
@@ -610,12 +612,17 @@ __global__ void __launch_bounds__(kThreads3, 1) k_sage_fused3(SageFusedArgs f) {
                  reinterpret_cast<const uint8_t*>(f.w_packed) + static_cast<size_t>(kc) * N * kChunkBytes,
                  N * kChunkBytes, bar_w);
     }
-    auto handle_of = [&](int64_t gid) -> uint32_t {  // global row id -> (shard, row in shard)
+    // global row id (+ the node's local id in the batch) -> (shard, row in shard); with a staged remote-row cache
+    // every row that is not in this GPU's HBM is read from the cache at its local id instead of from the peer
+    auto handle_of = [&](int64_t gid, int local_id) -> uint32_t {
       if (gid < 0) return kNoRow;
 #pragma unroll 1
       for (int p = 0; p < a.feat.num_parts; ++p)
-        if (gid >= a.feat.row_begin[p] && gid < a.feat.row_begin[p + 1])
+        if (gid >= a.feat.row_begin[p] && gid < a.feat.row_begin[p + 1]) {
+          if (f.xcache && !((f.local_mask >> p) & 1u))
+            return (static_cast<uint32_t>(f.cache_part) << 28) | static_cast<uint32_t>(local_id);
           return (static_cast<uint32_t>(p) << 28) | static_cast<uint32_t>(gid - a.feat.row_begin[p]);
+        }
       return kNoRow;
     };
     auto resolve = [&](int tile, int stage) {
@@ -649,14 +656,16 @@ __global__ void __launch_bounds__(kThreads3, 1) k_sage_fused3(SageFusedArgs f) {
         // are skipped: peer memory is not cached in the local L2.
         uint32_t hnd[kKP + 1];
 #pragma unroll
-        for (int j = 0; j < kKP; ++j) hnd[j] = handle_of(gid[j]);
-        hnd[kKP] = handle_of(self_gid);
+        for (int j = 0; j < kKP; ++j) hnd[j] = handle_of(gid[j], sidx[j]);
+        hnd[kKP] = handle_of(self_gid, t);
         if (f.l2_prefetch) {
+          const unsigned pf_mask = f.local_mask | (f.xcache ? (1u << f.cache_part) : 0u);
 #pragma unroll
           for (int j = 0; j <= kKP; ++j) {
             const uint32_t h = hnd[j];
-            if (h != kNoRow && ((f.local_mask >> (h >> 28)) & 1u)) {
-              const uint8_t* p = reinterpret_cast<const uint8_t*>(a.feat.base[h >> 28]) +
+            if (h != kNoRow && ((pf_mask >> (h >> 28)) & 1u)) {
+              const uint8_t* p = reinterpret_cast<const uint8_t*>((f.xcache && static_cast<int>(h >> 28) == f.cache_part)
+                                                                      ? f.xcache : a.feat.base[h >> 28]) +
                                  static_cast<int64_t>(h & 0x0FFFFFFFu) * row_bytes;
               asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
               if (row_bytes > 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 128));

@@ -109,7 +109,7 @@ class GraphSageEngine(object):
                calibration_margin: float = 1.3, calibration_batches: int = 16, pipeline: bool = False,
                use_peer_allreduce: bool = True, use_gather_bwd: Optional[bool] = None,
                check_every: int = 64, auto_regrow: bool = True, feature_format: str = 'bf16',
-               deterministic_sampling: bool = False):
+               deterministic_sampling: bool = False, stage_remote_rows: Optional[bool] = None):
     self.nat = require_native()
     # 'mxfp8': `feature_table` holds data.quantize_mxfp8 rows (uint8, in_dim + 16 bytes); the fused layer-1 kernel
     # de-quantises in its loaders (half the gather bytes), so the fused path is mandatory for that format
@@ -119,6 +119,12 @@ class GraphSageEngine(object):
       assert int(in_dim) == 128, 'MXFP8 features: in_dim must be 128'
       use_fused = True
     self.pipeline = bool(pipeline)
+    # Multi-GPU: the rows of a batch's nodes that live in PEER HBM are copied once per batch into a local buffer
+    # indexed by local node id -- by a bulk gather kernel on the SAMPLING stream, one batch ahead of the training
+    # step -- and the fused layer-1 kernel reads them from there (each is needed ~2.5x, and 256-byte random reads
+    # issued from inside the GEMM kernel are bound by NVLink latency, not bandwidth).  None = on when the feature
+    # table has non-local parts; False keeps the in-kernel peer loads of the fused layer.
+    self._stage_remote_opt = stage_remote_rows
     import os as _os3
     # measured on B200 (profiles/): running the weight-gradient GEMMs and the zero fills on an auxiliary stream LOSES 3 %
     # (0.245 vs 0.237 ms/step): the extra CTAs compete with the critical dgrad -> scatter -> cast chain.  Kept as an option.
@@ -235,6 +241,16 @@ class GraphSageEngine(object):
                               for l in range(2, self.L + 1)]
     self.dH = [None] + [torch.zeros(self.cap_T[l], self.dims_out[l - 1], dtype=f32, device=dev)
                         for l in range(1, self.L)]
+    want = self._stage_remote_opt
+    if want is None:
+      import os as _os4
+      want = _os4.environ.get('GLT_B200_STAGE_REMOTE', '1') != '0'
+    has_remote = hasattr(self.feat, 'all_local') and not self.feat.all_local()
+    self.stage_remote = bool(want and has_remote)
+    self._xcache = None
+    if self.stage_remote:
+      row_bytes = self.in_dim * 2 if self.feature_format == 'bf16' else self.in_dim + 16
+      self._xcache = [torch.zeros(int(a_.cap_nodes), row_bytes, dtype=torch.uint8, device=dev) for a_ in self._arenas]
     self._tc_plans = {}
     self._graphs = []
     self._graph_fb = self._graph_opt = self._graph_full = None
@@ -443,6 +459,9 @@ class GraphSageEngine(object):
     # (the increment itself is folded into the first sampling kernel: step_inc)
     ar.sample(self.gh, self._seeds[which], None, self.seed, 0, False, False, True, len(self._arenas))
     self._k(2 + 2 * self.L)  # table clear + init_seeds + (sample, relabel) per hop
+    if self.stage_remote:
+      self.feat.stage_remote_rows(ar.nodes, ar.counters, self.L + 1, self._xcache[which])
+      self._k(1)
 
   def _forward(self, train: bool = True):
     nat, ar = self.nat, self.arena
@@ -459,8 +478,9 @@ class GraphSageEngine(object):
     nodes = ar.nodes if l == 1 else None
     src_local = None if l == 1 else self.Z[l - 1]
     if self.fused_ok[l]:
+      xc = self._xcache[self._cur] if (l == 1 and self.stage_remote) else None
       nat.sage_fused(feat, nodes, src_local, d, ar.counters, nh, ell, ks, ar.deg, self.w_packed[l],
-                     self.b(l), relu, self.Z[l], self.A[l])
+                     self.b(l), relu, self.Z[l], self.A[l], xc)
       self._k(1)
     else:
       nat.sage_aggregate(feat, nodes, src_local, d, ar.counters, nh, ell, ks, ar.deg, self.A[l])

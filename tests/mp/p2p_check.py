@@ -90,30 +90,38 @@ def main():
   ok(f'engine steps with P2P sampling + fused gather, loss={float(loss.item()):.3f}')
   # numerics of the fused tcgen05 layer with rows resolved across shards: recompute its saved
   # A operand [mean | self] from the (here locally available) full feature matrix
-  assert eng.fused_ok[1]
-  eng.seeds_dev.copy_(torch.randperm(N, device=dev)[:256])
-  eng._sample(); eng._forward_layer(1)     # eager: current weights, no collective involved
-  torch.cuda.synchronize()
-  ar = eng.arena
-  c = ar.counters.cpu().tolist()
-  cum = c[:eng.L + 2]
-  T = cum[eng.L]
-  nodes = ar.nodes[:cum[eng.L + 1]]
-  H = feats[nodes].float()
-  mean = torch.zeros(T, 128, device=dev)
-  for h in range(eng.L):
-    k, rows = eng.fanouts[h], cum[h + 1] - cum[h]
-    if rows == 0:
-      continue
-    ell = ar.ell[h][:rows * k].view(rows, k).long()
-    valid = (ell >= 0).unsqueeze(-1)
-    dg = ar.deg[cum[h]:cum[h + 1]].float().clamp(min=1).unsqueeze(1)
-    mean[cum[h]:cum[h + 1]] = (H[ell.clamp(min=0)] * valid).sum(1) / dg
-  A_ref = torch.cat([mean, H[:T]], dim=1)
-  assert torch.allclose(eng.A[1][:T].float(), A_ref, atol=2e-2, rtol=2e-2), 'fused A operand mismatch'
-  Z_ref = torch.relu(A_ref.to(torch.bfloat16).float() @ eng.W(1).float().t() + eng.b(1).float())
-  assert torch.allclose(eng.Z[1][:T].float(), Z_ref, atol=8e-2, rtol=3e-2), 'fused layer output mismatch'
-  ok('fused layer-1 numerics with peer-resolved rows')
+  def check_fused(e, what):
+    assert e.fused_ok[1]
+    e.seeds_dev.copy_(torch.randperm(N, device=dev)[:256])
+    e._sample(); e._forward_layer(1)     # eager: current weights, no collective involved
+    torch.cuda.synchronize()
+    ar = e.arena
+    c = ar.counters.cpu().tolist()
+    cum = c[:e.L + 2]
+    T = cum[e.L]
+    nodes = ar.nodes[:cum[e.L + 1]]
+    H = feats[nodes].float()
+    mean = torch.zeros(T, 128, device=dev)
+    for h in range(e.L):
+      k, rows = e.fanouts[h], cum[h + 1] - cum[h]
+      if rows == 0:
+        continue
+      ell = ar.ell[h][:rows * k].view(rows, k).long()
+      valid = (ell >= 0).unsqueeze(-1)
+      dg = ar.deg[cum[h]:cum[h + 1]].float().clamp(min=1).unsqueeze(1)
+      mean[cum[h]:cum[h + 1]] = (H[ell.clamp(min=0)] * valid).sum(1) / dg
+    A_ref = torch.cat([mean, H[:T]], dim=1)
+    assert torch.allclose(e.A[1][:T].float(), A_ref, atol=2e-2, rtol=2e-2), f'fused A operand mismatch ({what})'
+    Z_ref = torch.relu(A_ref.to(torch.bfloat16).float() @ e.W(1).float().t() + e.b(1).float())
+    assert torch.allclose(e.Z[1][:T].float(), Z_ref, atol=8e-2, rtol=3e-2), f'fused layer output mismatch ({what})'
+    ok(f'fused layer-1 numerics, {what}')
+
+  assert eng.stage_remote, 'a partitioned table must turn remote-row staging on by default'
+  check_fused(eng, 'remote rows staged into the local cache on the sampling stream')
+  eng_ip = GraphSageEngine(pg.graph, pf2.table, labels, in_dim=128, num_nodes=N, fanouts=[4, 3], batch_size=256,
+                           hidden=256, num_classes=8, device=dev, use_cuda_graph=False, stage_remote_rows=False)
+  assert not eng_ip.stage_remote
+  check_fused(eng_ip, 'peer rows read in place over NVLink from inside the tcgen05 kernel')
   # parameters stay identical across ranks (all-reduced gradients)
   p = eng.p32.clone()
   dist.all_reduce(p, op=dist.ReduceOp.MAX)
