@@ -1036,7 +1036,10 @@ static void sage_fused(RowTableHandle* feat, const c10::optional<Tensor>& nodes,
   f.relu = relu;
   f.z = z.data_ptr();
   f.feat_fp8 = fp8 ? 1 : 0;
-  static const bool l2pf = [] { const char* e = std::getenv("GLT_B200_L2_PREFETCH"); return e ? std::atoi(e) != 0 : true; }();
+  // Measured on B200 (profiles/fused_trace_r2_{prefetch,noprefetch}.txt): the resolver-side prefetch.global.L2 of the next
+  // tile's rows does NOT shorten the loaders' tile time (8.9 -> 9.3 us) and lengthens the prologue (4.2 -> 6.8 us): the
+  // loaders are bound by bytes in flight, not by DRAM-vs-L2 latency.  Off by default; GLT_B200_L2_PREFETCH=1 enables it.
+  static const bool l2pf = [] { const char* e = std::getenv("GLT_B200_L2_PREFETCH"); return e ? std::atoi(e) != 0 : false; }();
   f.l2_prefetch = (l2pf && feat != nullptr && !(src_local.has_value() && src_local->defined())) ? 1 : 0;
   f.local_mask = feat != nullptr ? feat->local_mask : 0u;
   f.xcache = nullptr;
