@@ -693,7 +693,9 @@ struct RowTableHandle {
 
   explicit RowTableHandle(int dev) : device(dev) { tbl.num_parts = 0; tbl.row_begin[0] = 0; }
 
-  void append(const Tensor& part) {
+  // remote = true: the rows live in a PEER GPU's HBM (IPC-mapped); cudaPointerGetAttributes cannot tell -- it reports
+  // the importing device for memory opened with cudaIpcOpenMemHandle -- so the caller says so (parallel/partitioned.py)
+  void append(const Tensor& part, bool remote = false) {
     TORCH_CHECK(tbl.num_parts < kMaxParts, "too many row-table parts");
     TORCH_CHECK(part.dim() >= 1 && part.is_contiguous(), "parts must be contiguous [rows, ...]");
     const int64_t w = part.numel() / std::max<int64_t>(part.size(0), 1);
@@ -705,7 +707,7 @@ struct RowTableHandle {
     TORCH_CHECK(part.scalar_type() == dtype, "dtype mismatch between parts");
     TORCH_CHECK((part.dim() > 1 ? w : 1) == width || part.size(0) == 0, "row width mismatch");
     tbl.base[tbl.num_parts] = part.size(0) > 0 ? dev_ptr(part) : nullptr;
-    if (part.size(0) > 0 && part.is_cuda()) {
+    if (part.size(0) > 0 && part.is_cuda() && !remote) {
       cudaPointerAttributes at{};
       if (cudaPointerGetAttributes(&at, part.data_ptr()) == cudaSuccess && at.type == cudaMemoryTypeDevice &&
           at.device == device)
@@ -1489,7 +1491,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def_readonly("n_rel", &HeteroArena::n_rel);
   py::class_<RowTableHandle>(m, "RowTableHandle")
       .def(py::init<int>())
-      .def("append", &RowTableHandle::append)
+      .def("append", &RowTableHandle::append, py::arg("part"), py::arg("remote") = false)
       .def("num_rows", &RowTableHandle::num_rows)
       .def_readonly("width", &RowTableHandle::width)
       .def_property_readonly("num_parts", [](const RowTableHandle& t) { return t.tbl.num_parts; })

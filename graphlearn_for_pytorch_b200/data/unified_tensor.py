@@ -42,22 +42,28 @@ class UnifiedTensor(object):
     if self._handle is None:
       nat = require_native()
       h = nat.RowTableHandle(self.current_device)
-      for p in self._parts:
-        h.append(p)
+      for i, p in enumerate(self._parts):
+        h.append(p, bool(self._part_remote[i]) if i < len(self._part_remote) else False)
       self._handle = h
     return self._handle
 
-  def _append(self, t: torch.Tensor, dev: int):
+  def _append(self, t: torch.Tensor, dev: int, remote: bool = False):
     assert t.dtype == self.dtype, f'dtype mismatch: {t.dtype} vs {self.dtype}'
     self._parts.append(t)
     self._part_devices.append(dev)
+    if not hasattr(self, '_part_remote'):
+      self._part_remote = [False] * (len(self._parts) - 1)
+    self._part_remote.append(bool(remote))
     self._handle = None
 
-  def append_shared_tensor(self, shared_tensor: torch.Tensor):
-    """Append a CUDA tensor (possibly on a peer device / opened from CUDA IPC)."""
+  def append_shared_tensor(self, shared_tensor: torch.Tensor, remote: bool = False):
+    """Append a CUDA tensor (possibly on a peer device / opened from CUDA IPC).  remote=True marks rows that live in
+    a PEER GPU's HBM (an IPC mapping looks like local memory to the runtime): kernels that treat local and peer rows
+    differently (remote-row staging of the fused engine) rely on it."""
     assert shared_tensor.is_cuda
     _enable_peer(self.current_device, shared_tensor.device.index)
-    self._append(shared_tensor.contiguous(), shared_tensor.device.index)
+    remote = remote or shared_tensor.device.index != self.current_device
+    self._append(shared_tensor.contiguous(), shared_tensor.device.index, remote)
 
   def append_cpu_tensor(self, cpu_tensor: torch.Tensor):
     """Append a host part; it is page-locked so kernels can read it in place."""

@@ -105,7 +105,7 @@ class PartitionedFeature(object):
       for r, p in enumerate(self.peers):
         self.unified.append_shared_tensor(self.replica[r * h:(r + 1) * h])   # hot head of rank r: local
         if bounds[r + 1] - bounds[r] > h:
-          self.unified.append_shared_tensor(p[h:])                           # cold tail: owner's HBM
+          self.unified.append_shared_tensor(p[h:], remote=(r != rank))       # cold tail: owner's HBM
         else:
           self.unified.append_shared_tensor(p[:0])
       return
@@ -117,7 +117,7 @@ class PartitionedFeature(object):
       lo = max(bounds[r], H)
       if lo >= bounds[r + 1]:
         continue
-      self.unified.append_shared_tensor(p[lo - bounds[r]:])             # cold rows stay partitioned
+      self.unified.append_shared_tensor(p[lo - bounds[r]:], remote=(r != rank))   # cold rows stay partitioned
 
   def _build_replica(self, group, use_multicast: bool) -> torch.Tensor:
     import torch.distributed as dist
