@@ -82,6 +82,8 @@ def parse_args(argv=None):
                  help='repeat the K-step timed region on fresh batches until this many seconds are measured')
   p.add_argument('--feat-format', default='bf16', choices=['bf16', 'mxfp8'],
                  help='ours/engine: feature storage (mxfp8 = e4m3 + UE8M0/32 block scales, de-quantised in the fused kernel)')
+  p.add_argument('--dropout', type=float, default=0.0,
+                 help='hidden-layer dropout in the engine (default 0: the reference arm model has none)')
   p.add_argument('--no-fused', action='store_true')
   p.add_argument('--fused', default='auto', choices=['auto', 'on'],
                  help="'auto': time fused vs unfused layer 1 at warm-up and keep the faster")
@@ -315,7 +317,7 @@ def build_ours(args, rank, world, device, need_engine=True):
                         use_fused=False if args.no_fused else (True if args.fused == 'on' else 'auto'),
                         use_cuda_graph=not args.no_graph,
                         calibration_seeds=None if args.no_calibrate else pool,
-                        pipeline=not args.no_pipeline, feature_format=args.feat_format)
+                        pipeline=not args.no_pipeline, feature_format=args.feat_format, dropout=args.dropout)
   eng._keep = keep
   return eng, pool
 

@@ -20,6 +20,7 @@ p.add_argument('--nodes', type=int, default=100_000)
 p.add_argument('--edges', type=int, default=2_000_000)
 p.add_argument('--epochs', type=int, default=2)
 p.add_argument('--batch', type=int, default=1024)
+p.add_argument('--dropout', type=float, default=0.5, help='hidden-layer dropout (engine mode and loader-mode model)')
 p.add_argument('--split-ratio', type=float, default=0.2, help='fraction of (hot) feature rows kept in HBM')
 args = p.parse_args()
 
@@ -36,7 +37,7 @@ if args.mode == 'loader':
   ds.init_node_labels(y)
   loader = glt.loader.NeighborLoader(ds, [15, 10, 5], train_idx, batch_size=args.batch, shuffle=True,
                                      drop_last=True, device=device)
-  model = GraphSAGE(x.shape[1], 256, n_cls, num_layers=3).to(device)
+  model = GraphSAGE(x.shape[1], 256, n_cls, num_layers=3, dropout=args.dropout).to(device)
   opt = torch.optim.Adam(model.parameters(), lr=3e-3)
   for epoch in range(args.epochs):
     t0, tot, correct, seen = time.time(), 0.0, 0, 0
@@ -72,7 +73,7 @@ else:
   ut = glt.data.UnifiedTensor(0, torch.bfloat16); ut.append_shared_tensor(feats)
   eng = GraphSageEngine(graph, ut._table(), y.to(device), in_dim=in_dim, num_nodes=args.nodes, fanouts=[15, 10, 5],
                         batch_size=args.batch, hidden=256, num_classes=n_cls, device=device,
-                        calibration_seeds=train_idx, pipeline=True)
+                        calibration_seeds=train_idx, pipeline=True, dropout=args.dropout)
   eng.warmup_and_capture()
   pinned = train_idx.pin_memory()
   for epoch in range(args.epochs):

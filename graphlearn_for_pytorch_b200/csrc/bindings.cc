@@ -932,7 +932,7 @@ static void sage_gather_bwd(const Tensor& dA, int64_t d, SamplerArena& ar, int64
 }
 
 static void relu_bwd_cast(const Tensor& dH, const Tensor& Z, const Tensor& counters, int64_t n_hops,
-                          Tensor dPre, const c10::optional<Tensor>& colsum, bool prezeroed) {
+                          Tensor dPre, const c10::optional<Tensor>& colsum, bool prezeroed, double gscale) {
   c10::cuda::CUDAGuard guard(dH.device());
   TORCH_CHECK(dPre.size(0) <= dH.size(0) && dPre.size(0) <= Z.size(0) && dPre.size(1) % 8 == 0);
   TORCH_CHECK(dH.scalar_type() == torch::kFloat32 && Z.scalar_type() == torch::kBFloat16 &&
@@ -942,8 +942,24 @@ static void relu_bwd_cast(const Tensor& dH, const Tensor& Z, const Tensor& count
   launch_relu_bwd_cast(dH.data_ptr<float>(), Z.data_ptr(), counters.data_ptr<int32_t>(), n_hops,
                        dPre.size(0), dPre.size(1), dPre.data_ptr(),
                        (colsum.has_value() && colsum->defined()) ? colsum->data_ptr<float>() : nullptr, cur_stream(),
-                       prezeroed);
+                       prezeroed, static_cast<float>(gscale));
   check_cuda_err("relu_bwd_cast");
+}
+
+static void dropout_bf16(Tensor Z, const Tensor& counters, int64_t n_hops, double p, int64_t seed, int64_t layer,
+                         const c10::optional<Tensor>& step_dev) {
+  c10::cuda::CUDAGuard guard(Z.device());
+  TORCH_CHECK(Z.scalar_type() == torch::kBFloat16 && Z.is_contiguous() && Z.dim() == 2 && Z.size(1) % 8 == 0,
+              "dropout_bf16: contiguous bf16 [rows, d], d % 8 == 0");
+  TORCH_CHECK(p >= 0.0 && p < 1.0, "dropout_bf16: p in [0, 1)");
+  const int32_t* st = nullptr;
+  if (step_dev.has_value() && step_dev->defined()) {
+    TORCH_CHECK(step_dev->scalar_type() == torch::kInt32 && step_dev->is_cuda());
+    st = step_dev->data_ptr<int32_t>();
+  }
+  launch_dropout_bf16(Z.data_ptr(), counters.data_ptr<int32_t>(), n_hops, Z.size(0), Z.size(1),
+                      static_cast<float>(p), static_cast<uint64_t>(seed), static_cast<int>(layer), st, cur_stream());
+  check_cuda_err("dropout_bf16");
 }
 
 static void bias_relu(Tensor Z, const Tensor& bias, const Tensor& counters, int64_t n_hops, bool relu) {
@@ -1509,7 +1525,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("sage_scatter_block", &sage_scatter_block);
   m.def("add_block_f32", &add_block_f32);
   m.def("relu_bwd_cast", &relu_bwd_cast, py::arg("dH"), py::arg("Z"), py::arg("counters"), py::arg("n_hops"),
-        py::arg("dPre"), py::arg("colsum"), py::arg("prezeroed") = false);
+        py::arg("dPre"), py::arg("colsum"), py::arg("prezeroed") = false, py::arg("gscale") = 1.0);
+  m.def("dropout_bf16", &dropout_bf16, py::arg("Z"), py::arg("counters"), py::arg("n_hops"), py::arg("p"),
+        py::arg("seed"), py::arg("layer"), py::arg("step_dev") = py::none());
   m.def("zero_grads", &zero_grads);
   m.def("set_pdl", [](bool on) { return set_pdl(on ? 1 : 0) != 0; });
   m.def("sage_gather_bwd", &sage_gather_bwd);

@@ -250,7 +250,13 @@ void launch_sage_gather_bwd(const SageGatherBwdArgs& a, cudaStream_t s);
 // dPre = (Z > 0) ? bf16(dH) : 0 for rows < cum[n_hops]; 0 beyond.
 // colsum (optional, fp32 [d]): fused bias gradient = column sums of dPre.
 void launch_relu_bwd_cast(const float* dH, const void* Z, const int32_t* cum, int n_hops, int cap,
-                          int d, void* dPre, float* colsum, cudaStream_t s, bool prezeroed = false);
+                          int d, void* dPre, float* colsum, cudaStream_t s, bool prezeroed = false,
+                          float gscale = 1.f);
+// In-place inverted dropout (keep prob 1-p, kept values scaled by 1/(1-p)) on rows < cum[n_hops] of bf16 Z[cap, d];
+// mask = Philox(seed, layer, *step_dev, element).  Backward: launch_relu_bwd_cast(..., gscale = 1/(1-p)) on the
+// post-dropout Z.
+void launch_dropout_bf16(void* Z, const int32_t* cum, int n_hops, int cap, int d, float p, uint64_t seed, int layer,
+                         const int32_t* step_dev, cudaStream_t s);
 // g[0..n) = 0, *loss = 0, *correct = 0 (one launch at the start of the gradient phase; the *_prezeroed variants of
 // the kernels below then skip their own memsets, which keeps the step a pure kernel chain)
 void launch_zero_grads(float* g, int64_t n, float* loss, int32_t* correct, cudaStream_t s);

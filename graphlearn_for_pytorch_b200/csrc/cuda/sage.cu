@@ -173,9 +173,10 @@ __global__ void __launch_bounds__(256) k_sage_scatter_bwd(SageScatterArgs a) {
 
 __global__ void __launch_bounds__(256) k_relu_bwd_cast(const float* dH, const __nv_bfloat16* Z, const int32_t* cum,
                                                        int n_hops, int cap, int d, __nv_bfloat16* dPre,
-                                                       float* colsum) {
+                                                       float* colsum, float gscale) {
   pdl_enter();
-  // colsum != nullptr: also accumulate the bias gradient (column sums of dPre).  Requires
+  // gscale: 1/(1-p) when Z is the post-dropout activation (dropped elements are 0 there, so the ReLU test also
+  // masks them).  colsum != nullptr: also accumulate the bias gradient (column sums of dPre).  Requires
   // d | 2048 so that a thread keeps the same 8 columns across grid-stride iterations.
   __shared__ float s_acc[256][8];
   const int T = min(cum[n_hops], cap);
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(256) k_relu_bwd_cast(const float* dH, const __
       for (int q = 0; q < 8; ++q) z[q] = 0.f;
       bf16x8_accum(*reinterpret_cast<const uint4*>(Z + e), z);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) g[q] = z[q] > 0.f ? g[q] : 0.f;
+      for (int q = 0; q < 8; ++q) g[q] = z[q] > 0.f ? g[q] * gscale : 0.f;
       o = pack_bf16x8(g, 1.f);
       if (colsum) {
         float r[8];
@@ -463,13 +464,54 @@ void launch_sage_scatter_bwd(const SageScatterArgs& a, cudaStream_t s) {
   });
 }
 
+// In-place inverted dropout on the first cum[n_hops] rows of a bf16 activation.  The keep mask is a pure function
+// of (seed, layer, optimizer step, element), so a replayed step drops the same elements; the step is read from the
+// device-side Adam counter, which makes the kernel CUDA-graph friendly.
+__global__ void __launch_bounds__(256) k_dropout_bf16(__nv_bfloat16* Z, const int32_t* cum, int n_hops, int cap, int d,
+                                                      uint32_t thresh16, float scale, uint64_t seed, int layer,
+                                                      const int32_t* step_dev) {
+  pdl_enter();
+  const int T = min(cum[n_hops], cap);
+  const int64_t n8 = static_cast<int64_t>(T) * d / 8;
+  const uint32_t step = step_dev ? static_cast<uint32_t>(*step_dev) : 0u;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    U4 c;
+    c.x = static_cast<uint32_t>(i);
+    c.y = static_cast<uint32_t>(i >> 32);
+    c.z = step;
+    c.w = 0xD509u + static_cast<uint32_t>(layer);
+    const U4 r = philox4x32_10(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), c);
+    const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+    uint4 v = *reinterpret_cast<const uint4*>(Z + i * 8);
+    float z[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) z[q] = 0.f;
+    bf16x8_accum(v, z);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const uint32_t u = (rr[q >> 1] >> ((q & 1) * 16)) & 0xFFFFu;
+      z[q] = u >= thresh16 ? z[q] : 0.f;
+    }
+    *reinterpret_cast<uint4*>(Z + i * 8) = pack_bf16x8(z, scale);
+  }
+}
+
+void launch_dropout_bf16(void* Z, const int32_t* cum, int n_hops, int cap, int d, float p, uint64_t seed, int layer,
+                         const int32_t* step_dev, cudaStream_t s) {
+  const uint32_t thresh = static_cast<uint32_t>(fminf(fmaxf(p, 0.f), 1.f) * 65536.f);
+  const float scale = p < 1.f ? 1.f / (1.f - p) : 0.f;
+  launch_k(k_dropout_bf16, dim3(grid_for(static_cast<int64_t>(cap) * d / 8, 256, 148 * 8)), dim3(256), 0, s,
+           reinterpret_cast<__nv_bfloat16*>(Z), cum, n_hops, cap, d, thresh, scale, seed, layer, step_dev);
+}
+
 void launch_relu_bwd_cast(const float* dH, const void* Z, const int32_t* cum, int n_hops, int cap,
-                          int d, void* dPre, float* colsum, cudaStream_t s, bool prezeroed) {
+                          int d, void* dPre, float* colsum, cudaStream_t s, bool prezeroed, float gscale) {
   if (colsum && (2048 % d != 0)) colsum = nullptr;  // caller falls back to launch_colsum_bf16
   if (colsum && !prezeroed) cudaMemsetAsync(colsum, 0, sizeof(float) * d, s);
   launch_k(k_relu_bwd_cast, dim3(grid_for(static_cast<int64_t>(cap) * d / 8, 256 * 2, 148 * 4)), dim3(256), 0, s,
            dH, reinterpret_cast<const __nv_bfloat16*>(Z), cum, n_hops, cap, d,
-           reinterpret_cast<__nv_bfloat16*>(dPre), colsum);
+           reinterpret_cast<__nv_bfloat16*>(dPre), colsum, gscale);
 }
 
 void launch_bias_relu(void* Z, const void* bias, const int32_t* cum, int n_hops, int cap, int d,

@@ -109,8 +109,14 @@ class GraphSageEngine(object):
                calibration_margin: float = 1.3, calibration_batches: int = 16, pipeline: bool = False,
                use_peer_allreduce: bool = True, use_gather_bwd: Optional[bool] = None,
                check_every: int = 64, auto_regrow: bool = True, feature_format: str = 'bf16',
-               deterministic_sampling: bool = False, stage_remote_rows: Optional[bool] = None):
+               deterministic_sampling: bool = False, stage_remote_rows: Optional[bool] = None,
+               dropout: float = 0.0):
     self.nat = require_native()
+    # dropout on the hidden activations (the reference example trains with p = 0.5,
+    # examples/train_sage_ogbn_products.py:58): one in-place Philox kernel per hidden layer in training steps,
+    # mask keyed by (seed, layer, optimizer step, element); backward rescales inside relu_bwd_cast.
+    assert 0.0 <= float(dropout) < 1.0
+    self.dropout = float(dropout)
     # 'mxfp8': `feature_table` holds data.quantize_mxfp8 rows (uint8, in_dim + 16 bytes); the fused layer-1 kernel
     # de-quantises in its loaders (half the gather bytes), so the fused path is mandatory for that format
     assert feature_format in ('bf16', 'mxfp8')
@@ -137,7 +143,7 @@ class GraphSageEngine(object):
     if use_gather_bwd is None:
       import os as _os
       use_gather_bwd = _os.environ.get('GLT_B200_GATHER_BWD', '0') == '1'
-    self.use_gather_bwd = bool(use_gather_bwd)
+    self.use_gather_bwd = bool(use_gather_bwd) and self.dropout == 0.0
     # every dense contraction outside the fused layer-1 kernel runs on the TMA-fed tcgen05 GEMM kernel
     # (csrc/cuda/tc_gemm.cu); GLT_B200_TC_GEMM=0 falls back to cuBLAS for A/B measurements
     import os as _os2
@@ -466,10 +472,17 @@ class GraphSageEngine(object):
   def _forward(self, train: bool = True):
     nat, ar = self.nat, self.arena
     for l in range(1, self.L + 1):
-      self._forward_layer(l)
+      self._forward_layer(l, train)
     self._forward_loss(train)
 
-  def _forward_layer(self, l: int):
+  def _forward_layer(self, l: int, train: bool = True):
+    self._forward_layer_nodrop(l)
+    if train and self.dropout > 0.0 and l < self.L:
+      self.nat.dropout_bf16(self.Z[l], self.arena.counters, self.L - l + 1, self.dropout, self.seed, l,
+                            self.step_dev)
+      self._k(1)
+
+  def _forward_layer_nodrop(self, l: int):
     nat, ar = self.nat, self.arena
     ell, ks, nh = self._ell(l)
     d = self.dims_in[l - 1]
@@ -576,7 +589,7 @@ class GraphSageEngine(object):
           main.wait_event(ev_zero)
         nat.sage_scatter_bwd(self.dA[l], self.dims_in[l - 1], ar.counters, nh, ell, ks, ar.deg, self.dH[l - 1])
         nat.relu_bwd_cast(self.dH[l - 1], self.Z[l - 1], ar.counters, nh + 1, self.dPre[l - 1],
-                          self.g32[pboff:pboff + pn], True)
+                          self.g32[pboff:pboff + pn], True, 1.0 / (1.0 - self.dropout))
         self._k(2)
         continue
       if self.use_tc_gemm:
@@ -603,7 +616,7 @@ class GraphSageEngine(object):
         nat.zero_rows(self.dH[l - 1], ar.counters, nh + 1)
         nat.sage_scatter_bwd(self.dA[l], self.dims_in[l - 1], ar.counters, nh, ell, ks, ar.deg, self.dH[l - 1])
         nat.relu_bwd_cast(self.dH[l - 1], self.Z[l - 1], ar.counters, nh + 1, self.dPre[l - 1],
-                          self.g32[pboff:pboff + pn], True)
+                          self.g32[pboff:pboff + pn], True, 1.0 / (1.0 - self.dropout))
         self._k(3)
 
   _f32_mode = None
@@ -680,10 +693,10 @@ class GraphSageEngine(object):
       for mode in (True, False):
         self.fused_ok[l] = mode
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        self._forward_layer(l)
+        self._forward_layer_nodrop(l)
         e0.record()
         for _ in range(iters):
-          self._forward_layer(l)
+          self._forward_layer_nodrop(l)
         e1.record()
         e1.synchronize()
         res[mode] = e0.elapsed_time(e1) / iters

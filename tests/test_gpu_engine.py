@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 DEV = torch.device('cuda', 0)
 
 
-def _setup(N=6000, E=120000, Fdim=128, C=47, fan=(5, 4, 3), bs=256, fused=True, graph=False, hidden=256):
+def _setup(N=6000, E=120000, Fdim=128, C=47, fan=(5, 4, 3), bs=256, fused=True, graph=False, hidden=256, **kw):
   ei, topo = rmat_csr(N, E, seed=3)
   g = glt.data.Graph(topo, 'CUDA', 0)
   torch.manual_seed(0)
@@ -20,7 +20,7 @@ def _setup(N=6000, E=120000, Fdim=128, C=47, fan=(5, 4, 3), bs=256, fused=True, 
   ut = glt.data.UnifiedTensor(0, torch.bfloat16)
   ut.append_shared_tensor(feats)
   eng = GraphSageEngine(g, ut._table(), labels, in_dim=Fdim, num_nodes=N, fanouts=list(fan), batch_size=bs,
-                        hidden=hidden, num_classes=C, device=DEV, use_fused=fused, use_cuda_graph=graph, seed=5)
+                        hidden=hidden, num_classes=C, device=DEV, use_fused=fused, use_cuda_graph=graph, seed=5, **kw)
   eng._keep = (ut, feats, topo)
   return eng, feats, labels
 
@@ -62,6 +62,10 @@ def _dense_reference(eng, feats, labels, n_valid_seeds):
     Z = A @ W.t() + b
     if l < L:
       Z = F.relu(Z)
+      if getattr(eng, 'dropout', 0.0) > 0.0:
+        # the keep mask is read back from the engine's post-dropout activation (0 there = dropped or ReLU-dead)
+        keep = (eng.Z[l][:T] != 0).float()
+        Z = Z * keep / (1.0 - eng.dropout)
       Z = Z + (Z.to(torch.bfloat16).float() - Z).detach()   # bf16 storage, straight-through grad
     acts.append((A, Z))
     H = Z
@@ -409,3 +413,66 @@ def test_mxfp8_features_fused_layer_and_gather_match_dequantised_reference(nativ
     _, c, n = e.evaluate_batch(torch.arange(512, device=DEV))
     accs[name] = c / n
   assert accs['bf16'] > 0.5 and accs['mxfp8'] > accs['bf16'] - 0.08, accs
+
+
+def test_dropout_kernel_mask_is_keyed_by_step_and_scaled(native):
+  Z = torch.ones(4096, 256, device=DEV, dtype=torch.bfloat16)
+  ctr = torch.tensor([0, 3000], device=DEV, dtype=torch.int32)
+  step = torch.zeros(2, device=DEV, dtype=torch.int32)
+  a = Z.clone(); native.dropout_bf16(a, ctr, 1, 0.5, 7, 1, step)
+  b = Z.clone(); native.dropout_bf16(b, ctr, 1, 0.5, 7, 1, step)
+  assert torch.equal(a, b)                                  # same (seed, layer, step) -> same mask
+  assert torch.equal(a[3000:], Z[3000:])                    # rows beyond the device counter untouched
+  vals = a[:3000].float()
+  assert set(vals.unique().tolist()) == {0.0, 2.0}
+  assert abs((vals > 0).float().mean().item() - 0.5) < 0.01
+  step[0] = 1
+  c = Z.clone(); native.dropout_bf16(c, ctr, 1, 0.5, 7, 1, step)
+  assert not torch.equal(a, c)                              # next optimizer step -> new mask
+  d = Z.clone(); native.dropout_bf16(d, ctr, 1, 0.5, 7, 2, step)
+  assert not torch.equal(c, d)                              # other layer -> other mask
+  e = Z.clone(); native.dropout_bf16(e, ctr, 1, 0.25, 7, 1, step)
+  ve = e[:3000].float()
+  assert abs((ve > 0).float().mean().item() - 0.75) < 0.01
+  assert torch.allclose(ve[ve > 0], torch.tensor(1.0 / 0.75, device=DEV), rtol=1e-2)
+
+
+def test_engine_dropout_forward_backward_matches_pytorch_with_same_mask(native):
+  eng, feats, labels = _setup(dropout=0.5)
+  seeds = torch.randperm(6000, device=DEV)[:256]
+  eng.seeds_dev.copy_(seeds)
+  eng._sample(); eng._forward(); eng._backward()
+  torch.cuda.synchronize()
+  ref_loss, acts, params, cum = _dense_reference(eng, feats, labels, 256)
+  assert abs(float(eng.loss.item()) - ref_loss) < 3e-2 * max(1.0, abs(ref_loss))
+  for l in range(1, eng.L):
+    T = cum[eng.L - l + 1]
+    z = eng.Z[l][:T].float()
+    assert 0.15 < (z > 0).float().mean().item() < 0.35       # ~half of the ~half that survive the ReLU
+    assert torch.allclose(z, acts[l - 1][1].detach(), atol=6e-2, rtol=6e-2), f'Z{l}'
+  for l in range(1, eng.L + 1):
+    off, n, k = eng._w_off[l - 1]
+    gW = eng.g32[off:off + n * k].view(n, k)
+    W, b = params[l - 1]
+    ref = W.grad[:n, :k]
+    err = (gW - ref).abs().max().item()
+    assert err < 3e-2 * max(1.0, ref.abs().max().item()), (l, err)
+  # evaluation never drops
+  eng._forward(train=False)
+  torch.cuda.synchronize()
+  T = cum[eng.L]
+  assert (eng.Z[1][:T] > 0).float().mean().item() > 0.4
+
+
+def test_engine_with_dropout_still_learns(native):
+  eng, feats, _ = _setup(N=8000, E=100000, bs=512, fan=(4, 3), graph=True, C=8, dropout=0.3)
+  w = torch.randn(128, 8, device=DEV)
+  eng.labels = (feats.float() @ w).argmax(1)
+  eng.warmup_and_capture(n_eager=1)
+  losses = []
+  for i in range(80):
+    eng.train_step(torch.randperm(8000, device=DEV)[:512])
+    losses.append(float(eng.loss.item()))
+  assert losses[-1] < 0.7 * losses[0], (losses[0], losses[-1])
+  loss, correct, n = eng.evaluate_batch(torch.randperm(8000, device=DEV)[:512])
+  assert n == 512 and correct / n > 0.5
