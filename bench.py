@@ -56,6 +56,10 @@ SHAPES = {
 METRIC = 'GraphSAGE ogbn-products-shape training throughput (seed nodes/s, device-timed, max over ranks)'
 
 
+def metric_name(args):
+  return METRIC if args.shape == 'products' else METRIC.replace('ogbn-products-shape', f'ogbn-{args.shape}-shape')
+
+
 def parse_args(argv=None):
   p = argparse.ArgumentParser()
   p.add_argument('--gpus', type=int, default=1)
@@ -93,6 +97,12 @@ def parse_args(argv=None):
   p.add_argument('--hot-fraction', type=float, default=None,
                  help='multi-GPU: fraction of every rank\'s (hotness-ordered) feature rows replicated on all GPUs '
                       '(default 0.25 for products, 0.15 for papers100m like the reference example)')
+  p.add_argument('--replica-budget-gb', type=float, default=16.0,
+                 help='multi-GPU placement policy: per-GPU HBM budget for REPLICATED data.  The CSR is replicated on '
+                      'every GPU when it fits (the reference\'s multi-GPU layout: graph_mode=CUDA per trainer), the '
+                      'rest of the budget replicates the hottest feature rows (NVSwitch multicast fill); what does '
+                      'not fit stays range-partitioned and is read from peer HBM in-kernel.  0 = fully partitioned '
+                      '(hot fraction 0.25 / 0.15 as in round 1)')
   p.add_argument('--seed', type=int, default=0)
   p.add_argument('--sections', action='store_true', help='print per-stage device times (eager) and exit')
   p.add_argument('--profile-steps', type=int, default=0,
@@ -102,8 +112,22 @@ def parse_args(argv=None):
   for k in ('nodes', 'edges', 'feat_dim', 'classes'):
     if getattr(a, k) is None:
       setattr(a, k, sh[k])
+  a.replicate_topology = False
+  a.placement = 'explicit --hot-fraction'
   if a.hot_fraction is None:
-    a.hot_fraction = 0.15 if a.shape == 'papers100m' else 0.25
+    budget = a.replica_budget_gb * 2 ** 30
+    if budget <= 0:
+      a.hot_fraction = 0.15 if a.shape == 'papers100m' else 0.25
+      a.placement = 'partitioned (budget 0)'
+    else:
+      topo_bytes = a.edges * (4 if a.nodes < 2 ** 31 - 1 else 8)
+      if topo_bytes <= budget:
+        a.replicate_topology = True
+        budget -= topo_bytes
+      in_dim = (a.feat_dim + 63) // 64 * 64
+      row_bytes = in_dim * 2 if a.feat_format == 'bf16' else in_dim + 16
+      a.hot_fraction = min(1.0, budget / float(a.nodes * row_bytes))
+      a.placement = f'replica budget {a.replica_budget_gb:g} GB/GPU'
   if a.dtype == 'fp32':
     a.path = 'loader'
   return a
@@ -257,7 +281,7 @@ def build_ours(args, rank, world, device, need_engine=True):
   half = E // 2
   bounds = range_bounds(N, world)
   old2new = None
-  if world > 1 and args.hot_fraction > 0:
+  if world > 1 and 0 < args.hot_fraction < 1.0:
     # hotness reordering (the reference's examples do sort_by_in_degree + split_ratio): nodes are
     # sorted by degree and dealt round-robin to the ranks, so every rank's id range is balanced and
     # starts with its hottest rows, which are replicated on all GPUs through NVSwitch multicast
@@ -288,7 +312,7 @@ def build_ours(args, rank, world, device, need_engine=True):
     table = ut._table()
     keep = (graph, ut, feats, shard)
   else:
-    pg = PartitionedGraph(shard, bounds, device)
+    pg = PartitionedGraph(shard, bounds, device, replicate_topology=args.replicate_topology)
     graph = pg.graph
     b, e = bounds[rank], bounds[rank + 1]
     gl = torch.Generator(device=device)
@@ -301,7 +325,8 @@ def build_ours(args, rank, world, device, need_engine=True):
     if args.feat_format == 'mxfp8':
       local = torch.cat([glt.data.quantize_mxfp8(local[b0:min(e - b, b0 + rows)]) for b0 in range(0, e - b, rows)])
     pf = PartitionedFeature(local, bounds, device,
-                            hot_per_rank=int(args.hot_fraction * (bounds[1] - bounds[0])))
+                            hot_per_rank=min(int(args.hot_fraction * (bounds[1] - bounds[0])),
+                                             min(bounds[r + 1] - bounds[r] for r in range(world))))
     table = pf.table
     keep = (pg, pf)
   torch.cuda.empty_cache()
@@ -430,7 +455,7 @@ def run_ours(args):
       cfg = canonical_config(args, 1)
       cfg['precision'] = 'fp32' if args.dtype == 'fp32' else cfg['precision']
       print(json.dumps({
-        'metric': METRIC, 'value': arm['value'], 'unit': 'samples/s', 'n_gpus': 1, 'steps': K, 'warmup': W,
+        'metric': metric_name(args), 'value': arm['value'], 'unit': 'samples/s', 'n_gpus': 1, 'steps': K, 'warmup': W,
         'ms_per_step': arm['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': arm['value'] / BASELINE_SAMPLES_PER_S, 'dtype': args.dtype, 'data': 'synthetic',
         'impl': 'ours', 'config': cfg, 'details': {'path': 'loader', 'api': arm['api']}, 'timed': arm['timed'],
@@ -515,7 +540,7 @@ def run_ours(args):
     value = per_step_seeds / (dev_t['ms_per_step'] / 1e3)
     e2e = per_step_seeds / (e2e_t['ms_per_step'] / 1e3)
     out = {
-      'metric': METRIC, 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': K, 'warmup': W,
+      'metric': metric_name(args), 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': K, 'warmup': W,
       'ms_per_step': dev_t['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
       'vs_baseline': value / BASELINE_SAMPLES_PER_S, 'dtype': 'bf16', 'data': 'synthetic',
       'impl': 'ours',
@@ -529,8 +554,10 @@ def run_ours(args):
         'gather_backward': bool(eng.use_gather_bwd),
         'feature_format': args.feat_format,
         'remote_rows_staged_on_sampling_stream': bool(getattr(eng, 'stage_remote', False)),
-        'hot_feature_replica': (None if world == 1 else {'fraction': args.hot_fraction,
+        'hot_feature_replica': (None if world == 1 else {'fraction': round(args.hot_fraction, 4),
                                                          'fill': getattr(eng._keep[1], 'fill_mode', None)}),
+        'placement': (None if world == 1 else {'policy': args.placement,
+                                               'topology_replicated': bool(args.replicate_topology)}),
         'grad_allreduce': 'peer-HBM all-reduce fused into Adam (NVLink, in-graph)' if eng.peer_group is not None
                           else ('nccl' if world > 1 else 'none'),
         'cuda_graph': eng._graph_fb is not None, 'pipelined_sample_train_overlap': bool(eng.pipeline),
@@ -578,7 +605,7 @@ def run_reference(args):
   try:
     sys.path.insert(0, os.path.join(ROOT, 'baseline'))
     import ref_bench
-    ref_bench.main(args, BASELINE_SAMPLES_PER_S, canonical_config(args, int(os.environ.get('WORLD_SIZE', '1'))), METRIC)
+    ref_bench.main(args, BASELINE_SAMPLES_PER_S, canonical_config(args, int(os.environ.get('WORLD_SIZE', '1'))), metric_name(args))
   except Exception as e:  # the reference arm must never break the driver
     if int(os.environ.get('RANK', '0')) == 0:
       print(json.dumps({'impl': 'reference', 'unavailable': f'{type(e).__name__}: {str(e)[:200]}'}))

@@ -128,13 +128,15 @@ class GraphSageEngine(object):
     # Multi-GPU: the rows of a batch's nodes that live in PEER HBM are copied once per batch into a local buffer
     # indexed by local node id -- by a bulk gather kernel on the SAMPLING stream, one batch ahead of the training
     # step -- and the fused layer-1 kernel reads them from there (each is needed ~2.5x, and 256-byte random reads
-    # issued from inside the GEMM kernel are bound by NVLink latency, not bandwidth).  None = on when the feature
-    # table has non-local parts; False keeps the in-kernel peer loads of the fused layer.
+    # issued from inside the GEMM kernel are bound by NVLink latency, not bandwidth).  True = stage when the feature
+    # table has non-local parts; None/False = in-kernel peer loads (the measured default, see _build_buffers).
     self._stage_remote_opt = stage_remote_rows
     import os as _os3
     # measured on B200 (profiles/): running the weight-gradient GEMMs and the zero fills on an auxiliary stream LOSES 3 %
     # (0.245 vs 0.237 ms/step): the extra CTAs compete with the critical dgrad -> scatter -> cast chain.  Kept as an option.
     self.overlap_wgrad = _os3.environ.get('GLT_B200_OVERLAP_WGRAD', '0') != '0'
+    # pipelined engines: zero the fp32 scatter targets on the sampling stream (off the training chain)
+    self.side_zero = _os3.environ.get('GLT_B200_SIDE_ZERO', '0') != '0'
     self.deterministic_sampling = bool(deterministic_sampling)
     self.use_peer_allreduce = bool(use_peer_allreduce)
     # use_gather_bwd (csrc/cuda/transpose.cu, validated on B200 in round 2): the sampler also builds the transposed
@@ -250,7 +252,10 @@ class GraphSageEngine(object):
     want = self._stage_remote_opt
     if want is None:
       import os as _os4
-      want = _os4.environ.get('GLT_B200_STAGE_REMOTE', '1') != '0'
+      # measured (profiles/r2_gpu_call7_8gpu_session.log, call11): staging is neutral at 2 GPUs (0.275 vs 0.270 ms)
+      # and LOSES 4 % at 8 GPUs (0.308 vs 0.296 ms/step) -- the staging kernel competes with the sampler for the
+      # side stream and the unfused layer 1 already hides the NVLink latency behind its occupancy -> opt-in
+      want = _os4.environ.get('GLT_B200_STAGE_REMOTE', '0') != '0'
     has_remote = hasattr(self.feat, 'all_local') and not self.feat.all_local()
     self.stage_remote = bool(want and has_remote)
     self._xcache = None
@@ -613,11 +618,16 @@ class GraphSageEngine(object):
                               self.g32[pboff:pboff + pn])
           self._k(1)
           continue
-        nat.zero_rows(self.dH[l - 1], ar.counters, nh + 1)
+        if getattr(self, '_zero_ev', None) is not None:
+          if l == self.L:
+            main.wait_event(self._zero_ev)   # zero fills were issued on the sampling stream (_pipelined_body)
+        else:
+          nat.zero_rows(self.dH[l - 1], ar.counters, nh + 1)
+          self._k(1)
         nat.sage_scatter_bwd(self.dA[l], self.dims_in[l - 1], ar.counters, nh, ell, ks, ar.deg, self.dH[l - 1])
         nat.relu_bwd_cast(self.dH[l - 1], self.Z[l - 1], ar.counters, nh + 1, self.dPre[l - 1],
                           self.g32[pboff:pboff + pn], True, 1.0 / (1.0 - self.dropout))
-        self._k(3)
+        self._k(2)
 
   _f32_mode = None
 
@@ -666,10 +676,20 @@ class GraphSageEngine(object):
     self._cur = cur
     main = torch.cuda.current_stream()
     self._side.wait_stream(main)                       # fork
+    self._zero_ev = None
     with torch.cuda.stream(self._side):
+      if self.side_zero and self.L > 1 and not self.use_gather_bwd and not self.overlap_wgrad:
+        # the zero fill of the fp32 scatter targets of THIS step's backward leaves the training chain: it runs on
+        # the sampling stream (idle for 2/3 of the step) before the next batch is sampled
+        for l in range(self.L, 1, -1):
+          self.nat.zero_rows(self.dH[l - 1], self._arenas[cur].counters, self.L - l + 2)
+        self._k(self.L - 1)
+        self._zero_ev = torch.cuda.Event()
+        self._zero_ev.record(self._side)
       self._sample(1 - cur)
     self._forward()
     self._backward()
+    self._zero_ev = None
     main.wait_stream(self._side)                        # join
 
   def _step_eager(self):

@@ -76,6 +76,19 @@ def main():
   eb = set(zip(sb.node[sb.row].tolist(), sb.node[sb.col].tolist()))
   assert ea == eb and sa.num_sampled_nodes == sb.num_sampled_nodes
   ok('multi-hop arena sampling over peer CSR shards')
+  pgr = PartitionedGraph(shard_topology(topo, bounds, rank, dev), bounds, dev, replicate_topology=True)
+  c = NeighborSampler(pgr.graph, [5, 3], with_edge=True, seed=7, device=dev)
+  oc = c.sample_one_hop(seeds, 5, stream=3)
+  assert torch.equal(oa.nbr, oc.nbr) and torch.equal(oa.edge, oc.edge)
+  sc = c.sample_from_nodes(seeds)
+  ec = set(zip(sc.node[sc.row].tolist(), sc.node[sc.col].tolist()))
+  assert ea == ec
+  ok('sampling on the locally replicated topology (all shards pulled over NVLink at setup)')
+  # full feature replica: every rank's whole range is "hot" -> no remote part left in the table
+  per = min(bounds[r + 1] - bounds[r] for r in range(world))
+  pfa = PartitionedFeature(full[bounds[rank]:bounds[rank + 1]].clone(), bounds, dev, hot_per_rank=per)
+  assert torch.equal(pfa[ids], full[ids]), 'full-replica gather mismatch'
+  ok(f'full feature replica ({pfa.fill_mode})')
 
   # 4. engine step with partitioned graph + features
   from graphlearn_for_pytorch_b200.models import GraphSageEngine
@@ -116,12 +129,12 @@ def main():
     assert torch.allclose(e.Z[1][:T].float(), Z_ref, atol=8e-2, rtol=3e-2), f'fused layer output mismatch ({what})'
     ok(f'fused layer-1 numerics, {what}')
 
-  assert eng.stage_remote, 'a partitioned table must turn remote-row staging on by default'
-  check_fused(eng, 'remote rows staged into the local cache on the sampling stream')
-  eng_ip = GraphSageEngine(pg.graph, pf2.table, labels, in_dim=128, num_nodes=N, fanouts=[4, 3], batch_size=256,
-                           hidden=256, num_classes=8, device=dev, use_cuda_graph=False, stage_remote_rows=False)
-  assert not eng_ip.stage_remote
-  check_fused(eng_ip, 'peer rows read in place over NVLink from inside the tcgen05 kernel')
+  assert not eng.stage_remote, 'in-kernel peer loads are the measured default'
+  check_fused(eng, 'peer rows read in place over NVLink from inside the tcgen05 kernel')
+  eng_st = GraphSageEngine(pg.graph, pf2.table, labels, in_dim=128, num_nodes=N, fanouts=[4, 3], batch_size=256,
+                           hidden=256, num_classes=8, device=dev, use_cuda_graph=False, stage_remote_rows=True)
+  assert eng_st.stage_remote
+  check_fused(eng_st, 'remote rows staged into the local cache on the sampling stream')
   # parameters stay identical across ranks (all-reduced gradients)
   p = eng.p32.clone()
   dist.all_reduce(p, op=dist.ReduceOp.MAX)
