@@ -105,6 +105,8 @@ def parse_args(argv=None):
                       '(hot fraction 0.25 / 0.15 as in round 1)')
   p.add_argument('--seed', type=int, default=0)
   p.add_argument('--sections', action='store_true', help='print per-stage device times (eager) and exit')
+  p.add_argument('--kernel-times', action='store_true',
+                 help='print the in-situ device time of every launch of an eager step (warm L2, events) and exit')
   p.add_argument('--profile-steps', type=int, default=0,
                  help='run this many eager steps between cudaProfilerStart/Stop (for ncu) and exit')
   a = p.parse_args(argv)
@@ -476,6 +478,19 @@ def run_ours(args):
     if rank == 0:
       print(json.dumps({'sections_ms_max_over_ranks': dict(zip(sorted(sec), [round(float(x), 4) for x in t])),
                         'n_gpus': world}), flush=True)
+    if world > 1:
+      dist.barrier()
+      os._exit(0)
+    return
+  if args.kernel_times:
+    eng._graphs = []
+    nb = max(1, min(12, pool.numel() // bs))
+    kt = eng.profile_kernels(pool[:nb * bs].view(nb, bs).to(device), iters=10)
+    if rank == 0:
+      print('# in-situ device time per launch (eager unpipelined step, events, mean of 10 steps)')
+      for name, us in kt:
+        print(f'{us:9.2f} us  {name}')
+      print(f'{sum(u for _, u in kt):9.2f} us  total')
     if world > 1:
       dist.barrier()
       os._exit(0)

@@ -271,7 +271,7 @@ struct SamplerArena {
   // every sample() once enable_transpose(n_hops) was called
   int tr_hops = 0;
   int64_t tr_cap_edges = 0;
-  Tensor tr_cnt, tr_off, tr_cursor, tr_tgt, tr_block_sums;
+  Tensor tr_cnt, tr_off, tr_cursor, tr_tgt, tr_block_sums, tr_meta, tr_meta_inv;
 
   // cap_override: optional calibrated frontier capacities per hop (+ one trailing entry for the
   // number of nodes the last hop may add); empty = worst case (max_seeds * prod(fanouts)).
@@ -321,6 +321,8 @@ struct SamplerArena {
     tr_off = torch::zeros({cap_nodes + 1}, o32);
     tr_tgt = torch::zeros({std::max<int64_t>(tr_cap_edges, 1)}, o32);
     tr_block_sums = torch::zeros({cap_nodes / 1024 + 2}, o32);
+    tr_meta = torch::zeros({cap_nodes, 4}, o32);
+    tr_meta_inv = torch::zeros({cap_nodes, 2}, o32.dtype(torch::kFloat32));
   }
 
   void build_transpose(cudaStream_t s) {
@@ -341,6 +343,8 @@ struct SamplerArena {
     a.cursor = tr_cursor.data_ptr<int32_t>();
     a.tgt = tr_tgt.data_ptr<int32_t>();
     a.block_sums = tr_block_sums.data_ptr<int32_t>();
+    a.meta = tr_meta.data_ptr<int32_t>();
+    a.meta_inv = tr_meta_inv.data_ptr<float>();
     launch_build_transpose(a, s);
   }
 
@@ -899,11 +903,13 @@ static void add_block_f32(const Tensor& dA, int64_t col, int64_t d, const Tensor
 
 // EXPERIMENTAL atomics-free backward of the mean aggregation over the arena's transposed adjacency
 static void sage_gather_bwd(const Tensor& dA, int64_t d, SamplerArena& ar, int64_t n_hops_targets,
-                            const c10::optional<Tensor>& Z, Tensor dPre, const c10::optional<Tensor>& colsum) {
+                            const c10::optional<Tensor>& Z, Tensor dPre, const c10::optional<Tensor>& colsum,
+                            bool prezeroed, double gscale) {
   c10::cuda::CUDAGuard guard(dA.device());
   TORCH_CHECK(ar.tr_hops >= n_hops_targets && n_hops_targets >= 1, "enable_transpose(n_hops) covers too few hops");
   TORCH_CHECK(dA.scalar_type() == torch::kBFloat16 && dA.is_contiguous() && dA.size(1) == 2 * d && d % 8 == 0);
   TORCH_CHECK(dPre.scalar_type() == torch::kBFloat16 && dPre.is_contiguous() && dPre.size(1) == d);
+  TORCH_CHECK(d <= 1024, "sage_gather_bwd: d <= 1024");
   SageGatherBwdArgs a{};
   a.dA = dA.data_ptr();
   a.d = static_cast<int>(d);
@@ -916,6 +922,8 @@ static void sage_gather_bwd(const Tensor& dA, int64_t d, SamplerArena& ar, int64
   a.off = ar.tr_off.data_ptr<int32_t>();
   a.cnt_upto = ar.tr_cnt.data_ptr<int32_t>() + (n_hops_targets - 1) * ar.cap_nodes;
   a.tgt = ar.tr_tgt.data_ptr<int32_t>();
+  a.meta = ar.tr_meta.data_ptr<int32_t>();
+  a.meta_inv = ar.tr_meta_inv.data_ptr<float>();
   a.Z = nullptr;
   if (Z.has_value() && Z->defined()) {
     TORCH_CHECK(Z->scalar_type() == torch::kBFloat16 && Z->is_contiguous() && Z->size(1) == d && Z->size(0) >= dPre.size(0));
@@ -924,9 +932,12 @@ static void sage_gather_bwd(const Tensor& dA, int64_t d, SamplerArena& ar, int64
   a.dPre = dPre.data_ptr();
   a.colsum = nullptr;
   if (colsum.has_value() && colsum->defined()) {
-    TORCH_CHECK(colsum->scalar_type() == torch::kFloat32 && colsum->numel() >= d);
+    TORCH_CHECK(colsum->scalar_type() == torch::kFloat32 && colsum->numel() >= d && d % 4 == 0 &&
+                reinterpret_cast<uintptr_t>(colsum->data_ptr()) % 16 == 0, "colsum: fp32 [d], 16-byte aligned");
     a.colsum = colsum->data_ptr<float>();
   }
+  a.colsum_prezeroed = prezeroed ? 1 : 0;
+  a.gscale = static_cast<float>(gscale);
   launch_sage_gather_bwd(a, cur_stream());
   check_cuda_err("sage_gather_bwd");
 }
@@ -999,6 +1010,27 @@ static void zero_grads(Tensor g, const c10::optional<Tensor>& loss, const c10::o
                     (loss.has_value() && loss->defined()) ? loss->data_ptr<float>() : nullptr,
                     (correct.has_value() && correct->defined()) ? correct->data_ptr<int32_t>() : nullptr, cur_stream());
   check_cuda_err("zero_grads");
+}
+
+static void zero_step(Tensor g, const c10::optional<Tensor>& loss, const c10::optional<Tensor>& correct,
+                      std::vector<Tensor> rows, const Tensor& counters, std::vector<int64_t> idx) {
+  c10::cuda::CUDAGuard guard(g.device());
+  TORCH_CHECK(g.scalar_type() == torch::kFloat32 && g.is_contiguous() &&
+              reinterpret_cast<uintptr_t>(g.data_ptr()) % 16 == 0);
+  TORCH_CHECK(rows.size() <= 3 && rows.size() == idx.size(), "zero_step: at most 3 row buffers");
+  float* ptr[3] = {nullptr, nullptr, nullptr};
+  int ix[3] = {0, 0, 0}, cap[3] = {0, 0, 0}, d[3] = {0, 0, 0};
+  for (size_t q = 0; q < rows.size(); ++q) {
+    TORCH_CHECK(rows[q].scalar_type() == torch::kFloat32 && rows[q].is_contiguous() && rows[q].dim() == 2 &&
+                rows[q].size(1) % 4 == 0);
+    ptr[q] = rows[q].data_ptr<float>();
+    ix[q] = static_cast<int>(idx[q]); cap[q] = static_cast<int>(rows[q].size(0)); d[q] = static_cast<int>(rows[q].size(1));
+  }
+  launch_zero_step(g.data_ptr<float>(), g.numel(),
+                   (loss.has_value() && loss->defined()) ? loss->data_ptr<float>() : nullptr,
+                   (correct.has_value() && correct->defined()) ? correct->data_ptr<int32_t>() : nullptr, ptr,
+                   counters.data_ptr<int32_t>(), ix, cap, d, static_cast<int>(rows.size()), cur_stream());
+  check_cuda_err("zero_step");
 }
 
 static void colsum_bf16(const Tensor& X, const Tensor& counters, int64_t n_hops, Tensor out) {
@@ -1529,8 +1561,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("dropout_bf16", &dropout_bf16, py::arg("Z"), py::arg("counters"), py::arg("n_hops"), py::arg("p"),
         py::arg("seed"), py::arg("layer"), py::arg("step_dev") = py::none());
   m.def("zero_grads", &zero_grads);
+  m.def("zero_step", &zero_step);
   m.def("set_pdl", [](bool on) { return set_pdl(on ? 1 : 0) != 0; });
-  m.def("sage_gather_bwd", &sage_gather_bwd);
+  m.def("sage_gather_bwd", &sage_gather_bwd, py::arg("dA"), py::arg("d"), py::arg("arena"), py::arg("n_hops_targets"),
+        py::arg("Z"), py::arg("dPre"), py::arg("colsum"), py::arg("prezeroed") = false, py::arg("gscale") = 1.0);
   m.def("bias_relu", &bias_relu);
   m.def("softmax_nll", &softmax_nll, py::arg("logits"), py::arg("C"), py::arg("y"), py::arg("labels_all"),
         py::arg("nodes"), py::arg("counters"), py::arg("loss"), py::arg("dlogits"), py::arg("correct"),

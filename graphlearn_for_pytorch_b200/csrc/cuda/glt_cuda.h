@@ -225,6 +225,9 @@ struct TransposeArgs {
   int32_t* cursor;           // [n_hops][cap_nodes]: fill cursor per hop
   int32_t* tgt;              // [cap_edges]: target local ids
   int32_t* block_sums;       // [>= cap_nodes / 1024 + 2]
+  int32_t* meta;             // [cap_nodes][4] = {segment start, first in-neighbour, second in-neighbour, total in-edges}
+  float* meta_inv;           // [cap_nodes][2] = 1/deg of those two (the backward gather reads one record per source
+                             // instead of walking off -> tgt -> deg)
 };
 void launch_build_transpose(const TransposeArgs& a, cudaStream_t s);
 
@@ -239,9 +242,13 @@ struct SageGatherBwdArgs {
   const int32_t* off;        // transposed CSR
   const int32_t* cnt_upto;   // [cap_nodes] in-edges of the hops used by this layer (prefix of the segment)
   const int32_t* tgt;
+  const int32_t* meta;       // TransposeArgs::meta / meta_inv
+  const float* meta_inv;
   const void* Z;             // bf16 [cap_src, d] activations of the previous layer (ReLU mask) or nullptr
   void* dPre;                // bf16 [cap_src, d]
-  float* colsum;             // optional fp32 [d]: bias gradient
+  float* colsum;             // optional fp32 [d]: bias gradient (16-byte aligned: accumulated with red.v4)
+  int colsum_prezeroed;      // the caller already zeroed colsum (no memset node in the launch chain)
+  float gscale;              // 1/(1-p) when Z is a post-dropout activation, else 1
 };
 // dPre[s] = relu'(Z[s]) * (dA_self[s] + sum_{t in in(s)} dA_mean[t] / deg[t]); rows >= sources are zero-filled.
 // Replaces zero_rows + sage_scatter_bwd (fp32 atomics) + relu_bwd_cast.
@@ -260,6 +267,9 @@ void launch_dropout_bf16(void* Z, const int32_t* cum, int n_hops, int cap, int d
 // g[0..n) = 0, *loss = 0, *correct = 0 (one launch at the start of the gradient phase; the *_prezeroed variants of
 // the kernels below then skip their own memsets, which keeps the step a pure kernel chain)
 void launch_zero_grads(float* g, int64_t n, float* loss, int32_t* correct, cudaStream_t s);
+// launch_zero_grads + the zero fill of up to 3 fp32 row buffers (rows < cum[idx[q]]) in ONE launch
+void launch_zero_step(float* g, int64_t n, float* loss, int32_t* correct, float* const* rows, const int32_t* cum,
+                      const int* idx, const int* cap, const int* d, int n_rows, cudaStream_t s);
 // bias + relu epilogue over valid rows (zero beyond): Z = relu(Z + b)
 void launch_bias_relu(void* Z, const void* bias, const int32_t* cum, int n_hops, int cap, int d,
                       int relu, cudaStream_t s);

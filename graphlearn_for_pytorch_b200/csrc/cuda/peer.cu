@@ -73,10 +73,17 @@ __global__ void __launch_bounds__(256) k_adam_peer(PeerPtrs p, float* param, flo
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    // all peer loads of a batch of 8 ranks are issued before the first add: one NVLink round trip per batch
+    // instead of one per rank (the adds keep rank order: identical result on every rank)
 #pragma unroll 1
-    for (int r = 0; r < p.world; ++r) {  // fixed order: identical result on every rank
-      const float4 x = ld_cv4(p.g[r] + i * 4);
-      g.x += x.x; g.y += x.y; g.z += x.z; g.w += x.w;
+    for (int r0 = 0; r0 < p.world; r0 += 8) {
+      float4 x[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (r0 + q < p.world) x[q] = ld_cv4(p.g[r0 + q] + i * 4);
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (r0 + q < p.world) { g.x += x[q].x; g.y += x[q].y; g.z += x[q].z; g.w += x[q].w; }
     }
     float gi[4] = {g.x, g.y, g.z, g.w};
     float4 pp = reinterpret_cast<float4*>(param)[i];

@@ -35,7 +35,7 @@ __device__ __forceinline__ const uint8_t* src_row(const SageAggArgs& a, int s) {
 }
 
 // LPR lanes cooperate on one target row; each lane owns VPL 16-byte vectors.
-template <int LPR, int VPL, int NB>
+template <int LPR, int VPL>
 __global__ void __launch_bounds__(256) k_sage_aggregate(SageAggArgs a) {
   pdl_enter();
   constexpr int RPW = 32 / LPR;
@@ -69,37 +69,14 @@ __global__ void __launch_bounds__(256) k_sage_aggregate(SageAggArgs a) {
         if (s >= 0) my_ptr = src_row(a, s);
       }
       const int cnt = min(LPR, dg - j0);
-      if (NB == 1) {
-        for (int jj = 0; jj < cnt; ++jj) {
-          const uint8_t* p = reinterpret_cast<const uint8_t*>(
-              __shfl_sync(gmask, reinterpret_cast<unsigned long long>(my_ptr), jj, LPR));
-          if (p == nullptr) continue;
+      for (int jj = 0; jj < cnt; ++jj) {
+        const uint8_t* p = reinterpret_cast<const uint8_t*>(
+            __shfl_sync(gmask, reinterpret_cast<unsigned long long>(my_ptr), jj, LPR));
+        if (p == nullptr) continue;
 #pragma unroll
-          for (int v = 0; v < VPL; ++v) {
-            const int c = v * LPR + gl;
-            if (c < nvec) bf16x8_accum(ld_nc_v4(p + c * 16), acc[v]);
-          }
-        }
-      } else {
-        // EXPERIMENTAL (GLT_B200_AGG_BATCH=1): NB neighbour rows in flight per lane group before accumulating
-        for (int jb = 0; jb < cnt; jb += NB) {
-          uint4 buf[NB][VPL];
-#pragma unroll
-          for (int q = 0; q < NB; ++q) {
-            const int jj = min(jb + q, LPR - 1);
-            const uint8_t* p = reinterpret_cast<const uint8_t*>(
-                __shfl_sync(gmask, reinterpret_cast<unsigned long long>(my_ptr), jj, LPR));
-            const bool ok = (jb + q < cnt) && p != nullptr;
-#pragma unroll
-            for (int v = 0; v < VPL; ++v) {
-              const int c = v * LPR + gl;
-              buf[q][v] = (ok && c < nvec) ? ld_nc_v4(p + c * 16) : make_uint4(0, 0, 0, 0);
-            }
-          }
-#pragma unroll
-          for (int q = 0; q < NB; ++q)
-#pragma unroll
-            for (int v = 0; v < VPL; ++v) bf16x8_accum(buf[q][v], acc[v]);
+        for (int v = 0; v < VPL; ++v) {
+          const int c = v * LPR + gl;
+          if (c < nvec) bf16x8_accum(ld_nc_v4(p + c * 16), acc[v]);
         }
       }
     }
@@ -396,6 +373,32 @@ __global__ void k_zero_grads(float* g, int64_t n, float* loss, int32_t* correct)
   }
 }
 
+// k_zero_grads + up to 3 k_zero_rows in one launch (the fp32 scatter targets of the backward pass)
+struct ZeroStepArgs {
+  float* g; int64_t n; float* loss; int32_t* correct;
+  float* rows[3]; const int32_t* cum; int idx[3]; int cap[3]; int d[3]; int n_rows;
+};
+__global__ void __launch_bounds__(256) k_zero_step(ZeroStepArgs a) {
+  pdl_enter();
+  const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t nth = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int64_t n4 = a.n >> 2;
+  for (int64_t i = tid; i < n4; i += nth) reinterpret_cast<float4*>(a.g)[i] = z;
+  if (blockIdx.x == 0) {
+    for (int64_t i = (n4 << 2) + threadIdx.x; i < a.n; i += blockDim.x) a.g[i] = 0.f;
+    if (threadIdx.x == 0) {
+      if (a.loss) *a.loss = 0.f;
+      if (a.correct) *a.correct = 0;
+    }
+  }
+  for (int q = 0; q < a.n_rows; ++q) {
+    const int T = min(a.cum[a.idx[q]], a.cap[q]);
+    const int64_t m4 = static_cast<int64_t>(T) * a.d[q] / 4;
+    for (int64_t i = tid; i < m4; i += nth) reinterpret_cast<float4*>(a.rows[q])[i] = z;
+  }
+}
+
 __global__ void k_zero_rows(float* p, const int32_t* cum, int n_hops, int cap, int d) {
   pdl_enter();
   const int T = min(cum[n_hops], cap);
@@ -446,15 +449,10 @@ int set_pdl(int on) {
 }
 
 void launch_sage_aggregate(const SageAggArgs& a, cudaStream_t s) {
-  static const bool batched = [] {
-    const char* e = std::getenv("GLT_B200_AGG_BATCH");
-    return e && std::atoi(e) != 0;
-  }();
+  // (a variant keeping 4 neighbour rows in flight per lane group before accumulating measured 3 % SLOWER in the
+  // step -- 0.2447 vs 0.2380 ms, profiles/r2_gpu_call12 -- and was removed: the rows are L2-resident activations)
   GLT_DISPATCH_WIDTH(a.d, {
-    if (batched && VPL <= 2)
-      launch_k(k_sage_aggregate<LPR, VPL, 4>, dim3(grid_for(a.cap_targets, 8 * (32 / LPR))), dim3(256), 0, s, a);
-    else
-      launch_k(k_sage_aggregate<LPR, VPL, 1>, dim3(grid_for(a.cap_targets, 8 * (32 / LPR))), dim3(256), 0, s, a);
+    launch_k(k_sage_aggregate<LPR, VPL>, dim3(grid_for(a.cap_targets, 8 * (32 / LPR))), dim3(256), 0, s, a);
   });
 }
 
@@ -558,6 +556,21 @@ void launch_add_block_f32(const void* dA, int dA_ld, int col, int d, const int32
 
 void launch_zero_grads(float* g, int64_t n, float* loss, int32_t* correct, cudaStream_t s) {
   launch_k(k_zero_grads, dim3(grid_for(n / 4 + 1, 256, 148 * 2)), dim3(256), 0, s, g, n, loss, correct);
+}
+
+void launch_zero_step(float* g, int64_t n, float* loss, int32_t* correct, float* const* rows, const int32_t* cum,
+                      const int* idx, const int* cap, const int* d, int n_rows, cudaStream_t s) {
+  ZeroStepArgs a;
+  a.g = g; a.n = n; a.loss = loss; a.correct = correct; a.cum = cum; a.n_rows = n_rows;
+  int64_t items = n / 4 + 1;
+  for (int q = 0; q < 3; ++q) {
+    a.rows[q] = q < n_rows ? rows[q] : nullptr;
+    a.idx[q] = q < n_rows ? idx[q] : 0;
+    a.cap[q] = q < n_rows ? cap[q] : 0;
+    a.d[q] = q < n_rows ? d[q] : 0;
+    if (q < n_rows) items += static_cast<int64_t>(cap[q]) * d[q] / 4;
+  }
+  launch_k(k_zero_step, dim3(grid_for(items, 256 * 4, 148 * 8)), dim3(256), 0, s, a);
 }
 
 void launch_zero_rows(float* p, const int32_t* cum, int n_hops, int cap, int d, cudaStream_t s) {

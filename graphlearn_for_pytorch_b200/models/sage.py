@@ -136,7 +136,13 @@ class GraphSageEngine(object):
     # (0.245 vs 0.237 ms/step): the extra CTAs compete with the critical dgrad -> scatter -> cast chain.  Kept as an option.
     self.overlap_wgrad = _os3.environ.get('GLT_B200_OVERLAP_WGRAD', '0') != '0'
     # pipelined engines: zero the fp32 scatter targets on the sampling stream (off the training chain)
+    # (measured: 0.2435 vs 0.2380 ms/step -- the fill then competes with the fused layer-1 loaders for bandwidth)
     self.side_zero = _os3.environ.get('GLT_B200_SIDE_ZERO', '0') != '0'
+    # zero the gradient buffer AND the scatter targets in one launch at the start of the gradient phase
+    self.merged_zero = _os3.environ.get('GLT_B200_MERGED_ZERO', '0') != '0'
+    # programmatic dependent launch in pipelined capture: 'off' (measured default), 'train' (training-stream kernels
+    # only), 'all'
+    self.pdl_mode = _os3.environ.get('GLT_B200_PDL_MODE', 'off')
     self.deterministic_sampling = bool(deterministic_sampling)
     self.use_peer_allreduce = bool(use_peer_allreduce)
     # use_gather_bwd (csrc/cuda/transpose.cu, validated on B200 in round 2): the sampler also builds the transposed
@@ -145,7 +151,7 @@ class GraphSageEngine(object):
     if use_gather_bwd is None:
       import os as _os
       use_gather_bwd = _os.environ.get('GLT_B200_GATHER_BWD', '0') == '1'
-    self.use_gather_bwd = bool(use_gather_bwd) and self.dropout == 0.0
+    self.use_gather_bwd = bool(use_gather_bwd) and int(hidden) <= 1024
     # every dense contraction outside the fused layer-1 kernel runs on the TMA-fed tcgen05 GEMM kernel
     # (csrc/cuda/tc_gemm.cu); GLT_B200_TC_GEMM=0 falls back to cuBLAS for A/B measurements
     import os as _os2
@@ -535,7 +541,15 @@ class GraphSageEngine(object):
       self._k(1)
     # one launch zeroes the flat gradient buffer, the loss and the #correct counter; the kernels that accumulate
     # into them then skip their own memsets (memset nodes would cut the programmatic-launch chain of the step)
-    self.nat.zero_grads(self.g32, self.loss, self.correct)
+    self._rows_zeroed = False
+    if self.merged_zero and self.L > 1 and self.L <= 4 and not self.use_gather_bwd and \
+        getattr(self, '_zero_ev', None) is None and not self.overlap_wgrad:
+      # ... and the fp32 scatter targets of the backward pass in the same launch
+      self.nat.zero_step(self.g32, self.loss, self.correct, [self.dH[l - 1] for l in range(self.L, 1, -1)],
+                         self.arena.counters, [self.L - l + 2 for l in range(self.L, 1, -1)])
+      self._rows_zeroed = True
+    else:
+      self.nat.zero_grads(self.g32, self.loss, self.correct)
     self._k(1)
 
   def _plan(self, kind: str, l: int):
@@ -615,12 +629,14 @@ class GraphSageEngine(object):
         pboff, pn = self._b_off[l - 2]
         if self.use_gather_bwd:
           nat.sage_gather_bwd(self.dA[l], self.dims_in[l - 1], ar, nh, self.Z[l - 1], self.dPre[l - 1],
-                              self.g32[pboff:pboff + pn])
+                              self.g32[pboff:pboff + pn], True, 1.0 / (1.0 - self.dropout))
           self._k(1)
           continue
         if getattr(self, '_zero_ev', None) is not None:
           if l == self.L:
             main.wait_event(self._zero_ev)   # zero fills were issued on the sampling stream (_pipelined_body)
+        elif getattr(self, '_rows_zeroed', False):
+          pass                               # zeroed by k_zero_step at the start of the gradient phase
         else:
           nat.zero_rows(self.dH[l - 1], ar.counters, nh + 1)
           self._k(1)
@@ -686,7 +702,12 @@ class GraphSageEngine(object):
         self._k(self.L - 1)
         self._zero_ev = torch.cuda.Event()
         self._zero_ev.record(self._side)
-      self._sample(1 - cur)
+      if self.pdl_mode == 'train':
+        prev = self.nat.set_pdl(False)       # sampling kernels without the programmatic-launch attribute
+        self._sample(1 - cur)
+        self.nat.set_pdl(prev)
+      else:
+        self._sample(1 - cur)
     self._forward()
     self._backward()
     self._zero_ev = None
@@ -767,7 +788,8 @@ class GraphSageEngine(object):
         return
       # programmatic dependent launch helps single-stream chains and costs ~2 % when the sampling and training
       # streams interleave (measured, csrc/cuda/launch_utils.h): captured without it in pipelined mode
-      prev_pdl = self.nat.set_pdl(not self.pipeline) if hasattr(self.nat, 'set_pdl') else None
+      prev_pdl = self.nat.set_pdl((not self.pipeline) or self.pdl_mode in ('train', 'all')) \
+          if hasattr(self.nat, 'set_pdl') else None
       # capturing NCCL collectives works but makes process-group teardown hang on this stack
       # (measured: bench exit blocked until the timeout), so it is opt-in for world > 1
       single = self.world == 1 or self.peer_group is not None or \
@@ -887,6 +909,68 @@ class GraphSageEngine(object):
         for i, n in enumerate(names):
           acc[n] += ev[i].elapsed_time(ev[i + 1]) / iters
     return acc
+
+  def profile_kernels(self, seeds: torch.Tensor, iters: int = 10, queue_ahead_cycles: int = 6_000_000):
+    """Device time (us) of EVERY launch of an eager, unpipelined step, in launch order: -> [(name, us)].
+    Each native call is bracketed by CUDA events; a spin kernel at the head of the step lets the host queue the
+    whole step ahead of the GPU, so an interval is the kernel's own run time with the previous kernel's data still
+    in L2 (what `ncu`, which replays each kernel with cold caches, cannot show).  Diagnostic only."""
+    eng = self
+    log = []
+
+    class _Timed(object):
+      def __init__(self, obj, prefix=''):
+        object.__setattr__(self, '_o', obj)
+        object.__setattr__(self, '_p', prefix)
+
+      def __getattr__(self, name):
+        f = getattr(self._o, name)
+        if name in ('TcGemm', 'TcGemmMx'):
+          return lambda *a, **k: _Timed(f(*a, **k), name + '.')
+        if not callable(f) or name.startswith('_') or isinstance(f, type) or name in ('set_pdl',):
+          return f
+
+        def call(*a, **k):
+          e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+          e0.record()
+          r = f(*a, **k)
+          e1.record()
+          log.append((self._p + name, e0, e1))
+          return r
+        return call
+
+    real_nat, real_plans = self.nat, self._tc_plans
+    batches = seeds if seeds.dim() == 2 else seeds.unsqueeze(0)
+    acc, names = None, None
+    try:
+      self.nat, self._tc_plans = _Timed(real_nat), {}
+      self._cur = 0
+      for it in range(iters + 2):
+        del log[:]
+        self._stage_seeds(self._seeds[0], batches[it % batches.shape[0]])
+        torch.cuda._sleep(int(queue_ahead_cycles))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ar = self._arenas[0]
+        ar.sample(self.gh, self._seeds[0], None, self.seed, 0, False, False, True, len(self._arenas))
+        e1.record()
+        log.append(('arena.sample (all sampling kernels)', e0, e1))
+        if self.stage_remote:
+          self.feat.stage_remote_rows(ar.nodes, ar.counters, self.L + 1, self._xcache[0])
+        self._forward()
+        self._backward()
+        self._allreduce()
+        self._optimizer()
+        torch.cuda.synchronize()
+        if it >= 2:
+          if acc is None:
+            names, acc = [n for n, _, _ in log], [0.0] * len(log)
+          if len(log) == len(acc):
+            for i, (_, a0, a1) in enumerate(log):
+              acc[i] += a0.elapsed_time(a1) * 1e3 / iters
+    finally:
+      self.nat, self._tc_plans = real_nat, real_plans
+    return list(zip(names, acc))
 
   @torch.no_grad()
   def evaluate_batch(self, seeds: torch.Tensor):

@@ -268,7 +268,8 @@ def test_transposed_adjacency_matches_ell(native):
 
 
 @experimental
-def test_gather_backward_matches_pytorch(native):
+@pytest.mark.parametrize('hidden', [256, 512, 64])
+def test_gather_backward_matches_pytorch(native, hidden):
   ei, topo = rmat_csr(6000, 120000, seed=3)
   g = glt.data.Graph(topo, 'CUDA', 0)
   torch.manual_seed(0)
@@ -277,7 +278,7 @@ def test_gather_backward_matches_pytorch(native):
   ut = glt.data.UnifiedTensor(0, torch.bfloat16)
   ut.append_shared_tensor(feats)
   eng = GraphSageEngine(g, ut._table(), labels, in_dim=128, num_nodes=6000, fanouts=[5, 4, 3], batch_size=256,
-                        hidden=256, num_classes=47, device=DEV, use_fused=True, use_cuda_graph=False, seed=5,
+                        hidden=hidden, num_classes=47, device=DEV, use_fused=(hidden <= 256), use_cuda_graph=False, seed=5,
                         use_gather_bwd=True)
   eng.seeds_dev.copy_(torch.randperm(6000, device=DEV)[:256])
   eng._sample(); eng._forward(); eng._backward()
@@ -437,8 +438,10 @@ def test_dropout_kernel_mask_is_keyed_by_step_and_scaled(native):
   assert torch.allclose(ve[ve > 0], torch.tensor(1.0 / 0.75, device=DEV), rtol=1e-2)
 
 
-def test_engine_dropout_forward_backward_matches_pytorch_with_same_mask(native):
-  eng, feats, labels = _setup(dropout=0.5)
+@pytest.mark.parametrize('gather', [False, True])
+def test_engine_dropout_forward_backward_matches_pytorch_with_same_mask(native, gather):
+  eng, feats, labels = _setup(dropout=0.5, use_gather_bwd=gather)
+  assert eng.use_gather_bwd == gather
   seeds = torch.randperm(6000, device=DEV)[:256]
   eng.seeds_dev.copy_(seeds)
   eng._sample(); eng._forward(); eng._backward()
