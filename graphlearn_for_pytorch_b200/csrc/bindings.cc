@@ -1012,27 +1012,6 @@ static void zero_grads(Tensor g, const c10::optional<Tensor>& loss, const c10::o
   check_cuda_err("zero_grads");
 }
 
-static void zero_step(Tensor g, const c10::optional<Tensor>& loss, const c10::optional<Tensor>& correct,
-                      std::vector<Tensor> rows, const Tensor& counters, std::vector<int64_t> idx) {
-  c10::cuda::CUDAGuard guard(g.device());
-  TORCH_CHECK(g.scalar_type() == torch::kFloat32 && g.is_contiguous() &&
-              reinterpret_cast<uintptr_t>(g.data_ptr()) % 16 == 0);
-  TORCH_CHECK(rows.size() <= 3 && rows.size() == idx.size(), "zero_step: at most 3 row buffers");
-  float* ptr[3] = {nullptr, nullptr, nullptr};
-  int ix[3] = {0, 0, 0}, cap[3] = {0, 0, 0}, d[3] = {0, 0, 0};
-  for (size_t q = 0; q < rows.size(); ++q) {
-    TORCH_CHECK(rows[q].scalar_type() == torch::kFloat32 && rows[q].is_contiguous() && rows[q].dim() == 2 &&
-                rows[q].size(1) % 4 == 0);
-    ptr[q] = rows[q].data_ptr<float>();
-    ix[q] = static_cast<int>(idx[q]); cap[q] = static_cast<int>(rows[q].size(0)); d[q] = static_cast<int>(rows[q].size(1));
-  }
-  launch_zero_step(g.data_ptr<float>(), g.numel(),
-                   (loss.has_value() && loss->defined()) ? loss->data_ptr<float>() : nullptr,
-                   (correct.has_value() && correct->defined()) ? correct->data_ptr<int32_t>() : nullptr, ptr,
-                   counters.data_ptr<int32_t>(), ix, cap, d, static_cast<int>(rows.size()), cur_stream());
-  check_cuda_err("zero_step");
-}
-
 static void colsum_bf16(const Tensor& X, const Tensor& counters, int64_t n_hops, Tensor out) {
   c10::cuda::CUDAGuard guard(X.device());
   TORCH_CHECK(X.scalar_type() == torch::kBFloat16 && X.is_contiguous() && X.size(1) % 8 == 0);
@@ -1561,7 +1540,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("dropout_bf16", &dropout_bf16, py::arg("Z"), py::arg("counters"), py::arg("n_hops"), py::arg("p"),
         py::arg("seed"), py::arg("layer"), py::arg("step_dev") = py::none());
   m.def("zero_grads", &zero_grads);
-  m.def("zero_step", &zero_step);
   m.def("set_pdl", [](bool on) { return set_pdl(on ? 1 : 0) != 0; });
   m.def("sage_gather_bwd", &sage_gather_bwd, py::arg("dA"), py::arg("d"), py::arg("arena"), py::arg("n_hops_targets"),
         py::arg("Z"), py::arg("dPre"), py::arg("colsum"), py::arg("prezeroed") = false, py::arg("gscale") = 1.0);

@@ -267,9 +267,6 @@ void launch_dropout_bf16(void* Z, const int32_t* cum, int n_hops, int cap, int d
 // g[0..n) = 0, *loss = 0, *correct = 0 (one launch at the start of the gradient phase; the *_prezeroed variants of
 // the kernels below then skip their own memsets, which keeps the step a pure kernel chain)
 void launch_zero_grads(float* g, int64_t n, float* loss, int32_t* correct, cudaStream_t s);
-// launch_zero_grads + the zero fill of up to 3 fp32 row buffers (rows < cum[idx[q]]) in ONE launch
-void launch_zero_step(float* g, int64_t n, float* loss, int32_t* correct, float* const* rows, const int32_t* cum,
-                      const int* idx, const int* cap, const int* d, int n_rows, cudaStream_t s);
 // bias + relu epilogue over valid rows (zero beyond): Z = relu(Z + b)
 void launch_bias_relu(void* Z, const void* bias, const int32_t* cum, int n_hops, int cap, int d,
                       int relu, cudaStream_t s);

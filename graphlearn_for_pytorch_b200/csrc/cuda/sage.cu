@@ -373,32 +373,6 @@ __global__ void k_zero_grads(float* g, int64_t n, float* loss, int32_t* correct)
   }
 }
 
-// k_zero_grads + up to 3 k_zero_rows in one launch (the fp32 scatter targets of the backward pass)
-struct ZeroStepArgs {
-  float* g; int64_t n; float* loss; int32_t* correct;
-  float* rows[3]; const int32_t* cum; int idx[3]; int cap[3]; int d[3]; int n_rows;
-};
-__global__ void __launch_bounds__(256) k_zero_step(ZeroStepArgs a) {
-  pdl_enter();
-  const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  const int64_t nth = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-  const int64_t n4 = a.n >> 2;
-  for (int64_t i = tid; i < n4; i += nth) reinterpret_cast<float4*>(a.g)[i] = z;
-  if (blockIdx.x == 0) {
-    for (int64_t i = (n4 << 2) + threadIdx.x; i < a.n; i += blockDim.x) a.g[i] = 0.f;
-    if (threadIdx.x == 0) {
-      if (a.loss) *a.loss = 0.f;
-      if (a.correct) *a.correct = 0;
-    }
-  }
-  for (int q = 0; q < a.n_rows; ++q) {
-    const int T = min(a.cum[a.idx[q]], a.cap[q]);
-    const int64_t m4 = static_cast<int64_t>(T) * a.d[q] / 4;
-    for (int64_t i = tid; i < m4; i += nth) reinterpret_cast<float4*>(a.rows[q])[i] = z;
-  }
-}
-
 __global__ void k_zero_rows(float* p, const int32_t* cum, int n_hops, int cap, int d) {
   pdl_enter();
   const int T = min(cum[n_hops], cap);
@@ -556,21 +530,6 @@ void launch_add_block_f32(const void* dA, int dA_ld, int col, int d, const int32
 
 void launch_zero_grads(float* g, int64_t n, float* loss, int32_t* correct, cudaStream_t s) {
   launch_k(k_zero_grads, dim3(grid_for(n / 4 + 1, 256, 148 * 2)), dim3(256), 0, s, g, n, loss, correct);
-}
-
-void launch_zero_step(float* g, int64_t n, float* loss, int32_t* correct, float* const* rows, const int32_t* cum,
-                      const int* idx, const int* cap, const int* d, int n_rows, cudaStream_t s) {
-  ZeroStepArgs a;
-  a.g = g; a.n = n; a.loss = loss; a.correct = correct; a.cum = cum; a.n_rows = n_rows;
-  int64_t items = n / 4 + 1;
-  for (int q = 0; q < 3; ++q) {
-    a.rows[q] = q < n_rows ? rows[q] : nullptr;
-    a.idx[q] = q < n_rows ? idx[q] : 0;
-    a.cap[q] = q < n_rows ? cap[q] : 0;
-    a.d[q] = q < n_rows ? d[q] : 0;
-    if (q < n_rows) items += static_cast<int64_t>(cap[q]) * d[q] / 4;
-  }
-  launch_k(k_zero_step, dim3(grid_for(items, 256 * 4, 148 * 8)), dim3(256), 0, s, a);
 }
 
 void launch_zero_rows(float* p, const int32_t* cum, int n_hops, int cap, int d, cudaStream_t s) {

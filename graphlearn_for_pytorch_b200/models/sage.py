@@ -135,22 +135,15 @@ class GraphSageEngine(object):
     # measured on B200 (profiles/): running the weight-gradient GEMMs and the zero fills on an auxiliary stream LOSES 3 %
     # (0.245 vs 0.237 ms/step): the extra CTAs compete with the critical dgrad -> scatter -> cast chain.  Kept as an option.
     self.overlap_wgrad = _os3.environ.get('GLT_B200_OVERLAP_WGRAD', '0') != '0'
-    # pipelined engines: zero the fp32 scatter targets on the sampling stream (off the training chain)
-    # (measured: 0.2435 vs 0.2380 ms/step -- the fill then competes with the fused layer-1 loaders for bandwidth)
-    self.side_zero = _os3.environ.get('GLT_B200_SIDE_ZERO', '0') != '0'
-    # zero the gradient buffer AND the scatter targets in one launch at the start of the gradient phase
-    self.merged_zero = _os3.environ.get('GLT_B200_MERGED_ZERO', '0') != '0'
-    # programmatic dependent launch in pipelined capture: 'off' (measured default), 'train' (training-stream kernels
-    # only), 'all'
-    self.pdl_mode = _os3.environ.get('GLT_B200_PDL_MODE', 'off')
     self.deterministic_sampling = bool(deterministic_sampling)
     self.use_peer_allreduce = bool(use_peer_allreduce)
-    # use_gather_bwd (csrc/cuda/transpose.cu, validated on B200 in round 2): the sampler also builds the transposed
-    # adjacency of the batch and the backward of the aggregation becomes an atomics-free gather (replaces zero_rows +
-    # fp32-atomic scatter + relu_bwd_cast).  None = the measured default (GLT_B200_GATHER_BWD overrides).
+    # use_gather_bwd (csrc/cuda/transpose.cu): the sampler also builds the transposed adjacency of the batch (on the
+    # sampling stream) and the backward of the aggregation is an atomics-free gather (replaces zero_rows + fp32-atomic
+    # scatter + relu_bwd_cast: 4 launches per hidden layer -> 2).  Measured on B200 with the v3 kernel: 0.2244-0.2264
+    # vs 0.2363-0.2395 ms/step at products shape -> default on (GLT_B200_GATHER_BWD=0 restores the scatter path).
     if use_gather_bwd is None:
       import os as _os
-      use_gather_bwd = _os.environ.get('GLT_B200_GATHER_BWD', '0') == '1'
+      use_gather_bwd = _os.environ.get('GLT_B200_GATHER_BWD', '1') == '1'
     self.use_gather_bwd = bool(use_gather_bwd) and int(hidden) <= 1024
     # every dense contraction outside the fused layer-1 kernel runs on the TMA-fed tcgen05 GEMM kernel
     # (csrc/cuda/tc_gemm.cu); GLT_B200_TC_GEMM=0 falls back to cuBLAS for A/B measurements
@@ -541,15 +534,7 @@ class GraphSageEngine(object):
       self._k(1)
     # one launch zeroes the flat gradient buffer, the loss and the #correct counter; the kernels that accumulate
     # into them then skip their own memsets (memset nodes would cut the programmatic-launch chain of the step)
-    self._rows_zeroed = False
-    if self.merged_zero and self.L > 1 and self.L <= 4 and not self.use_gather_bwd and \
-        getattr(self, '_zero_ev', None) is None and not self.overlap_wgrad:
-      # ... and the fp32 scatter targets of the backward pass in the same launch
-      self.nat.zero_step(self.g32, self.loss, self.correct, [self.dH[l - 1] for l in range(self.L, 1, -1)],
-                         self.arena.counters, [self.L - l + 2 for l in range(self.L, 1, -1)])
-      self._rows_zeroed = True
-    else:
-      self.nat.zero_grads(self.g32, self.loss, self.correct)
+    self.nat.zero_grads(self.g32, self.loss, self.correct)
     self._k(1)
 
   def _plan(self, kind: str, l: int):
@@ -632,14 +617,8 @@ class GraphSageEngine(object):
                               self.g32[pboff:pboff + pn], True, 1.0 / (1.0 - self.dropout))
           self._k(1)
           continue
-        if getattr(self, '_zero_ev', None) is not None:
-          if l == self.L:
-            main.wait_event(self._zero_ev)   # zero fills were issued on the sampling stream (_pipelined_body)
-        elif getattr(self, '_rows_zeroed', False):
-          pass                               # zeroed by k_zero_step at the start of the gradient phase
-        else:
-          nat.zero_rows(self.dH[l - 1], ar.counters, nh + 1)
-          self._k(1)
+        nat.zero_rows(self.dH[l - 1], ar.counters, nh + 1)
+        self._k(1)
         nat.sage_scatter_bwd(self.dA[l], self.dims_in[l - 1], ar.counters, nh, ell, ks, ar.deg, self.dH[l - 1])
         nat.relu_bwd_cast(self.dH[l - 1], self.Z[l - 1], ar.counters, nh + 1, self.dPre[l - 1],
                           self.g32[pboff:pboff + pn], True, 1.0 / (1.0 - self.dropout))
@@ -692,25 +671,10 @@ class GraphSageEngine(object):
     self._cur = cur
     main = torch.cuda.current_stream()
     self._side.wait_stream(main)                       # fork
-    self._zero_ev = None
     with torch.cuda.stream(self._side):
-      if self.side_zero and self.L > 1 and not self.use_gather_bwd and not self.overlap_wgrad:
-        # the zero fill of the fp32 scatter targets of THIS step's backward leaves the training chain: it runs on
-        # the sampling stream (idle for 2/3 of the step) before the next batch is sampled
-        for l in range(self.L, 1, -1):
-          self.nat.zero_rows(self.dH[l - 1], self._arenas[cur].counters, self.L - l + 2)
-        self._k(self.L - 1)
-        self._zero_ev = torch.cuda.Event()
-        self._zero_ev.record(self._side)
-      if self.pdl_mode == 'train':
-        prev = self.nat.set_pdl(False)       # sampling kernels without the programmatic-launch attribute
-        self._sample(1 - cur)
-        self.nat.set_pdl(prev)
-      else:
-        self._sample(1 - cur)
+      self._sample(1 - cur)
     self._forward()
     self._backward()
-    self._zero_ev = None
     main.wait_stream(self._side)                        # join
 
   def _step_eager(self):
@@ -788,8 +752,7 @@ class GraphSageEngine(object):
         return
       # programmatic dependent launch helps single-stream chains and costs ~2 % when the sampling and training
       # streams interleave (measured, csrc/cuda/launch_utils.h): captured without it in pipelined mode
-      prev_pdl = self.nat.set_pdl((not self.pipeline) or self.pdl_mode in ('train', 'all')) \
-          if hasattr(self.nat, 'set_pdl') else None
+      prev_pdl = self.nat.set_pdl(not self.pipeline) if hasattr(self.nat, 'set_pdl') else None
       # capturing NCCL collectives works but makes process-group teardown hang on this stack
       # (measured: bench exit blocked until the timeout), so it is opt-in for world > 1
       single = self.world == 1 or self.peer_group is not None or \

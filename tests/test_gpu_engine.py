@@ -268,8 +268,11 @@ def test_transposed_adjacency_matches_ell(native):
 
 
 @experimental
+@pytest.mark.parametrize('gather', [True, False])
 @pytest.mark.parametrize('hidden', [256, 512, 64])
-def test_gather_backward_matches_pytorch(native, hidden):
+def test_backward_matches_pytorch_gather_and_scatter(native, hidden, gather):
+  """Weight / bias gradients of every layer against fp32 autograd on the same sampled batch, for the atomics-free
+  gather backward and the fp32-atomic scatter backward, at three hidden widths (lane-group shapes of the kernels)."""
   ei, topo = rmat_csr(6000, 120000, seed=3)
   g = glt.data.Graph(topo, 'CUDA', 0)
   torch.manual_seed(0)
@@ -278,20 +281,25 @@ def test_gather_backward_matches_pytorch(native, hidden):
   ut = glt.data.UnifiedTensor(0, torch.bfloat16)
   ut.append_shared_tensor(feats)
   eng = GraphSageEngine(g, ut._table(), labels, in_dim=128, num_nodes=6000, fanouts=[5, 4, 3], batch_size=256,
-                        hidden=hidden, num_classes=47, device=DEV, use_fused=(hidden <= 256), use_cuda_graph=False, seed=5,
-                        use_gather_bwd=True)
+                        hidden=hidden, num_classes=47, device=DEV, use_fused=(hidden <= 256), use_cuda_graph=False,
+                        seed=5, use_gather_bwd=gather)
+  assert eng.use_gather_bwd == gather
   eng.seeds_dev.copy_(torch.randperm(6000, device=DEV)[:256])
   eng._sample(); eng._forward(); eng._backward()
   torch.cuda.synchronize()
   ref_loss, acts, params, cum = _dense_reference(eng, feats, labels, 256)
+  errs = {}
   for l in range(1, eng.L + 1):
     off, n, k = eng._w_off[l - 1]
     gW = eng.g32[off:off + n * k].view(n, k)
     gW_ref = params[l - 1][0].grad
-    assert (gW - gW_ref).abs().max() / gW_ref.abs().max().clamp(min=1e-6) < 5e-2, f'dW{l}'
+    errs[f'dW{l}'] = float((gW - gW_ref).abs().max() / gW_ref.abs().max().clamp(min=1e-6))
     boff, _ = eng._b_off[l - 1]
     gb_ref = params[l - 1][1].grad
-    assert (eng.g32[boff:boff + n] - gb_ref).abs().max() / gb_ref.abs().max().clamp(min=1e-6) < 5e-2, f'db{l}'
+    errs[f'db{l}'] = float((eng.g32[boff:boff + n] - gb_ref).abs().max() / gb_ref.abs().max().clamp(min=1e-6))
+  # bf16 operands, fp32 accumulation: the error grows with the contraction length of the hidden layers
+  tol = 5e-2 if hidden <= 256 else 1e-1
+  assert all(e < tol for e in errs.values()), errs
 
 
 @experimental
