@@ -328,7 +328,8 @@ def build_ours(args, rank, world, device, need_engine=True):
       local = torch.cat([glt.data.quantize_mxfp8(local[b0:min(e - b, b0 + rows)]) for b0 in range(0, e - b, rows)])
     pf = PartitionedFeature(local, bounds, device,
                             hot_per_rank=min(int(args.hot_fraction * (bounds[1] - bounds[0])),
-                                             min(bounds[r + 1] - bounds[r] for r in range(world))))
+                                             min(bounds[r + 1] - bounds[r] for r in range(world))),
+                            full_replica=args.hot_fraction >= 1.0)
     table = pf.table
     keep = (pg, pf)
   torch.cuda.empty_cache()

@@ -72,6 +72,10 @@ __global__ void __launch_bounds__(256) k_adam_peer(PeerPtrs p, float* param, flo
   const int64_t n4 = n >> 2;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    // local optimizer state first: these loads are in flight while the peer gradients cross NVLink
+    const float4 pp = reinterpret_cast<const float4*>(param)[i];
+    const float4 mm = reinterpret_cast<const float4*>(m)[i];
+    const float4 vv = reinterpret_cast<const float4*>(v)[i];
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
     // all peer loads of a batch of 8 ranks are issued before the first add: one NVLink round trip per batch
     // instead of one per rank (the adds keep rank order: identical result on every rank)
@@ -86,9 +90,6 @@ __global__ void __launch_bounds__(256) k_adam_peer(PeerPtrs p, float* param, flo
         if (r0 + q < p.world) { g.x += x[q].x; g.y += x[q].y; g.z += x[q].z; g.w += x[q].w; }
     }
     float gi[4] = {g.x, g.y, g.z, g.w};
-    float4 pp = reinterpret_cast<float4*>(param)[i];
-    float4 mm = reinterpret_cast<float4*>(m)[i];
-    float4 vv = reinterpret_cast<float4*>(v)[i];
     float pa[4] = {pp.x, pp.y, pp.z, pp.w}, ma[4] = {mm.x, mm.y, mm.z, mm.w}, va[4] = {vv.x, vv.y, vv.z, vv.w};
 #pragma unroll
     for (int q = 0; q < 4; ++q) {

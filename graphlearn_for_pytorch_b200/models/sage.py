@@ -902,11 +902,14 @@ class GraphSageEngine(object):
           return r
         return call
 
-    real_nat, real_plans = self.nat, self._tc_plans
+    real_nat, real_plans, real_pgs = self.nat, self._tc_plans, self._peer_groups
     batches = seeds if seeds.dim() == 2 else seeds.unsqueeze(0)
     acc, names = None, None
     try:
       self.nat, self._tc_plans = _Timed(real_nat), {}
+      self._peer_groups = [_Timed(pg, 'PeerGroup.') for pg in real_pgs]
+      if real_pgs:
+        self.peer_group = self._peer_groups[0]
       self._cur = 0
       for it in range(iters + 2):
         del log[:]
@@ -932,7 +935,9 @@ class GraphSageEngine(object):
             for i, (_, a0, a1) in enumerate(log):
               acc[i] += a0.elapsed_time(a1) * 1e3 / iters
     finally:
-      self.nat, self._tc_plans = real_nat, real_plans
+      self.nat, self._tc_plans, self._peer_groups = real_nat, real_plans, real_pgs
+      if real_pgs:
+        self.peer_group = real_pgs[0]
     return list(zip(names, acc))
 
   @torch.no_grad()

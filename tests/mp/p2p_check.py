@@ -85,10 +85,10 @@ def main():
   assert ea == ec
   ok('sampling on the locally replicated topology (all shards pulled over NVLink at setup)')
   # full feature replica: every rank's whole range is "hot" -> no remote part left in the table
-  per = min(bounds[r + 1] - bounds[r] for r in range(world))
-  pfa = PartitionedFeature(full[bounds[rank]:bounds[rank + 1]].clone(), bounds, dev, hot_per_rank=per)
-  assert torch.equal(pfa[ids], full[ids]), 'full-replica gather mismatch'
-  ok(f'full feature replica ({pfa.fill_mode})')
+  pfa = PartitionedFeature(full[bounds[rank]:bounds[rank + 1]].clone(), bounds, dev, full_replica=True)
+  assert pfa.unified._table().num_parts == 1 and pfa.unified._table().all_local()
+  assert torch.equal(pfa[ids], full[ids]) and torch.equal(pfa.replica, full), 'full-replica gather mismatch'
+  ok(f'full feature replica, one local part ({pfa.fill_mode})')
 
   # 4. engine step with partitioned graph + features
   from graphlearn_for_pytorch_b200.models import GraphSageEngine
