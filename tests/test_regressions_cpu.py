@@ -113,3 +113,35 @@ def test_mxfp8_quantiser_roundtrip_and_layout():
   assert bool(((amax / torch.exp2(e))[ok] <= 448.0).all()) and bool(((amax / torch.exp2(e - 1))[ok] > 448.0).all())
   # bf16 input quantises like its fp32 value
   assert torch.equal(quantize_mxfp8(x.to(torch.bfloat16)), quantize_mxfp8(x.to(torch.bfloat16).float()))
+
+
+def test_bench_placement_policy_and_metric_names():
+  """bench.py multi-GPU placement: replicate what fits a per-GPU budget (topology first, then the hottest feature
+  rows), partition the rest; explicit --hot-fraction / --replica-budget-gb 0 keep the partitioned layout."""
+  import importlib.util, os
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  spec = importlib.util.spec_from_file_location('glt_bench_mod', os.path.join(root, 'bench.py'))
+  bench = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(bench)
+  a = bench.parse_args([])
+  assert a.shape == 'products' and a.replicate_topology and a.hot_fraction == 1.0
+  assert bench.metric_name(a) == bench.METRIC
+  p = bench.parse_args(['--shape', 'papers100m'])
+  assert p.replicate_topology and 0.3 < p.hot_fraction < 0.45      # 16 GB - 6.5 GB of CSR over 28.4 GB of rows
+  assert 'papers100m' in bench.metric_name(p) and 'products' not in bench.metric_name(p)
+  z = bench.parse_args(['--replica-budget-gb', '0'])
+  assert not z.replicate_topology and z.hot_fraction == 0.25
+  e = bench.parse_args(['--hot-fraction', '0.1'])
+  assert not e.replicate_topology and e.hot_fraction == 0.1
+  small = bench.parse_args(['--shape', 'papers100m', '--replica-budget-gb', '4'])
+  assert not small.replicate_topology and 0.1 < small.hot_fraction < 0.2    # CSR does not fit: all 4 GB go to rows
+
+
+def test_hotness_balanced_order_deals_hot_rows_round_robin():
+  from graphlearn_for_pytorch_b200.parallel.partitioned import hotness_balanced_order
+  hot = torch.tensor([5., 1., 9., 3., 7., 2., 8.])
+  old2new, bounds = hotness_balanced_order(hot, 3)
+  assert bounds == [0, 3, 5, 7]
+  assert sorted(old2new.tolist()) == list(range(7))
+  # the three hottest nodes (ids 2, 6, 4) open the three ranges
+  assert [int(old2new[i]) for i in (2, 6, 4)] == [0, 3, 5]
