@@ -23,6 +23,17 @@ import torch
 NTYPES = ['paper', 'author', 'institute', 'fos']
 BASE_ETYPES = [('paper', 'cites', 'paper'), ('paper', 'written_by', 'author'),
                ('author', 'affiliated_to', 'institute'), ('paper', 'topic', 'fos')]
+# IGBH-large / -full also carry the publication venues (reference dataset.py:186-210)
+VENUE_NTYPES = ['conference', 'journal']
+VENUE_ETYPES = [('paper', 'published', 'journal'), ('paper', 'venue', 'conference')]
+
+
+def ntypes_on_disk(base_path: str):
+  return NTYPES + [nt for nt in VENUE_NTYPES if osp.exists(osp.join(base_path, nt, 'node_feat.npy'))]
+
+
+def etypes_on_disk(base_path: str):
+  return BASE_ETYPES + [et for et in VENUE_ETYPES if osp.isdir(osp.join(base_path, etype_dir(et)))]
 
 
 def etype_dir(et: Tuple[str, str, str]) -> str:
@@ -30,7 +41,7 @@ def etype_dir(et: Tuple[str, str, str]) -> str:
 
 
 def make_synthetic_igbh(path: str, size: str = 'tiny', papers: int = 4000, feat_dim: int = 64, classes: int = 19,
-                        seed: int = 0):
+                        seed: int = 0, with_venues: bool = False):
   base = osp.join(path, size, 'processed')
   g = torch.Generator().manual_seed(seed)
   n = {'paper': papers, 'author': papers * 3 // 2, 'institute': max(papers // 40, 8), 'fos': max(papers // 20, 8)}
@@ -50,10 +61,18 @@ def make_synthetic_igbh(path: str, size: str = 'tiny', papers: int = 4000, feat_
            BASE_ETYPES[1]: rnd(papers, n['author'], papers * 3),
            BASE_ETYPES[2]: rnd(n['author'], n['institute'], n['author']),
            BASE_ETYPES[3]: rnd(papers, n['fos'], papers * 2)}
+  ntypes = list(NTYPES)
+  if with_venues:               # the schema of IGBH-large / -full: every paper has one journal or conference
+    n['journal'], n['conference'] = max(papers // 100, 4), max(papers // 100, 4)
+    for nt in VENUE_NTYPES:
+      feats[nt] = torch.randn(n[nt], feat_dim, generator=g)
+    edges[VENUE_ETYPES[0]] = rnd(papers, n['journal'], papers // 2)
+    edges[VENUE_ETYPES[1]] = rnd(papers, n['conference'], papers // 2)
+    ntypes += VENUE_NTYPES
   for et, ei in edges.items():
     os.makedirs(osp.join(base, etype_dir(et)), exist_ok=True)
     np.save(osp.join(base, etype_dir(et), 'edge_index.npy'), ei.numpy())
-  for nt in NTYPES:
+  for nt in ntypes:
     os.makedirs(osp.join(base, nt), exist_ok=True)
     np.save(osp.join(base, nt, 'node_feat.npy'), feats[nt].numpy())
   np.save(osp.join(base, 'paper', 'node_label_19.npy'), topic_of.numpy())
@@ -63,7 +82,7 @@ def make_synthetic_igbh(path: str, size: str = 'tiny', papers: int = 4000, feat_
 
 def float2half(base_path: str):
   """node_feat.npy -> node_feat_fp16.pt for every node type (halves the feature store)."""
-  for nt in NTYPES:
+  for nt in ntypes_on_disk(base_path):
     out = osp.join(base_path, nt, 'node_feat_fp16.pt')
     if not osp.exists(out):
       torch.save(torch.from_numpy(np.array(np.load(osp.join(base_path, nt, 'node_feat.npy'), mmap_mode='r'))).half(), out)
@@ -81,7 +100,7 @@ class IGBHeteroDataset(object):
     self.base_path = osp.join(path, dataset_size, 'processed')
     assert osp.isdir(self.base_path), f'{self.base_path} not found (make_synthetic_igbh() writes one)'
     self.in_memory, self.layout, self.use_fp16 = in_memory, layout.upper(), use_fp16
-    self.ntypes = list(NTYPES)
+    self.ntypes = ntypes_on_disk(self.base_path)
     self.edge_dict, self.feat_dict = {}, {}
     if use_fp16:
       float2half(self.base_path)
@@ -101,7 +120,7 @@ class IGBHeteroDataset(object):
   def _load_edges(self):
     mode = None if self.in_memory else 'r'
     if self.layout == 'COO':
-      for et in BASE_ETYPES:
+      for et in etypes_on_disk(self.base_path):
         ei = torch.from_numpy(np.array(np.load(osp.join(self.base_path, etype_dir(et), 'edge_index.npy'), mmap_mode=mode))).t()
         if et[0] == et[2]:        # cites: make it symmetric like the reference (add reverse + dedup not needed)
           self.edge_dict[et] = torch.cat([ei, ei.flip(0)], 1).contiguous()

@@ -174,3 +174,22 @@ def test_igbh_multi_gpu_trainer_runs_on_two_cpu_ranks(tmp_path):
               '--max_steps', '2', '--val_batches', '2', '--ckpt_path', os.path.join(ck, 'model_step_2.ckpt'),
               '--world_size', '2'], timeout=600)
   assert 'val-acc' in out
+
+
+def test_igbh_large_schema_with_venue_types(tmp_path):
+  """IGBH-large / -full carry journal and conference nodes: the loader picks them up from the directory layout and
+  the single-process trainer runs on the 6-type / 11-relation graph; download.py lists the full manifest."""
+  sys.path.insert(0, os.path.join(ROOT, 'examples', 'igbh'))
+  from dataset import IGBHeteroDataset, make_synthetic_igbh
+  d = str(tmp_path / 'igbh')
+  make_synthetic_igbh(d, papers=1200, with_venues=True)
+  ds = IGBHeteroDataset(d, 'tiny')
+  assert set(ds.ntypes) == {'paper', 'author', 'institute', 'fos', 'conference', 'journal'}
+  assert ('journal', 'rev_published', 'paper') in ds.edge_dict and ('paper', 'venue', 'conference') in ds.edge_dict
+  assert len(ds.etypes) == 11
+  _run(['examples/igbh/split_seeds.py', '--path', d, '--validation_frac', '0.1'])
+  out = _run(['examples/igbh/train_rgnn.py', '--path', d, '--fan_out', '3,3', '--epochs', '1', '--max_steps', '3',
+              '--batch_size', '64'])
+  assert 'val-acc' in out
+  out = _run(['examples/igbh/download.py', '--path', d, '--size', 'full', '--dry-run'])
+  assert out.count('would fetch') >= 16 and 'paper__venue__conference/edge_index.npy' in out
