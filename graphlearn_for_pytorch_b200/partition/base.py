@@ -39,12 +39,18 @@ def _typed_path(root: str, stem: str, t=None, ext='.pt'):
   return os.path.join(root, f'{stem}{ext}')
 
 
+def _plain(pb):
+  """Tensor books are written as PLAIN tensors: loadable with `weights_only=True` and by the reference's loader
+  (same on-disk format); they are wrapped into GLTPartitionBook again on load."""
+  return pb.as_subclass(torch.Tensor) if isinstance(pb, torch.Tensor) else pb
+
+
 def save_node_pb(output_dir: str, node_pb: PartitionBook, ntype: Optional[NodeType] = None):
-  torch.save(node_pb, _typed_path(output_dir, 'node_pb', ntype))
+  torch.save(_plain(node_pb), _typed_path(output_dir, 'node_pb', ntype))
 
 
 def save_edge_pb(output_dir: str, edge_pb: PartitionBook, etype: Optional[EdgeType] = None):
-  torch.save(edge_pb, _typed_path(output_dir, 'edge_pb', etype))
+  torch.save(_plain(edge_pb), _typed_path(output_dir, 'edge_pb', etype))
 
 
 def _graph_dir(root: str, etype=None):
@@ -285,7 +291,12 @@ def load_feature_partition_data(feature_data_dir: str, device: torch.device) -> 
 
 
 def _load_pb(path, device):
-  pb = torch.load(path, map_location=device, weights_only=False)
+  try:
+    pb = torch.load(path, map_location=device, weights_only=True)
+  except Exception:   # range books (objects) and files written before tensor books were stored plain
+    pb = torch.load(path, map_location=device, weights_only=False)
+  if type(pb) is torch.Tensor:
+    pb = GLTPartitionBook(pb)
   return pb
 
 

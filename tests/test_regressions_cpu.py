@@ -1,4 +1,5 @@
 """Regression tests for defects found in review (round-1 advisor findings)."""
+import pytest
 import torch
 
 
@@ -145,3 +146,16 @@ def test_hotness_balanced_order_deals_hot_rows_round_robin():
   assert sorted(old2new.tolist()) == list(range(7))
   # the three hottest nodes (ids 2, 6, 4) open the three ranges
   assert [int(old2new[i]) for i in (2, 6, 4)] == [0, 3, 5]
+
+
+def test_reference_reads_partitions_written_by_this_library():
+  """Format parity: the unmodified reference's load_partition reads our partitioner's output.
+  Needs the offline reference install (baseline/_ref); skipped when it is absent."""
+  import os, subprocess, sys
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  if not os.path.isdir(os.path.join(root, 'baseline', '_ref', 'graphlearn_torch')):
+    pytest.skip('baseline/_ref not installed')
+  out = subprocess.run([sys.executable, os.path.join(root, 'tools', 'partition_format_compat.py')],
+                       capture_output=True, text=True, timeout=300)
+  assert out.returncode == 0 and 'FORMAT OK' in out.stdout, out.stdout[-1500:] + out.stderr[-1500:]
+  assert 'False' not in out.stdout.split('reference loaded')[-1]
