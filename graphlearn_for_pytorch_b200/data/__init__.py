@@ -11,3 +11,10 @@ from .vineyard_utils import (vineyard_to_csr, load_vertex_feature_from_vineyard,
                              register_fragment_backend)
 from .quantize import (quantize_mxfp8, dequantize_mxfp8, mxfp8_row_bytes, quantize_mxfp8_parts,
                        pack_mx_scale_blocks)
+# names the reference's `data` namespace re-exports from its helpers (python/data/__init__.py star imports)
+from ..partition.partition_book import PartitionBook
+from ..utils import convert_to_tensor, coo_to_csc, coo_to_csr, ptr2ind, share_memory, squeeze
+from .dataset import rebuild_dataset, reduce_dataset
+from .feature import rebuild_feature, reduce_feature
+from .graph import rebuild_graph, reduce_graph
+from .table_dataset import rebuild_table_dataset, reduce_table_dataset

@@ -194,9 +194,28 @@ class Dataset(object):
       return None
     return self.graph.topo
 
-  def init_node_labels(self, node_label_data=None):
-    if node_label_data is not None:
-      self.node_labels = squeeze(convert_to_tensor(node_label_data))
+  def init_node_labels(self, node_label_data=None, id2idx=None):
+    """node_label_data: labels (dict per node type for heterogeneous graphs).  id2idx: optional global id -> row map
+    (tensor / array / sequence, dict per type) for label tables that hold only a fragment of the nodes (the
+    reference keeps such labels behind a Feature, data/dataset.py:358-365); here the labels are re-keyed by global
+    id once (-1 for ids without a row), so `node_labels[ids]` keeps working everywhere."""
+    if node_label_data is None:
+      return
+    labels = squeeze(convert_to_tensor(node_label_data))
+    if id2idx is not None:
+      def rekey(lab, m):
+        if m is None:
+          return lab
+        m = _gid2lid_tensor(m, 0) if hasattr(m, '_offset') else torch.as_tensor(convert_to_tensor(m), dtype=torch.int64)
+        out = torch.full((m.numel(),) + tuple(lab.shape[1:]), -1, dtype=lab.dtype)
+        ok = (m >= 0) & (m < lab.shape[0])
+        out[ok] = lab[m[ok]]
+        return out
+      if isinstance(labels, dict):
+        labels = {t: rekey(v, id2idx.get(t) if isinstance(id2idx, dict) else id2idx) for t, v in labels.items()}
+      else:
+        labels = rekey(labels, id2idx)
+    self.node_labels = labels
 
   # ------------------------------------------------------------------ IPC
   def share_ipc(self):

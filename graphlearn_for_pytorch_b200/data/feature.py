@@ -108,6 +108,12 @@ class Feature(object):
       if self.id2index is not None:
         self._id2index_dev = self.id2index.to(torch.device('cuda', self.device), dtype=torch.int64)
 
+  def lazy_init_with_ipc_handle(self):
+    """Finish the construction of a Feature received from another process (reference feature.py:242-261):
+    here `lazy_init` covers both cases -- a pending IPC handle is opened on first use -- so this is an alias."""
+    if self._ipc_handle is not None:
+      self.lazy_init()
+
   def _split_and_init(self):
     n = self.feature_tensor.shape[0]
     hot = int(n * self.split_ratio)

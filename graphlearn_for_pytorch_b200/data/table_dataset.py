@@ -56,8 +56,12 @@ class TableDataset(Dataset):
            split_ratio: float = 0.0, device_group_list=None, directed: bool = True,
            label: Optional[str] = 'label', device: Optional[int] = None,
            src_col: str = 'src_id', dst_col: str = 'dst_id', id_col: str = 'id',
-           feature_col: str = 'feature', weight_col: Optional[str] = None, **kwargs):
-    """edge tables need (src_id, dst_id[, weight]); node tables need (id, feature[, label])."""
+           feature_col: str = 'feature', weight_col: Optional[str] = None, reader_threads: int = 10,
+           reader_capacity: int = 10240, reader_batch_size: int = 1024, **kwargs):
+    """edge tables need (src_id, dst_id[, weight]); node tables need (id, feature[, label]).  The `reader_*`
+    arguments of the reference's ODPS reader (table_dataset.py:36-39) are accepted and unused: parquet / CSV /
+    pyarrow tables are read in one pass."""
+    del reader_threads, reader_capacity, reader_batch_size
     assert edge_tables, 'at least one edge table is required'
     hetero = len(edge_tables) > 1 or (node_tables is not None and len(node_tables) > 1)
     edge_index, edge_weights = {}, {}
@@ -100,3 +104,16 @@ class TableDataset(Dataset):
         if nt in labels:
           self.init_node_labels(labels[nt])
     return self
+
+
+def rebuild_table_dataset(ipc_handle):
+  ds = TableDataset.from_ipc_handle(ipc_handle)
+  return ds
+
+
+def reduce_table_dataset(dataset: TableDataset):
+  return (rebuild_table_dataset, (dataset.share_ipc(),))
+
+
+from multiprocessing.reduction import ForkingPickler  # noqa: E402
+ForkingPickler.register(TableDataset, reduce_table_dataset)

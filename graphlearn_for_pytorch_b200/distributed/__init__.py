@@ -16,3 +16,5 @@ from .rpc import (init_rpc, shutdown_rpc, rpc_is_initialized, get_rpc_master_add
                   all_gather, barrier, global_all_gather, global_barrier, RpcDataPartitionRouter,
                   rpc_sync_data_partitions, RpcCalleeBase, rpc_register, rpc_request_async, rpc_request,
                   rpc_global_request_async, rpc_global_request)
+# module-path aliases of the loader classes, importable as attributes like in the reference package
+from . import dist_link_neighbor_loader, dist_neighbor_loader, dist_subgraph_loader  # noqa: E402,F401

@@ -13,7 +13,7 @@ import torch
 from ..data import Dataset, DeviceGroup, Feature, Graph
 from ..partition import PartitionBook, RangePartitionBook, cat_feature_cache, load_partition
 from ..typing import EdgeType, FeaturePartitionData, GraphPartitionData, NodeType
-from ..utils.common import default_id_filter
+from ..utils.common import default_id_filter, default_id_select
 from ..utils.tensor import convert_to_tensor, id2idx, share_memory, squeeze
 
 
@@ -27,9 +27,17 @@ class DistDataset(Dataset):
   def __init__(self, num_partitions: int = 1, partition_idx: int = 0, graph_partition=None,
                node_feature_partition=None, edge_feature_partition=None, whole_node_labels=None,
                node_pb=None, edge_pb=None, node_feat_pb=None, edge_feat_pb=None, edge_dir: str = 'out',
-               node_split=None):
+               graph_caching: bool = False, node_split=None, id_filter=default_id_filter,
+               id_select=default_id_select):
+    """graph_caching: the partition directory holds the FULL topology (`load(..., graph_caching=True)`).
+    id_filter(node_pb, partition_idx) -> ids owned by this partition; id_select(ids, mask, node_pb) -> the ids of a
+    request that a given partition serves: hooks for partition books that are not plain tensors (the vineyard bridge
+    installs its own; reference dist_dataset.py:47-64)."""
     super().__init__(graph_partition, node_feature_partition, edge_feature_partition, whole_node_labels,
                      edge_dir, node_split)
+    self.graph_caching = graph_caching
+    self.id_filter = id_filter
+    self.id_select = id_select
     self.num_partitions = num_partitions
     self.partition_idx = partition_idx
     self.node_pb = node_pb
@@ -48,6 +56,7 @@ class DistDataset(Dataset):
            device_group_list: Optional[List[DeviceGroup]] = None,
            whole_node_label_file: Union[str, Dict[NodeType, str], None] = None,
            device: Optional[int] = None):
+    self.graph_caching = graph_caching
     (self.num_partitions, self.partition_idx, graph_data, node_feat_data, edge_feat_data, node_pb,
      edge_pb) = load_partition(root_dir, partition_idx, graph_caching)
     if isinstance(graph_data, dict):
@@ -135,7 +144,7 @@ class DistDataset(Dataset):
     def owned(pb, n_hint=None):
       if hasattr(pb, 'id_filter'):
         return pb.id_filter(pb, self.partition_idx)
-      return default_id_filter(pb, self.partition_idx)
+      return self.id_filter(pb, self.partition_idx)
     if isinstance(self.node_pb, dict):
       tr, va, te = {}, {}, {}
       for nt, pb in self.node_pb.items():
@@ -169,7 +178,7 @@ class DistDataset(Dataset):
   def from_ipc_handle(cls, ipc_handle):
     (num_partitions, partition_idx, base, node_pb, edge_pb, nfpb, efpb) = ipc_handle
     g, nf, ef, nl, edge_dir, split = base
-    return cls(num_partitions, partition_idx, g, nf, ef, nl, node_pb, edge_pb, nfpb, efpb, edge_dir, split)
+    return cls(num_partitions, partition_idx, g, nf, ef, nl, node_pb, edge_pb, nfpb, efpb, edge_dir, node_split=split)
 
 
 def rebuild_dist_dataset(ipc_handle):

@@ -126,10 +126,26 @@ class DistFeature(object):
     return fut
 
   # ------------------------------------------------------------------ collective exchange
-  def get_all2all(self, ids: torch.Tensor, input_type=None, group=None) -> torch.Tensor:
+  def get_all2all(self, sampler_result, ntype_list=None, input_type=None, group=None):
     """Feature exchange with collectives instead of RPC (reference `use_all2all`,
     dist_feature.py:239-378): counts -> ids -> rows, three all_to_all rounds.  Works on
-    gloo (CPU tensors) and NCCL (device tensors)."""
+    gloo (CPU tensors) and NCCL (device tensors).
+
+    `sampler_result`: an id tensor (-> rows, type `input_type`), a `SamplerOutput` (-> rows of its nodes) or a
+    `HeteroSamplerOutput` with `ntype_list` (-> {node type: rows}; every rank must pass the same list so that the
+    collectives line up, as in the reference signature `get_all2all(sampler_result, ntype_list)`)."""
+    from ..sampler import HeteroSamplerOutput, SamplerOutput
+    if isinstance(sampler_result, HeteroSamplerOutput):
+      types = list(ntype_list) if ntype_list is not None else sorted(sampler_result.node.keys())
+      empty = torch.empty(0, dtype=torch.int64)
+      return {nt: self._all2all_rows(sampler_result.node.get(nt, empty), nt, group) for nt in types}
+    if isinstance(sampler_result, SamplerOutput):
+      return self._all2all_rows(sampler_result.node, input_type, group)
+    if isinstance(ntype_list, str) and input_type is None:     # get_all2all(ids, ntype) positional form
+      input_type = ntype_list
+    return self._all2all_rows(sampler_result, input_type, group)
+
+  def _all2all_rows(self, ids: torch.Tensor, input_type=None, group=None) -> torch.Tensor:
     import torch.distributed as dist
     world = dist.get_world_size(group)
     assert world == self.num_partitions

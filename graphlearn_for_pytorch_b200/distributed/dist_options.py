@@ -99,7 +99,18 @@ class RemoteDistSamplingWorkerOptions(_BasicDistSamplingWorkerOptions):
   def __init__(self, server_rank: Optional[Union[int, List[int]]] = None, num_workers: int = 1,
                worker_devices=None, worker_concurrency: int = 4, master_addr=None, master_port=None,
                num_rpc_threads=None, rpc_timeout: float = 180, buffer_size: Optional[Union[int, str]] = None,
-               prefetch_size: int = 4, worker_key: Optional[str] = None, use_all2all: bool = False):
+               prefetch_size: int = 4, worker_key: Optional[str] = None, glt_graph=None,
+               workload_type: Optional[str] = None, use_all2all: bool = False):
+    # GraphScope hands over a handle that carries the rendezvous address and one loader port per workload
+    # ('train' | 'validate' | 'test'), reference dist_options.py:257-272
+    if glt_graph is not None:
+      if workload_type not in ('train', 'validate', 'test'):
+        raise ValueError(f"'{self.__class__.__name__}': workload_type must be 'train', 'validate' or 'test' "
+                         f"when glt_graph is given")
+      master_addr = glt_graph.master_addr
+      master_port = {'train': 'train_loader_master_port', 'validate': 'val_loader_master_port',
+                     'test': 'test_loader_master_port'}[workload_type]
+      master_port = getattr(glt_graph, master_port)
     super().__init__(num_workers, worker_devices, worker_concurrency, master_addr, master_port,
                      num_rpc_threads, rpc_timeout)
     if server_rank is not None:

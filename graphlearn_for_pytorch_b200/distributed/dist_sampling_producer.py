@@ -210,9 +210,13 @@ class DistMpSamplingProducer(object):
       self._pending_done += 1
     return n_batches
 
-  def is_all_sampling_completed_and_consumed(self) -> bool:
+  def is_all_sampling_completed(self) -> bool:
+    """Every worker reported the end of its share of the epoch (messages may still sit in the channel)."""
     self._check_errors()
-    return self._pending_done <= 0 and self.output_channel.empty()
+    return self._pending_done <= 0
+
+  def is_all_sampling_completed_and_consumed(self) -> bool:
+    return self.is_all_sampling_completed() and self.output_channel.empty()
 
   def check_errors(self):
     self._check_errors()

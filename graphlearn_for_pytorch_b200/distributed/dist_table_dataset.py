@@ -54,12 +54,32 @@ class DistTableDataset(DistDataset):
   """Every worker reads a SLICE of the node / edge tables; the workers partition the graph online together
   (`DistTableRandomPartitioner` over RPC) and each loads its partition (reference:
   python/distributed/dist_table_dataset.py:30-250)."""
-  def load(self, num_nodes, edge_tables, node_tables=None, graph_mode: str = 'CPU', feature_with_gpu=False,
-           label_col: Optional[str] = 'label', id_col: str = 'id', device=None, **kwargs):
-    """Collectively partition the table slices and load this rank's partition."""
-    from .rpc import all_gather, rpc_is_initialized
+  def load(self, num_nodes=0, edge_tables=None, node_tables=None, graph_mode: str = 'CPU', feature_with_gpu=False,
+           label_col: Optional[str] = 'label', id_col: str = 'id', device=None, *, num_partitions: Optional[int] = None,
+           partition_idx: Optional[int] = None, device_group_list=None, reader_threads: int = 10,
+           reader_capacity: int = 10240, reader_batch_size: int = 1024, label: Optional[str] = None,
+           edge_assign_strategy: str = 'by_src', chunk_size: int = 10000,
+           master_addr: Optional[str] = None, master_port: Optional[int] = None, num_rpc_threads: int = 16,
+           **kwargs):
+    """Collectively partition the table slices and load this rank's partition.
+
+    Keyword names follow the reference (`dist_table_dataset.py:36-56`): with `master_addr` / `master_port` (and
+    `num_partitions`, `partition_idx`) the worker group and the RPC agent are brought up here if they are not yet;
+    `label` is an alias of `label_col`; `edge_assign_strategy` / `chunk_size` go to the partitioner;
+    the `reader_*` knobs of the ODPS reader are accepted and unused (tables are read through pyarrow in one pass)."""
+    from .rpc import all_gather, init_rpc, rpc_is_initialized
+    del reader_threads, reader_capacity, reader_batch_size, device_group_list
+    kwargs.setdefault('edge_assign_strategy', edge_assign_strategy)
+    kwargs.setdefault('chunk_size', chunk_size)
+    if label is not None:
+      label_col = label
+    if get_context() is None and num_partitions is not None:
+      from .dist_context import init_worker_group
+      init_worker_group(int(num_partitions), int(partition_idx or 0), 'table-dataset')
+    if not rpc_is_initialized() and master_addr is not None:
+      init_rpc(master_addr, int(master_port), num_rpc_threads=num_rpc_threads)
     ctx = get_context()
-    assert ctx is not None and rpc_is_initialized(), 'init_worker_group() + init_rpc() first'
+    assert ctx is not None and rpc_is_initialized(), 'init_worker_group() + init_rpc() first (or pass master_addr)'
     out = kwargs.pop('output_dir', None)
     if out is None:
       # every rank must write under the same root: rank 0 picks it

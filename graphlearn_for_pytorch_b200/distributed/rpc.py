@@ -7,6 +7,7 @@ and barrier, callee registry, partition router.  It rides on torch.distributed.r
 here at all: sampling and feature kernels read peer HBM directly (parallel/); RPC remains
 the bootstrap / control plane and the cross-machine fallback.
 """
+import functools
 import atexit
 import collections
 import logging
@@ -37,6 +38,7 @@ def rpc_is_initialized() -> bool:
 
 
 def _require_initialized(func):
+  @functools.wraps(func)          # keeps the public signature (keyword names are part of the API)
   def wrapper(*args, **kwargs):
     if not rpc_is_initialized():
       raise RuntimeError('RPC has not been initialised; call init_rpc() first')

@@ -37,8 +37,12 @@ class LinkLoader(NodeLoader):
 
   def __init__(self, data: Dataset, link_sampler: BaseSampler, edge_label_index: InputEdges = None,
                edge_label: Optional[torch.Tensor] = None, neg_sampling: Optional[NegativeSampling] = None,
-               device: torch.device = None, batch_size: int = 1, shuffle: bool = False,
-               drop_last: bool = False, seed: Optional[int] = None, **kwargs):
+               device: torch.device = None, edge_dir: Optional[str] = None, batch_size: int = 1,
+               shuffle: bool = False, drop_last: bool = False, seed: Optional[int] = None, **kwargs):
+    """edge_dir: accepted for parity with the reference signature (link_loader.py:108); the direction used when
+    batches are assembled is the dataset's (`data.edge_dir`), which is also what the samplers are built with."""
+    assert edge_dir is None or edge_dir == data.edge_dir, 'edge_dir must match the dataset edge direction'
+    self.edge_dir = data.edge_dir
     self.data = data
     self.sampler = link_sampler
     self.neg_sampling = NegativeSampling.cast(neg_sampling)

@@ -137,6 +137,31 @@ class NeighborSampler(BaseSampler):
                                                          self.edge_dir, seed=self.seed + 17)
                                for et, g in self.graph.items()}
 
+  # accessors the reference exposes next to the lazy initialisers (neighbor_sampler.py:86-90,137-144,629-646)
+  def lazy_init_subgraph_op(self):
+    """The induced-subgraph operator needs no separate object here: `subgraph()` runs the native count / fill
+    kernels (CUDA) or `cpu_node_subgraph` on the graph handle; this only makes sure the graph is placed."""
+    self.lazy_init_sampler()
+
+  @property
+  def subgraph_op(self):
+    self.lazy_init_subgraph_op()
+    return self.subgraph
+
+  def create_inducer(self, input_batch_size: int):
+    """A fresh id table (global id -> dense local id, first-seen order) sized for a batch of `input_batch_size`
+    seeds; one table per node type on heterogeneous graphs."""
+    cap = self._max_sampled_nodes(int(input_batch_size))
+    if self._g_cls == 'homo':
+      return IdTable(self.device, cap)
+    ntypes = sorted({et[0] for et in self.graph} | {et[2] for et in self.graph})
+    return {nt: IdTable(self.device, cap) for nt in ntypes}
+
+  def get_inducer(self, input_batch_size: int):
+    if getattr(self, '_inducer', None) is None:
+      self._inducer = self.create_inducer(input_batch_size)
+    return self._inducer
+
   # ------------------------------------------------------------------ one hop
   def sample_one_hop(self, input_seeds: torch.Tensor, req_num: int,
                      etype: Optional[EdgeType] = None, stream: Optional[int] = None) -> NeighborOutput:

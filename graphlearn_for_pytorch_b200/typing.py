@@ -11,12 +11,12 @@ EDGE_TYPE_STR_SPLIT = '__'
 REVERSE_PREFIX = 'rev_'
 
 
-def as_str(t: Union[NodeType, EdgeType]) -> str:
+def as_str(type: Union[NodeType, EdgeType]) -> str:  # noqa: A002 - keyword name of the reference API
   """'paper' -> 'paper'; ('a','r','b') -> 'a__r__b'."""
-  if isinstance(t, str):
-    return t
-  if isinstance(t, (list, tuple)) and len(t) == 3:
-    return EDGE_TYPE_STR_SPLIT.join(t)
+  if isinstance(type, str):
+    return type
+  if isinstance(type, (list, tuple)) and len(type) == 3:
+    return EDGE_TYPE_STR_SPLIT.join(type)
   return ''
 
 

@@ -9,3 +9,6 @@ for _name in _SUBMODULES:
   for _k in _public:
     globals()[_k] = getattr(_mod, _k)
 del _name, _mod, _public, _k
+
+# the reference's star-import chain also exposes this typing helper as `glt.utils.reverse_edge_type`
+from ..typing import reverse_edge_type  # noqa: E402,F401

@@ -83,40 +83,40 @@ def index_select(data, index):
   return data[index]
 
 
-def merge_hetero_sampler_output(in_out, out_out, device, edge_dir: str = 'out'):
-  """Merge `in_out` into `out_out` (both HeteroSamplerOutput) with node dedup per type."""
+def merge_hetero_sampler_output(in_sample, out_sample, device, edge_dir: str = 'out'):
+  """Merge `in_sample` into `out_sample` (both HeteroSamplerOutput) with node dedup per type."""
   def _unique_with_inverse(a, b):
     cat = torch.cat([a, b])
     uniq, inv = torch.unique(cat, return_inverse=True)
     return cat, uniq, inv
-  for ntype, nodes in in_out.node.items():
-    if ntype not in out_out.node:
-      out_out.node[ntype] = nodes
+  for ntype, nodes in in_sample.node.items():
+    if ntype not in out_sample.node:
+      out_sample.node[ntype] = nodes
     else:
-      out_out.node[ntype] = torch.unique(torch.cat([out_out.node[ntype], nodes]))
-  for etype, rows in in_out.row.items():
-    cols = in_out.col[etype]
-    if etype in out_out.row:
-      out_out.row[etype] = torch.cat([out_out.row[etype], rows])
-      out_out.col[etype] = torch.cat([out_out.col[etype], cols])
+      out_sample.node[ntype] = torch.unique(torch.cat([out_sample.node[ntype], nodes]))
+  for etype, rows in in_sample.row.items():
+    cols = in_sample.col[etype]
+    if etype in out_sample.row:
+      out_sample.row[etype] = torch.cat([out_sample.row[etype], rows])
+      out_sample.col[etype] = torch.cat([out_sample.col[etype], cols])
     else:
-      out_out.row[etype] = rows
-      out_out.col[etype] = cols
-    if in_out.edge is not None and etype in in_out.edge:
-      if out_out.edge is None:
-        out_out.edge = {}
-      out_out.edge[etype] = torch.cat([out_out.edge[etype], in_out.edge[etype]]) \
-        if etype in out_out.edge else in_out.edge[etype]
-  return out_out
+      out_sample.row[etype] = rows
+      out_sample.col[etype] = cols
+    if in_sample.edge is not None and etype in in_sample.edge:
+      if out_sample.edge is None:
+        out_sample.edge = {}
+      out_sample.edge[etype] = torch.cat([out_sample.edge[etype], in_sample.edge[etype]]) \
+        if etype in out_sample.edge else in_sample.edge[etype]
+  return out_sample
 
 
-def format_hetero_sampler_output(in_out, edge_dir: str = 'out'):
+def format_hetero_sampler_output(in_sample, edge_dir: str = 'out'):
   """Make sure every edge type's endpoint node types exist in the node dict."""
-  for k in list(in_out.row.keys()):
+  for k in list(in_sample.row.keys()):
     for t in (k[0], k[-1]):
-      if t not in in_out.node:
-        in_out.node[t] = torch.empty(0, dtype=torch.int64, device=in_out.row[k].device)
-  return in_out
+      if t not in in_sample.node:
+        in_sample.node[t] = torch.empty(0, dtype=torch.int64, device=in_sample.row[k].device)
+  return in_sample
 
 
 # ---- append-only tensor files (on-disk partition format, chunked features) ----
@@ -139,8 +139,8 @@ def load_and_concatenate_tensors(filename: str, device=None) -> Optional[torch.T
   return out.to(device) if device is not None else out
 
 
-def default_id_select(ids: torch.Tensor, mask: torch.Tensor, pb=None) -> torch.Tensor:
-  return torch.masked_select(ids, mask)
+def default_id_select(srcs: torch.Tensor, p_mask: torch.Tensor, node_pb=None) -> torch.Tensor:
+  return torch.masked_select(srcs, p_mask)
 
 
 def default_id_filter(node_pb: torch.Tensor, partition_idx: int) -> torch.Tensor:

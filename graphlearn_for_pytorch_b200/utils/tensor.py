@@ -37,15 +37,16 @@ def convert_to_tensor(data: Any, dtype: Optional[torch.dtype] = None):
   return torch.tensor(data, dtype=dtype)
 
 
-def apply_to_all_tensor(data: Any, fn):
+def apply_to_all_tensor(data: Any, tensor_method, *args, **kwargs):
+  """Apply `tensor_method(tensor, *args, **kwargs)` to every tensor of a (nested) dict / list / tuple."""
   if data is None:
     return None
   if isinstance(data, dict):
-    return {k: apply_to_all_tensor(v, fn) for k, v in data.items()}
+    return {k: apply_to_all_tensor(v, tensor_method, *args, **kwargs) for k, v in data.items()}
   if isinstance(data, (list, tuple)):
-    return type(data)(apply_to_all_tensor(v, fn) for v in data)
+    return type(data)(apply_to_all_tensor(v, tensor_method, *args, **kwargs) for v in data)
   if isinstance(data, torch.Tensor):
-    return fn(data)
+    return tensor_method(data, *args, **kwargs)
   return data
 
 

@@ -159,3 +159,15 @@ def test_reference_reads_partitions_written_by_this_library():
                        capture_output=True, text=True, timeout=300)
   assert out.returncode == 0 and 'FORMAT OK' in out.stdout, out.stdout[-1500:] + out.stderr[-1500:]
   assert 'False' not in out.stdout.split('reference loaded')[-1]
+
+
+def test_public_api_matches_the_installed_reference():
+  """Every name a reference sub-package exports, every public method of the classes both define and every keyword
+  name of their signatures exists here too (checked against the live reference package, not a frozen list)."""
+  import os, subprocess, sys
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  if not os.path.isdir(os.path.join(root, 'baseline', '_ref', 'graphlearn_torch')):
+    pytest.skip('baseline/_ref not installed')
+  out = subprocess.run([sys.executable, os.path.join(root, 'tools', 'api_parity_with_reference.py')],
+                       capture_output=True, text=True, timeout=300)
+  assert out.returncode == 0 and 'API PARITY OK' in out.stdout, out.stdout[-3000:] + out.stderr[-1500:]
