@@ -15,6 +15,7 @@ from . import ops  # noqa: E402
 from . import data  # noqa: E402
 from . import sampler  # noqa: E402
 from . import loader  # noqa: E402
+from .typing import *  # noqa: E402,F401,F403  (NodeType, EdgeType, InputNodes, Split, ... at top level, as in the reference)
 
 __version__ = '0.1.0'
 

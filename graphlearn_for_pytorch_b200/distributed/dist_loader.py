@@ -56,7 +56,7 @@ def message_to_sampler_output(msg: SampleMessage, device, edge_dir: str = 'out')
     elif attr == 'batch':
       batch[t] = to(v)
     elif attr == 'num_sampled_nodes':
-      nsn[t] = v.tolist()
+      nsn[t] = v.to(torch.int64).cpu()
     elif attr == 'nfeats':
       x[t] = to(v)
     elif attr == 'nlabels':
@@ -68,7 +68,7 @@ def message_to_sampler_output(msg: SampleMessage, device, edge_dir: str = 'out')
     elif attr == 'eids':
       edge[t] = to(v)
     elif attr == 'num_sampled_edges':
-      nse[t] = v.tolist()
+      nse[t] = v.to(torch.int64).cpu()
     elif attr == 'efeats':
       ea[t] = to(v)
   out = HeteroSamplerOutput(node=node, row=row, col=col, edge=edge or None, batch=batch or None,
@@ -221,6 +221,13 @@ class DistLoader(object):
     if isinstance(out, HeteroSamplerOutput):
       return to_hetero_data(out, batch_label_dict=y, node_feat_dict=x, edge_feat_dict=ea, edge_dir=self.edge_dir)
     return to_data(out, batch_labels=y, node_feats=x, edge_feats=ea)
+
+
+def _loader_repr(self) -> str:
+  return f'{self.__class__.__name__}()'
+
+
+DistLoader.__repr__ = _loader_repr
 
 
 class DistNeighborLoader(DistLoader):

@@ -295,7 +295,9 @@ class DistNeighborSampler(ConcurrentEventLoop):
       node={nt: t.keys(0) for nt, t in tables.items()},
       row={k: torch.cat(v) for k, v in rows.items()}, col={k: torch.cat(v) for k, v in cols.items()},
       edge={k: torch.cat(v) for k, v in eids.items()} if self.with_edge else None, batch=batch,
-      num_sampled_nodes=num_nodes, num_sampled_edges=num_edges, edge_types=out_types, device=self.device)
+      num_sampled_nodes={k: torch.as_tensor(v, dtype=torch.int64) for k, v in num_nodes.items()},
+      num_sampled_edges={k: torch.as_tensor(v, dtype=torch.int64) for k, v in num_edges.items()},
+      edge_types=out_types, device=self.device)
 
   # ------------------------------------------------------------------ from edges
   async def _sample_from_edges(self, inputs: EdgeSamplerInput):

@@ -144,7 +144,11 @@ class DistRandomPartitioner(object):
     lo, hi = min(self.rank * per, n), min((self.rank + 1) * per, n)
     g = torch.Generator()
     g.manual_seed(1234 + self.rank + (hash(ntype) % 1000 if ntype else 0))
-    local = torch.randint(0, self.num_parts, (hi - lo,), generator=g)
+    # balanced: a random permutation of this slice dealt round-robin over the partitions (the remainder of each
+    # slice goes to different partitions on different ranks), so every partition gets n / num_parts nodes like the
+    # reference's chunked assignment (dist_random_partitioner.py:292-318)
+    local = torch.empty(hi - lo, dtype=torch.int64)
+    local[torch.randperm(hi - lo, generator=g)] = (torch.arange(hi - lo) + self.rank) % self.num_parts
     gathered = all_gather((lo, local))
     book = torch.empty(n, dtype=torch.int64)
     for name in self._workers:
@@ -184,33 +188,28 @@ class DistRandomPartitioner(object):
     if self.data_cls == 'hetero':
       node_pbs = {nt: self._node_book(nt) for nt in self.node_types}
       for nt in self.node_types:
-        if self.rank == 0:
-          save_node_pb(self.output_dir, GLTPartitionBook(node_pbs[nt]), nt)
+        save_node_pb(self.output_dir, GLTPartitionBook(node_pbs[nt]), nt)     # every rank: output dirs may differ
         if self.node_feat is not None and nt in self.node_feat:
           f = self._partition_one_feat(self.node_feat[nt], self.node_feat_ids[nt], node_pbs[nt], f'nfeat:{nt}')
           save_feature_partition(self.output_dir, self.rank, f, 'node_feat', nt)
       for et in self.edge_types:
         g, epb = self._partition_one_graph(node_pbs, et)
         save_graph_partition(self.output_dir, self.rank, g, et)
-        if self.rank == 0:
-          save_edge_pb(self.output_dir, GLTPartitionBook(epb), et)
+        save_edge_pb(self.output_dir, GLTPartitionBook(epb), et)
         if self.edge_feat is not None and et in self.edge_feat:
           f = self._partition_one_feat(self.edge_feat[et], self.edge_feat_ids[et], epb, f'efeat:{as_str(et)}')
           save_feature_partition(self.output_dir, self.rank, f, 'edge_feat', et)
     else:
       node_pb = self._node_book()
-      if self.rank == 0:
-        save_node_pb(self.output_dir, GLTPartitionBook(node_pb))
+      save_node_pb(self.output_dir, GLTPartitionBook(node_pb))
       if self.node_feat is not None:
         f = self._partition_one_feat(self.node_feat, self.node_feat_ids, node_pb, 'nfeat')
         save_feature_partition(self.output_dir, self.rank, f, 'node_feat')
       g, epb = self._partition_one_graph(node_pb)
       save_graph_partition(self.output_dir, self.rank, g)
-      if self.rank == 0:
-        save_edge_pb(self.output_dir, GLTPartitionBook(epb))
+      save_edge_pb(self.output_dir, GLTPartitionBook(epb))
       if self.edge_feat is not None:
         f = self._partition_one_feat(self.edge_feat, self.edge_feat_ids, epb, 'efeat')
         save_feature_partition(self.output_dir, self.rank, f, 'edge_feat')
-    if self.rank == 0:
-      save_meta(self.output_dir, self.num_parts, self.data_cls, self.node_types, self.edge_types)
+    save_meta(self.output_dir, self.num_parts, self.data_cls, self.node_types, self.edge_types)
     barrier()

@@ -149,3 +149,12 @@ class NodeLoader(object):
           edge_attr_dict[etype] = efeat[eids]
     return to_hetero_data(sampler_out, batch_label_dict=y_dict, node_feat_dict=x_dict,
                           edge_feat_dict=edge_attr_dict, edge_dir=self.data.edge_dir)
+
+
+def _loader_repr(self) -> str:
+  return f'{self.__class__.__name__}()'
+
+
+NodeLoader.__repr__ = _loader_repr     # `LinkNeighborLoader()` etc., as in the reference
+# the reference keeps its batching torch DataLoader in `_seed_loader` (len() = batches per epoch); same handle here
+NodeLoader._seed_loader = property(lambda self: self._batcher)

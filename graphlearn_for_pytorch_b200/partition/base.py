@@ -27,8 +27,11 @@ from .partition_book import GLTPartitionBook, PartitionBook
 def save_meta(output_dir: str, num_parts: int, data_cls: str = 'homo',
               node_types: Optional[List[NodeType]] = None, edge_types: Optional[List[EdgeType]] = None):
   meta = {'num_parts': num_parts, 'data_cls': data_cls, 'node_types': node_types, 'edge_types': edge_types}
-  with open(os.path.join(output_dir, 'META'), 'wb') as f:
+  path = os.path.join(output_dir, 'META')
+  tmp = f'{path}.tmp{os.getpid()}'
+  with open(tmp, 'wb') as f:
     pickle.dump(meta, f, pickle.HIGHEST_PROTOCOL)
+  os.replace(tmp, path)          # several ranks may write the same META into a shared directory
 
 
 def _typed_path(root: str, stem: str, t=None, ext='.pt'):
@@ -45,12 +48,18 @@ def _plain(pb):
   return pb.as_subclass(torch.Tensor) if isinstance(pb, torch.Tensor) else pb
 
 
+def _save_atomic(obj, path: str):
+  tmp = f'{path}.tmp{os.getpid()}'
+  torch.save(obj, tmp)
+  os.replace(tmp, path)
+
+
 def save_node_pb(output_dir: str, node_pb: PartitionBook, ntype: Optional[NodeType] = None):
-  torch.save(_plain(node_pb), _typed_path(output_dir, 'node_pb', ntype))
+  _save_atomic(_plain(node_pb), _typed_path(output_dir, 'node_pb', ntype))
 
 
 def save_edge_pb(output_dir: str, edge_pb: PartitionBook, etype: Optional[EdgeType] = None):
-  torch.save(_plain(edge_pb), _typed_path(output_dir, 'edge_pb', etype))
+  _save_atomic(_plain(edge_pb), _typed_path(output_dir, 'edge_pb', etype))
 
 
 def _graph_dir(root: str, etype=None):

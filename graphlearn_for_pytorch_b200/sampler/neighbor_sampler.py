@@ -27,6 +27,18 @@ from .negative_sampler import RandomNegativeSampler
 _MAX_ARENA_NODES = 1 << 27
 
 
+def _count_tensors(counts: dict) -> dict:
+  """Per-hop counts of a heterogeneous sample as int64 tensors keyed by type, like the reference
+  (neighbor_sampler.py:310-314; they stay on the host: every consumer reads them as Python ints)."""
+  out = {}
+  for k, v in counts.items():
+    t = torch.as_tensor(v, dtype=torch.int64)
+    nz = torch.nonzero(t).view(-1)
+    # the reference appends a hop's count only while the type still shows up (count_dict): no trailing zero hops
+    out[k] = t[:max(int(nz[-1]) + 1 if nz.numel() else 1, 1)]
+  return out
+
+
 class NeighborSampler(BaseSampler):
   """Args:
     graph: `Graph` (homo) or Dict[EdgeType, Graph] (hetero).
@@ -396,7 +408,8 @@ class NeighborSampler(BaseSampler):
       num_edges[key] = [int(x) for x in ne[r]]
     batch = {nt: node[nt][:num_nodes[nt][0]].clone() for nt in seeds_dict if nt in node}
     return HeteroSamplerOutput(node=node, row=row, col=col, edge=edge if self.with_edge else None, batch=batch,
-                               num_sampled_nodes=num_nodes, num_sampled_edges=num_edges, edge_types=out_types,
+                               num_sampled_nodes=_count_tensors(num_nodes),
+                               num_sampled_edges=_count_tensors(num_edges), edge_types=out_types,
                                device=self.device)
 
   def _hetero_sample_from_nodes(self, seeds_dict: Dict[NodeType, torch.Tensor]) -> HeteroSamplerOutput:
@@ -462,7 +475,7 @@ class NeighborSampler(BaseSampler):
       row={k: torch.cat(v) for k, v in rows.items()},
       col={k: torch.cat(v) for k, v in cols.items()},
       edge={k: torch.cat(v) for k, v in eids.items()} if self.with_edge else None,
-      batch=batch, num_sampled_nodes=num_nodes, num_sampled_edges=num_edges,
+      batch=batch, num_sampled_nodes=_count_tensors(num_nodes), num_sampled_edges=_count_tensors(num_edges),
       edge_types=out_types, device=self.device)
 
   # ------------------------------------------------------------------ from edges

@@ -277,7 +277,8 @@ def test_hetero_and_link_sampling_gpu_matches_cpu(native):
     ea = set(zip(a.node[st][a.row[et]].tolist(), a.node[dt][a.col[et]].tolist(), a.edge[et].tolist()))
     eb = set(zip(b.node[st][b.row[et]].cpu().tolist(), b.node[dt][b.col[et]].cpu().tolist(), b.edge[et].cpu().tolist()))
     assert ea == eb
-  assert a.num_sampled_nodes == b.num_sampled_nodes
+  assert {k: v.tolist() for k, v in a.num_sampled_nodes.items()} == \
+      {k: v.tolist() for k, v in b.num_sampled_nodes.items()}        # per-type int64 tensors (reference convention)
   # homogeneous link sampling with strict binary negatives on the GPU
   ds = ring_dataset(40, graph_mode='CUDA', with_gpu=True, device=0, split_ratio=1.0)
   s = NeighborSampler(ds.graph, [2], with_neg=True, seed=3, device=DEV)
