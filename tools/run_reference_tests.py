@@ -20,10 +20,32 @@ for _m in list(sys.modules):
   if _m.startswith('graphlearn_for_pytorch_b200.'):
     sys.modules['graphlearn_torch.' + _m[len('graphlearn_for_pytorch_b200.'):]] = sys.modules[_m]
 '''
+# `parameterized` is not installed in the image: the two decorators the reference tests use, in 20 lines
+PARAMETERIZED = '''import functools
+
+
+class parameterized(object):
+  @staticmethod
+  def expand(cases):
+    def deco(fn):
+      import sys
+      frame = sys._getframe(1)
+      for i, case in enumerate(cases):
+        args = case if isinstance(case, (list, tuple)) else (case,)
+
+        def make(a):
+          @functools.wraps(fn)
+          def test(self):
+            return fn(self, *a)
+          return test
+        t = make(tuple(args))
+        t.__name__ = f'{fn.__name__}_{i}'
+        frame.f_locals[t.__name__] = t
+      return None
+    return deco
+'''
 SKIP = {'test_vineyard.py',               # needs a vineyard server
-        'test_pyg_remote_backend.py',     # needs torch_geometric's remote-backend loaders and `parameterized`
-        'test_dist_neighbor_loader.py',   # `parameterized` is not installed here
-        'test_dist_link_loader.py',       # same
+        'test_pyg_remote_backend.py',     # needs torch_geometric's remote-backend loaders
         'test_sample_prob.py'}            # imports torch_geometric.transforms
 
 
@@ -39,6 +61,8 @@ def main():
   os.makedirs(os.path.join(work, 'alias', 'graphlearn_torch'))
   with open(os.path.join(work, 'alias', 'graphlearn_torch', '__init__.py'), 'w') as f:
     f.write(ALIAS)
+  with open(os.path.join(work, 'alias', 'parameterized.py'), 'w') as f:
+    f.write(PARAMETERIZED)
   tests = os.path.join(work, 'tests')
   shutil.copytree(src, tests)
   files = sorted(f for f in os.listdir(tests) if f.startswith('test_') and f.endswith('.py') and f not in SKIP)
