@@ -365,9 +365,7 @@ class DistNeighborSampler(ConcurrentEventLoop):
           break
         frontier = torch.unique(nbr)
         nodes.append(frontier)
-    table = IdTable(self.device, sum(n.numel() for n in nodes))
-    local = table.init(torch.cat(nodes))
-    node = table.keys(0)
+    node = torch.unique(torch.cat(nodes))          # ascending ids, like the single-machine subgraph()
     owners = self.dist_graph.get_node_partitions(node, None)
     futs, rows_g, cols_g, eids_g = [], [], [], []
     for p in range(self.num_partitions):
@@ -390,9 +388,9 @@ class DistNeighborSampler(ConcurrentEventLoop):
     empty = torch.empty(0, dtype=torch.int64, device=self.device)
     rg = torch.cat(rows_g) if rows_g else empty
     cg = torch.cat(cols_g) if cols_g else empty
-    return SamplerOutput(node=node, row=table.lookup(rg), col=table.lookup(cg),
+    return SamplerOutput(node=node, row=torch.searchsorted(node, rg), col=torch.searchsorted(node, cg),
                          edge=(torch.cat(eids_g) if eids_g else empty) if self.with_edge else None,
-                         batch=seeds, device=self.device, metadata=local[:seeds.numel()])
+                         batch=seeds, device=self.device, metadata=torch.searchsorted(node, seeds))
 
   # ------------------------------------------------------------------ message collation
   async def _get_node_feats(self, ids: torch.Tensor, ntype=None):

@@ -585,26 +585,27 @@ class NeighborSampler(BaseSampler):
 
   def node_subgraph(self, all_nodes: torch.Tensor, num_seeds: int = 0):
     """Induced subgraph on exactly `all_nodes` (no neighbourhood expansion).
-    -> (unique nodes, rows, cols, eids, local ids of the first `num_seeds` inputs)."""
+    -> (unique nodes in ASCENDING id order, rows, cols, eids, local ids of the first `num_seeds` inputs).
+
+    Conventions of the reference (neighbor_sampler.py:474-498, test/python/test_subgraph.py): the node list is the
+    sorted unique id set; edges come out ordered by (source-side row, position in the row); and the edge index is
+    REVERSED with respect to the stored adjacency -- `row` holds the adjacency's column side, `col` its row side --
+    the same message-flow orientation `sample_from_nodes` uses."""
     all_nodes = all_nodes.to(self.device, dtype=torch.int64).contiguous()
     self.lazy_init_sampler()
+    uniq = torch.unique(all_nodes)                       # sorted
     if self.is_cuda:
-      table = IdTable(self.device, all_nodes.numel())
-      local = table.init(all_nodes)
+      table = IdTable(self.device, uniq.numel())
+      table.init(uniq)                                   # ordered insert: local id == rank in `uniq`
       n = table.size()
       rows, cols, eids = table.native.subgraph(self.graph.graph_handler, n, self.with_edge)
       node = table.keys(0)
-      mapping = local[:num_seeds]
     else:
       topo = self.graph.topo
       node, rows, cols, eids = self._nat.cpu_node_subgraph(topo.indptr, topo.indices, topo.edge_ids,
-                                                           all_nodes, self.with_edge)
-      t = self._nat.CpuIdTable(node.numel())
-      t.insert(node)
-      mapping = t.lookup(all_nodes[:num_seeds].contiguous())
-    if self.edge_dir == 'in':
-      rows, cols = cols, rows
-    return node, rows, cols, (eids if self.with_edge else None), mapping
+                                                           uniq, self.with_edge)
+    mapping = torch.searchsorted(node, all_nodes[:num_seeds].contiguous())
+    return node, cols, rows, (eids if self.with_edge else None), mapping
 
   # ------------------------------------------------------------------ random walk
   def random_walk(self, starts: torch.Tensor, walk_length: int, p: float = 1.0, q: float = 1.0,

@@ -114,7 +114,7 @@ def _w_link_and_subgraph(rank, world, port):
     nodes = set(b.node.tolist())
     src, dst = b.node[b.edge_index[0]], b.node[b.edge_index[1]]
     got = set(zip(src.tolist(), dst.tolist()))
-    want = {(a, c) for a in nodes for c in nodes if (c - a) % N in (1, 2)}
+    want = {(c, a) for a in nodes for c in nodes if (c - a) % N in (1, 2)}       # (neighbour, source), as sampled batches
     assert got == want                                    # induced edges from *both* partitions
     assert torch.equal(b.node[b.mapping], b.batch)
   loader.shutdown(); sub.shutdown()

@@ -97,7 +97,7 @@ def test_subgraph_loader():
     assert torch.equal(b.node[b.mapping], b.batch)
     assert torch.equal(b.x[:, 0].long(), b.node)
     src, dst = b.node[b.edge_index[0]], b.node[b.edge_index[1]]
-    assert torch.all(((dst - src) % 40 == 1) | ((dst - src) % 40 == 2))
+    assert torch.all(((src - dst) % 40 == 1) | ((src - dst) % 40 == 2))      # same orientation as NeighborLoader batches
 
 
 def test_hetero_neighbor_loader():

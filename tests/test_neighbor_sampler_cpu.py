@@ -91,8 +91,10 @@ def test_subgraph_and_mapping():
   nodes = set(out.node.tolist())
   assert nodes == {0, 1, 2, 3, 4, 5}
   assert out.node[out.metadata].tolist() == [0, 3]
-  src, dst = out.node[out.row], out.node[out.col]
-  got = set(zip(src.tolist(), dst.tolist()))
+  assert out.node.tolist() == sorted(nodes)                     # ascending ids (reference convention)
+  # reversed edge index, like sample_from_nodes: row = the adjacency's column side (a + 1, a + 2), col = a
+  nbr, src = out.node[out.row], out.node[out.col]
+  got = set(zip(src.tolist(), nbr.tolist()))
   want = {(a, b) for a in nodes for b in nodes if (b - a) % 40 in (1, 2)}
   assert got == want
 

@@ -4,7 +4,10 @@
 test/python/*.py are copied next to it and run with pytest.  Most of them build CUDA graphs in setUp, so the useful
 run is on a GPU box; on a CPU-only machine test_partition / test_graph / the CPU cases of the sampler tests run.
 
-  python tools/run_reference_tests.py [/root/reference] [-k expr]
+  python tools/run_reference_tests.py [/root/reference] [--patch-cuda-to-cpu] [-k expr]
+
+--patch-cuda-to-cpu rewrites `torch.device('cuda:0')` / `torch.device('cuda', 0)` in the copied tests to the CPU
+device, which lets the sampler tests' logic (expected node lists, edge indices, edge ids) run on a CPU-only machine.
 """
 import os
 import shutil
@@ -52,6 +55,9 @@ SKIP = {'test_vineyard.py',               # needs a vineyard server
 def main():
   args = sys.argv[1:]
   ref = args.pop(0) if args and not args[0].startswith('-') else '/root/reference'
+  patch = '--patch-cuda-to-cpu' in args
+  if patch:
+    args.remove('--patch-cuda-to-cpu')
   src = os.path.join(ref, 'test', 'python')
   if not os.path.isdir(src):
     print('no reference tests at', src)
@@ -63,9 +69,22 @@ def main():
     f.write(ALIAS)
   with open(os.path.join(work, 'alias', 'parameterized.py'), 'w') as f:
     f.write(PARAMETERIZED)
+  # the tests build / check torch_geometric Data objects: map them to this package's attribute-compatible containers
+  os.makedirs(os.path.join(work, 'alias', 'torch_geometric', 'data'))
+  with open(os.path.join(work, 'alias', 'torch_geometric', '__init__.py'), 'w') as f:
+    f.write('from . import data\n')
+  with open(os.path.join(work, 'alias', 'torch_geometric', 'data', '__init__.py'), 'w') as f:
+    f.write('from graphlearn_for_pytorch_b200.loader.data import Data, HeteroData  # noqa: F401\n')
   tests = os.path.join(work, 'tests')
   shutil.copytree(src, tests)
   files = sorted(f for f in os.listdir(tests) if f.startswith('test_') and f.endswith('.py') and f not in SKIP)
+  if patch:
+    for f in files:
+      path = os.path.join(tests, f)
+      src_txt = open(path).read()
+      src_txt = src_txt.replace("torch.device('cuda:0')", "torch.device('cpu')").replace(
+          "torch.device('cuda', 0)", "torch.device('cpu')")
+      open(path, 'w').write(src_txt)
   env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(work, 'alias'), ROOT,
                                                      os.path.join(ROOT, 'baseline', 'shims')]))
   rc = 0
