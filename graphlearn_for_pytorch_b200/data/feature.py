@@ -44,6 +44,10 @@ class Feature(object):
                dtype: torch.dtype = torch.float32):
     self.feature_tensor = feature_tensor.to(dtype) if feature_tensor is not None and \
         feature_tensor.dtype != dtype else feature_tensor
+    # a tensor (id -> row), any sequence convertible to one, or an offset map such as the range partition book's
+    # `OffsetId2Index` (row = id - offset; reference partition_book.py:50-64), which is kept as an object
+    if id2index is not None and not isinstance(id2index, torch.Tensor) and not hasattr(id2index, 'offset'):
+      id2index = torch.as_tensor(id2index, dtype=torch.int64)
     self.id2index = id2index
     self.split_ratio = float(split_ratio)
     self.device_group_list = device_group_list
@@ -65,6 +69,8 @@ class Feature(object):
     self.lazy_init()
     dev = torch.device('cuda', self.device)
     ids = ids.to(dev, dtype=torch.int64).contiguous()
+    if self._id2index_dev is None and self.id2index is not None:
+      ids = self.id2index[ids]        # offset map: plain arithmetic on the device
     out = self._unified._table().gather(ids, self._id2index_dev, 0)
     tail = self._shape[1:]
     return out if len(tail) == 1 else out.view(ids.numel(), *tail)
@@ -105,7 +111,7 @@ class Feature(object):
         self._init_from_ipc()
       else:
         self._split_and_init()
-      if self.id2index is not None:
+      if isinstance(self.id2index, torch.Tensor):
         self._id2index_dev = self.id2index.to(torch.device('cuda', self.device), dtype=torch.int64)
 
   def lazy_init_with_ipc_handle(self):
@@ -156,13 +162,13 @@ class Feature(object):
         cpu = self._cpu_part
         if cpu is not None and not cpu.is_shared():
           self._cpu_part = cpu = cpu.clone().share_memory_()
-        if self.id2index is not None:
+        if isinstance(self.id2index, torch.Tensor):
           self.id2index = self.id2index.cpu().share_memory_()
         return (self._cuda_parts_by_group, cpu, full, self.id2index, self.split_ratio,
                 self.device_group_list, self.with_gpu, self.dtype, self._shape)
       if self.feature_tensor is not None:
         self.feature_tensor.share_memory_()
-      if self.id2index is not None:
+      if isinstance(self.id2index, torch.Tensor):
         self.id2index = self.id2index.cpu().share_memory_()
       return (None, None, self.feature_tensor, self.id2index, self.split_ratio,
               self.device_group_list, self.with_gpu, self.dtype, self._shape)

@@ -39,8 +39,9 @@ def message_to_sampler_output(msg: SampleMessage, device, edge_dir: str = 'out')
       node=to(msg['ids']), row=to(msg['rows']), col=to(msg['cols']),
       edge=to(msg['eids']) if 'eids' in msg else None,
       batch=to(msg['batch']) if 'batch' in msg else None,
-      num_sampled_nodes=msg['num_sampled_nodes'].tolist() if 'num_sampled_nodes' in msg else None,
-      num_sampled_edges=msg['num_sampled_edges'].tolist() if 'num_sampled_edges' in msg else None,
+      # per-hop counts stay int64 tensors, like the reference's loader hands them out (dist_loader.py:428-447)
+      num_sampled_nodes=msg['num_sampled_nodes'].to(torch.int64).cpu() if 'num_sampled_nodes' in msg else None,
+      num_sampled_edges=msg['num_sampled_edges'].to(torch.int64).cpu() if 'num_sampled_edges' in msg else None,
       device=device, metadata=md)
     return out, (to(msg['nfeats']) if 'nfeats' in msg else None), \
         (to(msg['nlabels']) if 'nlabels' in msg else None), (to(msg['efeats']) if 'efeats' in msg else None)

@@ -137,6 +137,24 @@ def global_barrier(timeout=None):
 
 
 # ----------------------------------------------------------------------------- init / shutdown
+def _own_worker_name():
+  return rpc.get_worker_info().name
+
+
+def _discover_name_by_rank(global_rank: int, fallback: str, timeout: float, interval: float = 0.2) -> str:
+  """Name of the member that joined a dynamic RPC group with `global_rank`; `fallback` after `timeout` seconds
+  (the conventional `<group>_<rank>` name is then resolved lazily by `_wait_for_member`)."""
+  import time
+  deadline = time.time() + min(float(timeout), 60.0)
+  while True:
+    try:
+      return rpc.rpc_sync(global_rank, _own_worker_name, timeout=5.0)
+    except Exception:  # noqa: BLE001  (not joined yet / transient connect error)
+      if time.time() > deadline:
+        return fallback
+      time.sleep(interval)
+
+
 def init_rpc(master_addr: str, master_port: int, num_rpc_threads: int = 16, rpc_timeout: float = 180,
              is_dynamic: bool = False):
   """Join the RPC world described by the current DistContext."""
@@ -168,8 +186,14 @@ def init_rpc(master_addr: str, master_port: int, num_rpc_threads: int = 16, rpc_
       names = collections.defaultdict(list)
       names[ctx.role] = [f'{ctx.group_name}_{r}' for r in range(ctx.world_size)]
       if ctx.role == DistRole.CLIENT:
-        g = os.environ.get('GLT_B200_PEER_GROUP', _DEFAULT_SERVER_GROUP)
-        names[DistRole.SERVER] = [f'{g}_{r}' for r in range(ctx.num_servers())]
+        g = os.environ.get('GLT_B200_PEER_GROUP')
+        if g is not None:
+          names[DistRole.SERVER] = [f'{g}_{r}' for r in range(ctx.num_servers())]
+        else:
+          # servers own global ranks [0, num_servers): ask each one for its name (it may use any group name), with
+          # bounded retries while it is still joining (reference rpc.py:300-318)
+          names[DistRole.SERVER] = [_discover_name_by_rank(r, f'{_DEFAULT_SERVER_GROUP}_{r}', rpc_timeout)
+                                    for r in range(ctx.num_servers())]
       elif ctx.role == DistRole.SERVER:
         g = os.environ.get('GLT_B200_PEER_GROUP', _DEFAULT_CLIENT_GROUP)
         names[DistRole.CLIENT] = [f'{g}_{r}' for r in range(ctx.num_clients())]

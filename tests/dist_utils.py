@@ -51,6 +51,7 @@ def check_batch(b, with_edge=True):
   if with_edge and b.edge is not None and b.edge_attr is not None:
     assert torch.equal(b.edge_attr[:, 0].long(), b.edge)
   assert sum(b.num_sampled_nodes) == b.node.numel()
+  assert torch.is_tensor(b.num_sampled_nodes) and b.num_sampled_nodes.dtype == torch.int64   # reference convention
 
 
 def _entry(rank, world, port, fn, args, err_q):

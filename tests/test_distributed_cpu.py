@@ -366,7 +366,9 @@ def _w_server_client_auto(rank, world, port, seed_files, dynamic):
   from graphlearn_for_pytorch_b200.sampler import RemoteNodePathSamplerInput
   if rank < 2:
     ds = build_partition(rank, 2)
-    d.init_server(2, rank, ds, '127.0.0.1', port, num_clients=2, is_dynamic=dynamic)
+    # dynamic: a non-default server group name, which the clients must discover by rank (they are not told)
+    d.init_server(2, rank, ds, '127.0.0.1', port, num_clients=2, is_dynamic=dynamic,
+                  server_group_name='custom_named_servers' if dynamic else None)
     d.wait_and_shutdown_server()
     return
   crank = rank - 2

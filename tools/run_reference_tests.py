@@ -10,6 +10,7 @@ run is on a GPU box; on a CPU-only machine test_partition / test_graph / the CPU
 device, which lets the sampler tests' logic (expected node lists, edge indices, edge ids) run on a CPU-only machine.
 """
 import os
+import re
 import shutil
 import subprocess
 import sys
@@ -58,6 +59,14 @@ def main():
   patch = '--patch-cuda-to-cpu' in args
   if patch:
     args.remove('--patch-cuda-to-cpu')
+  only = None
+  for a in list(args):
+    if a.startswith('--only='):       # --only=test_subgraph.py,test_feature.py
+      only = set(a[len('--only='):].split(','))
+      args.remove(a)
+  show = '--show' in args             # print the whole pytest output of every file
+  if show:
+    args.remove('--show')
   src = os.path.join(ref, 'test', 'python')
   if not os.path.isdir(src):
     print('no reference tests at', src)
@@ -77,13 +86,18 @@ def main():
     f.write('from graphlearn_for_pytorch_b200.loader.data import Data, HeteroData  # noqa: F401\n')
   tests = os.path.join(work, 'tests')
   shutil.copytree(src, tests)
-  files = sorted(f for f in os.listdir(tests) if f.startswith('test_') and f.endswith('.py') and f not in SKIP)
+  files = sorted(f for f in os.listdir(tests) if f.startswith('test_') and f.endswith('.py') and f not in SKIP
+                 and (only is None or f in only))
   if patch:
     for f in files:
       path = os.path.join(tests, f)
       src_txt = open(path).read()
-      src_txt = src_txt.replace("torch.device('cuda:0')", "torch.device('cpu')").replace(
-          "torch.device('cuda', 0)", "torch.device('cpu')")
+      # every spelling of a CUDA device (cuda:0 / ('cuda', i % n) / bare 'cuda'), and a device count of at least one
+      src_txt = re.sub(r"torch\.device\(\s*'cuda(:\d+)?'\s*(,[^()]*(\([^()]*\))?[^()]*)?\)", "torch.device('cpu')", src_txt)
+      src_txt = re.sub(r"'cuda(:\d+)?'", "'cpu'", src_txt)                      # device='cuda:1'
+      src_txt = src_txt.replace('torch.cuda.device_count()', 'max(torch.cuda.device_count(), 1)')
+      src_txt = re.sub(r"device\s*=\s*0\b", "device='cpu'", src_txt)           # torch.tensor(..., device=0)
+      src_txt = re.sub(r"\.to\(0\)", ".to('cpu')", src_txt).replace('.cuda()', '.cpu()')
       open(path, 'w').write(src_txt)
   env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(work, 'alias'), ROOT,
                                                      os.path.join(ROOT, 'baseline', 'shims')]))
@@ -98,6 +112,8 @@ def main():
       continue
     tail = [ln for ln in out.stdout.strip().splitlines() if 'passed' in ln or 'failed' in ln or 'error' in ln]
     print(f'{f:40s} {tail[-1] if tail else out.stdout[-200:]}', flush=True)
+    if show:
+      print(out.stdout[-6000:], out.stderr[-3000:], flush=True)
     rc |= out.returncode
   return rc
 
