@@ -1423,6 +1423,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("cpu_random_walk", &cpu_random_walk);
   m.def("cpu_stitch", &cpu_stitch);
   m.def("cpu_nbr_prob", &cpu_nbr_prob);
+  m.def("cpu_gather_rows", &cpu_gather_rows, py::arg("table"), py::arg("ids"), py::arg("id2index"), py::arg("offset"),
+        py::arg("out"), py::arg("pos"));
   py::class_<CpuIdTable>(m, "CpuIdTable")
       .def(py::init<int64_t>())
       .def("reset", &CpuIdTable::reset)

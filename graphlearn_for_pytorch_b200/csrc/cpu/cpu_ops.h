@@ -34,9 +34,12 @@ class CpuIdTable {
   int64_t find_one(int64_t key) const;
 
  private:
+  struct Slot { int64_t key; int32_t val; uint32_t gen; };
   void rehash(int64_t min_slots);
-  std::vector<int64_t> slots_key_, slots_val_, keys_;
+  std::vector<Slot> slots_;
+  std::vector<int64_t> keys_;
   uint64_t mask_ = 0;
+  uint32_t gen_ = 1;
 };
 
 std::tuple<Tensor, Tensor> cpu_negative_sample(
@@ -53,6 +56,11 @@ Tensor cpu_random_walk(const Tensor& indptr, const Tensor& indices, const Tensor
 std::tuple<Tensor, Tensor, Tensor> cpu_stitch(
     int64_t num_seeds, const std::vector<Tensor>& idx_list, const std::vector<Tensor>& nbrs_list,
     const std::vector<Tensor>& nbrs_num_list, const std::vector<Tensor>& eids_list);
+
+// out[pos[i]] (or out[i]) = table[id2index[ids[i]] - 0] (or table[ids[i] - offset]); rows are copied as raw bytes by
+// all intra-op threads.  Host tier of Feature / RPC feature callee / DistFeature stitch.
+void cpu_gather_rows(const Tensor& table, const Tensor& ids, const c10::optional<Tensor>& id2index, int64_t offset,
+                     Tensor out, const c10::optional<Tensor>& pos);
 
 Tensor cpu_nbr_prob(const Tensor& indptr, const Tensor& indices, const Tensor& nbr_indptr,
                     const Tensor& last_prob, const Tensor& nbr_last_prob, int64_t k);

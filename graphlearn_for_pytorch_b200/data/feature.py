@@ -13,6 +13,7 @@ from typing import List, Optional
 
 import torch
 
+from ..ops import _load as _native_module
 from ..utils.device import get_available_device
 from ..parallel.peer import IpcCudaTensor
 from .unified_tensor import UnifiedTensor
@@ -81,11 +82,33 @@ class Feature(object):
     gathered through the unified table on the device and copied back."""
     ids = ids.to('cpu', dtype=torch.int64)
     if self.feature_tensor is not None:
-      idx = self.id2index[ids] if self.id2index is not None else ids
-      return self.feature_tensor[idx]
+      out = torch.empty((ids.numel(), *self.feature_tensor.shape[1:]), dtype=self.feature_tensor.dtype)
+      return self.cpu_get_into(ids, out)
     if not self.with_gpu:
       raise RuntimeError('feature tensor is not available in this process')
     return self.__getitem__(ids).cpu()
+
+  def cpu_get_into(self, ids: torch.Tensor, out: torch.Tensor, pos: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[pos] (or out[:len(ids)]) = rows of `ids`, one fused native pass over all intra-op threads
+    (`cpu_gather_rows`: id2index / offset mapping, bounds checks and the row copies in the same loop; no temporary
+    for the gathered rows).  Falls back to torch indexing for tensors the native op does not take."""
+    ids = ids.to('cpu', dtype=torch.int64).contiguous().view(-1)
+    ft = self.feature_tensor
+    i2i = self.id2index
+    nat = _native_module()
+    if (nat is not None and ft.device.type == 'cpu' and ft.is_contiguous() and out.is_contiguous()
+        and out.device.type == 'cpu' and out.dtype == ft.dtype and ft.shape[0] > 0
+        and (i2i is None or hasattr(i2i, 'offset') or (i2i.device.type == 'cpu' and i2i.dtype == torch.int64))):
+      off = int(i2i.offset) if (i2i is not None and hasattr(i2i, 'offset')) else 0
+      table = i2i.contiguous() if isinstance(i2i, torch.Tensor) else None
+      nat.cpu_gather_rows(ft, ids, table, off, out, None if pos is None else pos.contiguous())
+      return out
+    rows = ft[i2i[ids] if i2i is not None else ids]
+    if pos is None:
+      out[:ids.numel()] = rows
+    else:
+      out[pos] = rows
+    return out
 
   # ------------------------------------------------------------------ init
   def _check_and_set_device(self):

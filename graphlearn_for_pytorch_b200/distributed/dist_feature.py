@@ -88,11 +88,16 @@ class DistFeature(object):
     owners = pb[ids_cpu]
     feat = self._feat(input_type)
     width = feat.shape[1:]
-    out = torch.zeros((ids_cpu.numel(), *width), dtype=feat.dtype, device=self.device)
+    # every id with an owner in [0, num_partitions) gets its row written below: no zero fill needed then
+    covered = bool(((owners >= 0) & (owners < self.num_partitions)).all())
+    out = (torch.empty if covered else torch.zeros)((ids_cpu.numel(), *width), dtype=feat.dtype, device=self.device)
     local_mask = owners == self.partition_idx
     if bool(local_mask.any()):
       pos = torch.nonzero(local_mask, as_tuple=False).view(-1)
-      out[pos.to(self.device)] = self.local_get(ids_cpu[pos], True, input_type).to(self.device)
+      if self.device.type == 'cpu' and not getattr(feat, 'with_gpu', False) and feat.feature_tensor is not None:
+        feat.cpu_get_into(ids_cpu[pos], out, pos)       # gather straight into the result rows (one native pass)
+      else:
+        out[pos.to(self.device)] = self.local_get(ids_cpu[pos], True, input_type).to(self.device)
     pending = []
     for p in range(self.num_partitions):
       if p == self.partition_idx:

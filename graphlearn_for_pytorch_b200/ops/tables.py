@@ -5,9 +5,16 @@ One table per node type gives the hetero inducer.  CPU: native flat hash map
 warp-aggregated (unordered inside a hop, hop-contiguous) afterwards.
 Reference counterparts: csrc/cpu/inducer.cc:25-181, csrc/cuda/inducer.cu:75-338.
 """
+import threading
+
 import torch
 
 from . import require_native
+
+# Host tables are recycled: a sampler makes one table per batch (per node type), the native table resets in O(1)
+# (generation-stamped slots) and grows on demand, so a released table serves any later batch without clearing or
+# re-allocating tens of megabytes of slots.
+_CPU_POOL, _CPU_POOL_MAX, _CPU_POOL_LOCK = [], 16, threading.Lock()
 
 
 class IdTable(object):
@@ -19,8 +26,24 @@ class IdTable(object):
     if self.is_cuda:
       self._t = nat.DeviceTable(self.device.index or 0, self.capacity)
     else:
-      self._t = nat.CpuIdTable(self.capacity)
+      with _CPU_POOL_LOCK:
+        self._t = _CPU_POOL.pop() if _CPU_POOL else None
+      if self._t is None:
+        self._t = nat.CpuIdTable(self.capacity)
+      else:
+        self._t.reset()
     self._size = 0
+
+  def __del__(self):
+    t = getattr(self, '_t', None)
+    if t is not None and not getattr(self, 'is_cuda', True):
+      self._t = None
+      try:
+        with _CPU_POOL_LOCK:
+          if len(_CPU_POOL) < _CPU_POOL_MAX:
+            _CPU_POOL.append(t)
+      except Exception:  # noqa: BLE001  (interpreter shutdown)
+        pass
 
   def reset(self):
     if self.is_cuda:

@@ -24,7 +24,10 @@ class GLTPartitionBook(PartitionBook, torch.Tensor):
   """A plain tensor book: book[id] = partition id."""
 
   def __getitem__(self, indices) -> torch.Tensor:
-    return torch.Tensor.__getitem__(self, indices)
+    # The lookup result is a PLAIN tensor: a subclass result would infect every mask / gather derived from it
+    # (each op then detours through Python's __torch_function__) and, worse, the RPC pickler only takes the
+    # zero-copy tensor-table path for exact `torch.Tensor`s -- subclass instances are pickled storage by storage.
+    return torch.Tensor.__getitem__(self.as_subclass(torch.Tensor), indices)
 
 
 class RangePartitionBook(PartitionBook):
