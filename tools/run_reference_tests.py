@@ -49,8 +49,7 @@ class parameterized(object):
     return deco
 '''
 SKIP = {'test_vineyard.py',               # needs a vineyard server
-        'test_pyg_remote_backend.py',     # needs torch_geometric's remote-backend loaders
-        'test_sample_prob.py'}            # imports torch_geometric.transforms
+        'test_sample_prob.py'}            # downloads OGB-MAG through torch_geometric.datasets
 
 
 def main():
@@ -81,7 +80,18 @@ def main():
   # the tests build / check torch_geometric Data objects: map them to this package's attribute-compatible containers
   os.makedirs(os.path.join(work, 'alias', 'torch_geometric', 'data'))
   with open(os.path.join(work, 'alias', 'torch_geometric', '__init__.py'), 'w') as f:
-    f.write('from . import data\n')
+    f.write('from . import data, utils\n')
+  # test_pyg_remote_backend uses two index helpers of torch_geometric.utils.sparse
+  os.makedirs(os.path.join(work, 'alias', 'torch_geometric', 'utils'))
+  with open(os.path.join(work, 'alias', 'torch_geometric', 'utils', '__init__.py'), 'w') as f:
+    f.write('from . import sparse\n')
+  with open(os.path.join(work, 'alias', 'torch_geometric', 'utils', 'sparse.py'), 'w') as f:
+    f.write('import torch\n\n\n'
+            'def index2ptr(index, size=None):\n'
+            '  size = int(index.max()) + 1 if size is None else size\n'
+            '  return torch.cat([index.new_zeros(1), torch.bincount(index, minlength=size).cumsum(0)])\n\n\n'
+            'def ptr2index(ptr):\n'
+            '  return torch.repeat_interleave(torch.arange(ptr.numel() - 1, device=ptr.device), ptr[1:] - ptr[:-1])\n')
   with open(os.path.join(work, 'alias', 'torch_geometric', 'data', '__init__.py'), 'w') as f:
     f.write('from graphlearn_for_pytorch_b200.loader.data import Data, HeteroData  # noqa: F401\n')
   tests = os.path.join(work, 'tests')
