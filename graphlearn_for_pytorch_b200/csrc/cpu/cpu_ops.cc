@@ -161,6 +161,12 @@ std::tuple<Tensor, Tensor, Tensor, Tensor> coo_to_csr(
 // Uniform neighbour sampling (Floyd k-subset, without replacement by default).
 // Reference semantics: csrc/cpu/random_sampler.cc:26-153 (req_num<0 => all).
 // ----------------------------------------------------------------------------
+// Rows per parallel chunk of the uniform sampler: a row costs about k random reads (k < 0: its whole adjacency), and
+// a chunk has to be worth far more than starting a thread (tens of microseconds).
+static inline int64_t sample_grain(int64_t k) {
+  return std::max<int64_t>(256, 32768 / std::max<int64_t>(k < 0 ? 32 : k, 1));
+}
+
 static inline int64_t row_degree(const int64_t* ip, int64_t num_rows, int64_t v) {
   // Ids beyond the local CSR have no neighbours (partition shards only cover
   // rows up to their max local src id; reference random_sampler.cu:45-50).
@@ -189,7 +195,7 @@ std::tuple<Tensor, Tensor, Tensor> cpu_sample_neighbors(
   Tensor counts = torch::empty({bs}, torch::kInt64);
   int64_t* cnt = counts.data_ptr<int64_t>();
   std::vector<int64_t> offs(bs + 1, 0);
-  glt::parallel_for(0, bs, 4096, [&](int64_t b, int64_t e) {   // degree reads are random: spread the misses
+  glt::parallel_for(0, bs, 16384, [&](int64_t b, int64_t e) {   // degree reads are random: spread the misses
     for (int64_t i = b; i < e; ++i) {
       int64_t d = row_degree(ip, num_rows, sd[i]);
       cnt[i] = (k < 0) ? d : (replace ? (d > 0 ? k : 0) : std::min(d, k));
@@ -201,7 +207,7 @@ std::tuple<Tensor, Tensor, Tensor> cpu_sample_neighbors(
   Tensor out_e = with_edge ? torch::empty({offs[bs]}, torch::kInt64) : Tensor();
   int64_t* nb = nbrs.data_ptr<int64_t>();
   int64_t* oe = with_edge ? out_e.data_ptr<int64_t>() : nullptr;
-  glt::parallel_for(0, bs, 64, [&](int64_t b, int64_t e) {
+  glt::parallel_for(0, bs, sample_grain(k), [&](int64_t b, int64_t e) {
     std::vector<uint32_t> chosen;
     for (int64_t i = b; i < e; ++i) {
       const int64_t v = sd[i];
@@ -268,7 +274,7 @@ std::tuple<Tensor, Tensor, Tensor> cpu_sample_neighbors_weighted(
   Tensor counts = torch::empty({bs}, torch::kInt64);
   int64_t* cnt = counts.data_ptr<int64_t>();
   std::vector<int64_t> offs(bs + 1, 0);
-  glt::parallel_for(0, bs, 4096, [&](int64_t b, int64_t e) {
+  glt::parallel_for(0, bs, 16384, [&](int64_t b, int64_t e) {
     for (int64_t i = b; i < e; ++i) {
       int64_t d = row_degree(ip, num_rows, sd[i]);
       cnt[i] = (k < 0) ? d : std::min(d, k);
@@ -279,7 +285,7 @@ std::tuple<Tensor, Tensor, Tensor> cpu_sample_neighbors_weighted(
   Tensor out_e = with_edge ? torch::empty({offs[bs]}, torch::kInt64) : Tensor();
   int64_t* nb = nbrs.data_ptr<int64_t>();
   int64_t* oe = with_edge ? out_e.data_ptr<int64_t>() : nullptr;
-  glt::parallel_for(0, bs, 64, [&](int64_t b, int64_t e) {
+  glt::parallel_for(0, bs, 256, [&](int64_t b, int64_t e) {
     std::vector<std::pair<float, int64_t>> keys;
     for (int64_t i = b; i < e; ++i) {
       const int64_t v = sd[i];
@@ -398,7 +404,7 @@ Tensor CpuIdTable::lookup(const Tensor& keys) const {
   Tensor out = torch::empty_like(keys);
   const int64_t* k = keys.data_ptr<int64_t>();
   int64_t* o = out.data_ptr<int64_t>();
-  glt::parallel_for(0, keys.numel(), 4096, [&](int64_t b, int64_t e) {
+  glt::parallel_for(0, keys.numel(), 8192, [&](int64_t b, int64_t e) {
     for (int64_t i = b; i < e; ++i) o[i] = find_one(k[i]);
   });
   return out;
@@ -435,7 +441,7 @@ std::tuple<Tensor, Tensor> cpu_negative_sample(
   TORCH_CHECK(num_cols > 0, "num_cols must be positive");
   std::vector<int64_t> r(req), c(req);
   std::vector<uint8_t> ok(req, 0);
-  glt::parallel_for(0, req, 256, [&](int64_t b, int64_t e) {
+  glt::parallel_for(0, req, 2048, [&](int64_t b, int64_t e) {
     for (int64_t i = b; i < e; ++i) {
       for (int64_t t = 0; t < trials; ++t) {
         int64_t rr = bounded(philox_draw(seed, stream, i, 2 * t), (uint32_t)num_rows);
@@ -484,7 +490,7 @@ std::tuple<Tensor, Tensor, Tensor, Tensor> cpu_node_subgraph(
   const int64_t n = nodes.numel();
   const int64_t* nd = nodes.data_ptr<int64_t>();
   std::vector<int64_t> cnt(n + 1, 0);
-  glt::parallel_for(0, n, 64, [&](int64_t b, int64_t e) {
+  glt::parallel_for(0, n, 1024, [&](int64_t b, int64_t e) {
     for (int64_t i = b; i < e; ++i) {
       int64_t v = nd[i], c = 0;
       if (v >= 0 && v < num_rows)
@@ -498,7 +504,7 @@ std::tuple<Tensor, Tensor, Tensor, Tensor> cpu_node_subgraph(
   int64_t* pr = rows.data_ptr<int64_t>();
   int64_t* pc = cols.data_ptr<int64_t>();
   int64_t* pe = with_edge ? oe.data_ptr<int64_t>() : nullptr;
-  glt::parallel_for(0, n, 64, [&](int64_t b, int64_t e) {
+  glt::parallel_for(0, n, 1024, [&](int64_t b, int64_t e) {
     for (int64_t i = b; i < e; ++i) {
       int64_t v = nd[i], o = cnt[i];
       if (v < 0 || v >= num_rows) continue;
@@ -534,7 +540,7 @@ Tensor cpu_random_walk(const Tensor& indptr, const Tensor& indices, const Tensor
   int64_t* o = out.data_ptr<int64_t>();
   const bool biased = !(p == 1.0 && q == 1.0);
   const double maxw = std::max({1.0, 1.0 / p, 1.0 / q});
-  glt::parallel_for(0, n, 64, [&](int64_t b, int64_t e) {
+  glt::parallel_for(0, n, 512, [&](int64_t b, int64_t e) {
     for (int64_t i = b; i < e; ++i) {
       int64_t cur = st[i], prev = -1;
       o[i * (walk_length + 1)] = cur;
@@ -631,7 +637,7 @@ Tensor cpu_nbr_prob(const Tensor& indptr, const Tensor& indices, const Tensor& n
   const float* nlp = nbr_last_prob.data_ptr<float>();
   Tensor cur = torch::zeros({n}, torch::kFloat32);
   float* cp = cur.data_ptr<float>();
-  glt::parallel_for(0, std::min(n, rows), 256, [&](int64_t b, int64_t e) {
+  glt::parallel_for(0, std::min(n, rows), 2048, [&](int64_t b, int64_t e) {
     for (int64_t v = b; v < e; ++v) {
       if (ip[v + 1] == ip[v]) continue;  // isolated rows stay 0 (reference :181-185)
       double acc = 1.0;
