@@ -12,6 +12,7 @@
 #include <cstdint>
 #include <exception>
 #include <mutex>
+#include <system_error>
 #include <thread>
 #include <vector>
 
@@ -41,11 +42,18 @@ inline void parallel_for(int64_t begin, int64_t end, int64_t grain, const F& f) 
   };
   std::vector<std::thread> workers;
   workers.reserve(nt - 1);
+  int64_t inline_from = nt;          // chunks [inline_from, nt) run on the caller when no more threads can be started
   for (int64_t t = 1; t < nt; ++t) {
     const int64_t lo = begin + t * chunk, hi = std::min(end, lo + chunk);
-    workers.emplace_back(run, lo, hi);
+    try {
+      workers.emplace_back(run, lo, hi);
+    } catch (const std::system_error&) {   // thread limit reached: finish the rest here instead of terminating
+      inline_from = t;
+      break;
+    }
   }
   run(begin, std::min(end, begin + chunk));
+  for (int64_t t = inline_from; t < nt; ++t) run(begin + t * chunk, std::min(end, begin + (t + 1) * chunk));
   for (auto& w : workers) w.join();
   if (err) std::rethrow_exception(err);
 }

@@ -96,7 +96,48 @@ static void test_inducer() {
   CHECK_T(t.size() == 5005 && t.find_one(1000003LL * 4999) == 5004);
   t.reset();
   CHECK_T(t.size() == 0 && vec(t.insert(i64({3}))) == (std::vector<int64_t>{0}));
+  // O(1) reset by generation stamp: keys of earlier generations are gone, recycled tables behave like new ones
+  for (int round = 0; round < 50; ++round) {
+    t.reset();
+    CHECK_T(t.find_one(1000003LL * 7) == -1 && t.find_one(3) == -1);
+    CHECK_T(vec(t.insert(i64({40 + round, 3, 40 + round}))) == (std::vector<int64_t>{0, 1, 0}));
+    CHECK_T(vec(t.keys(0)) == (std::vector<int64_t>{40 + round, 3}));
+  }
   std::printf("CpuIdTable (inducer) ok\n");
+}
+
+static void test_gather_rows_and_threads() {
+  const int64_t n = 5000, w = 7;
+  Tensor table = torch::arange(n * w, torch::kFloat32).view({n, w});
+  Tensor ids = torch::randint(0, n, {20000}, torch::kInt64);
+  Tensor out = torch::zeros({20000, w}, torch::kFloat32);
+  at::set_num_threads(4);                                                          // chunks run on several threads
+  glt::cpu_gather_rows(table, ids, c10::nullopt, 0, out, c10::nullopt);
+  CHECK_T(torch::equal(out, table.index_select(0, ids)));
+  Tensor perm = torch::randperm(n, torch::kInt64);                                  // id2index lookup + scatter positions
+  Tensor pos = torch::randperm(20000, torch::kInt64);
+  Tensor out2 = torch::zeros({20000, w}, torch::kFloat32);
+  glt::cpu_gather_rows(table, ids, perm, 0, out2, pos);
+  CHECK_T(torch::equal(out2.index_select(0, pos), table.index_select(0, perm.index_select(0, ids))));
+  Tensor out3 = torch::zeros({3, w}, torch::kFloat32);                              // offset map (range partition book)
+  glt::cpu_gather_rows(table, i64({1000, 1002, 1001}), c10::nullopt, 1000, out3, c10::nullopt);
+  CHECK_T(torch::equal(out3, table.index_select(0, i64({0, 2, 1}))));
+  bool raised = false;
+  try { glt::cpu_gather_rows(table, i64({n}), c10::nullopt, 0, out3, c10::nullopt); } catch (const c10::Error&) { raised = true; }
+  CHECK_T(raised);
+  // the samplers give the same answer on one thread and on many (counter-based RNG, per-row output slots)
+  auto [ptr, ind, e, wgt] = glt::coo_to_csr(torch::randint(0, 3000, {60000}, torch::kInt64),
+                                            torch::randint(0, 3000, {60000}, torch::kInt64), c10::nullopt,
+                                            c10::nullopt, 3000, true);
+  (void)wgt;
+  Tensor seeds = torch::randint(0, 3000, {40000}, torch::kInt64);
+  at::set_num_threads(1);
+  auto a = glt::cpu_sample_neighbors(ptr, ind, e, seeds, 5, true, false, 11, 3);
+  at::set_num_threads(4);
+  auto b = glt::cpu_sample_neighbors(ptr, ind, e, seeds, 5, true, false, 11, 3);
+  CHECK_T(torch::equal(std::get<0>(a), std::get<0>(b)) && torch::equal(std::get<1>(a), std::get<1>(b)) &&
+          torch::equal(std::get<2>(a), std::get<2>(b)));
+  std::printf("cpu_gather_rows / threaded loops ok\n");
 }
 
 static void test_subgraph_and_negative() {
@@ -160,6 +201,7 @@ int main() {
   test_coo_to_csr();
   test_sampler();
   test_inducer();
+  test_gather_rows_and_threads();
   test_subgraph_and_negative();
   test_stitch();
   test_serializer();
