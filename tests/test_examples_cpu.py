@@ -193,3 +193,12 @@ def test_igbh_large_schema_with_venue_types(tmp_path):
   assert 'val-acc' in out
   out = _run(['examples/igbh/download.py', '--path', d, '--size', 'full', '--dry-run'])
   assert out.count('would fetch') >= 16 and 'paper__venue__conference/edge_index.npy' in out
+
+
+def test_cpu_mode_distributed_loader_benchmark_runs():
+  """benchmarks/bench_dist_loader_cpu.py (2 trainers x 1 sampling worker over localhost RPC) on a small graph."""
+  import json
+  out = _run(['benchmarks/bench_dist_loader_cpu.py', 'ours', '--nodes', '20000', '--edges', '200000', '--workers', '1',
+              '--epochs', '2', '--train-frac', '0.2'], timeout=400)
+  line = json.loads([ln for ln in out.splitlines() if ln.startswith('{')][-1])
+  assert line['impl'] == 'ours' and line['best_epoch']['batches'] == 4 and line['best_epoch']['M_edges_per_s'] > 0
