@@ -165,9 +165,14 @@ def init_rpc(master_addr: str, master_port: int, num_rpc_threads: int = 16, rpc_
     ctx = get_context()
     if ctx is None:
       raise RuntimeError("distributed context is not set; call init_worker_group / init_server / init_client")
+    # TensorPipe channels for tensor payloads: multiplexed TCP + the basic fallback (the reference's choice,
+    # rpc.py:256-258); GLT_B200_RPC_CHANNELS overrides the list, e.g. "cma,mpt_uv,basic" lets peers on ONE machine
+    # move tensors with cross-memory attach (needs ptrace permission between the processes)
+    import os
+    channels = [c for c in os.environ.get('GLT_B200_RPC_CHANNELS', 'mpt_uv,basic').split(',') if c]
     opts = rpc.TensorPipeRpcBackendOptions(num_worker_threads=num_rpc_threads, rpc_timeout=rpc_timeout,
                                            init_method=f'tcp://{master_addr}:{master_port}',
-                                           _transports=['uv'], _channels=['mpt_uv', 'basic'])
+                                           _transports=['uv'], _channels=channels)
     if is_dynamic:
       rpc.init_rpc(name=ctx.worker_name, rank=ctx.global_rank, world_size=None, rpc_backend_options=opts)
     else:
