@@ -26,6 +26,6 @@ def _lazy(name):
 
 
 def __getattr__(name):
-  if name in ('channel', 'partition', 'distributed', 'parallel', 'models'):
+  if name in ('channel', 'partition', 'distributed', 'parallel', 'models', 'py_graphlearn_torch'):
     return _lazy(name)
   raise AttributeError(name)

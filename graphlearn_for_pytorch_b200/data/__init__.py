@@ -18,3 +18,12 @@ from .dataset import rebuild_dataset, reduce_dataset
 from .feature import rebuild_feature, reduce_feature
 from .graph import rebuild_graph, reduce_graph
 from .table_dataset import rebuild_table_dataset, reduce_table_dataset
+
+
+def __getattr__(name):
+  # `pywrap`: the native-module handle of the reference's Python layer (`from .. import py_graphlearn_torch as
+  # pywrap`); resolved on first use because the facade imports this sub-package
+  if name == 'pywrap':
+    import importlib
+    return importlib.import_module('..py_graphlearn_torch', __name__)
+  raise AttributeError(name)

@@ -14,8 +14,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'baseline', 'shims'))
 sys.path.insert(0, os.path.join(ROOT, 'baseline', '_ref'))
 
-# internals of the reference that have no public use here (native module handle, steps of its all2all exchange)
-KNOWN = {'data.pywrap', 'sampler.pywrap', 'distributed.DistFeature.communicate_node_feats',
+# internals of the reference that have no public use here (steps of its all2all exchange)
+KNOWN = {'distributed.DistFeature.communicate_node_feats',
          'distributed.DistFeature.communicate_node_id', 'distributed.DistFeature.remote_selecting_get_all2all',
          'distributed.DistFeature.remote_selecting_prepare'}
 SUBS = ['data', 'sampler', 'loader', 'channel', 'partition', 'distributed', 'utils', 'typing']
