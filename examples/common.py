@@ -83,3 +83,32 @@ def synthetic_mag(num_papers=30_000, num_authors=20_000, num_insts=500, num_fiel
   w = torch.randn(feat_dim, num_classes, generator=g)
   labels = {'paper': (feats['paper'] @ w).argmax(1)}
   return edges, feats, labels, sizes
+
+
+def add_dataset_args(parser, nodes=100_000, edges=2_000_000):
+  """--root / --dataset select an OGB directory on disk (parsed by glt.utils.load_ogb_node_dataset, no `ogb` package
+  needed); without --root a synthetic graph of --nodes / --edges is generated."""
+  parser.add_argument('--root', default=None, help='directory that contains e.g. ogbn_products/ (OGB raw layout)')
+  parser.add_argument('--dataset', default='ogbn-products')
+  parser.add_argument('--nodes', type=int, default=nodes)
+  parser.add_argument('--edges', type=int, default=edges)
+
+
+def load_homo(args, feat_dim=100, num_classes=47, undirected=True):
+  """-> (edge_index, x fp32, y int64, {'train' | 'valid' | 'test': indices}, num_nodes)."""
+  if getattr(args, 'root', None):
+    d = glt.utils.load_ogb_node_dataset(args.root, args.dataset)
+    ei, n = d['edge_index'], d['num_nodes']
+    if undirected:                                      # what T.ToUndirected / to_symmetric do in the reference scripts
+      ei = torch.cat([ei, ei.flip(0)], 1)
+    y = d['y'].to(torch.int64)
+    split = dict(d['split'])
+    if 'train' not in split:
+      perm = torch.randperm(n, generator=torch.Generator().manual_seed(0))
+      split = {'train': perm[: n // 10], 'valid': perm[n // 10: n // 10 + n // 50], 'test': perm[-(n // 50):]}
+    return ei, d['x'], y, split, n
+  ei, x, y = synthetic_homo(args.nodes, args.edges, feat_dim=feat_dim, num_classes=num_classes)
+  n = args.nodes
+  perm = torch.randperm(n, generator=torch.Generator().manual_seed(0))
+  n_tr, n_ev = n // 10, max(n // 50, 1)
+  return ei, x, y, {'train': perm[:n_tr], 'valid': perm[n_tr:n_tr + n_ev], 'test': perm[n_tr + n_ev:n_tr + 2 * n_ev]}, n

@@ -8,10 +8,12 @@ Counterpart of the reference's examples/distributed/dist_train_sage_supervised.p
 import argparse
 import os
 import sys
+import time
 
 import torch
 import torch.distributed as dist
 import torch.nn.functional as F
+from torch.distributed.algorithms.join import Join
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from common import glt  # noqa: E402
@@ -28,6 +30,8 @@ def main():
   p.add_argument('--master-port', type=int, default=29700)
   p.add_argument('--epochs', type=int, default=2)
   p.add_argument('--workers', type=int, default=0, help='0 = collocated sampling, >0 = sampling subprocesses')
+  p.add_argument('--eval-every', type=int, default=1, help='epochs between test-set evaluations (0 = never)')
+  p.add_argument('--batch', type=int, default=512)
   args = p.parse_args()
 
   cuda = torch.cuda.is_available()
@@ -41,23 +45,59 @@ def main():
           whole_node_label_file=os.path.join(args.root, 'labels.pt'), device=device.index)
   train = torch.load(os.path.join(args.root, 'train_idx.pt'))
   train = train[ds.node_pb[train] == args.rank]
-  if args.workers > 0:
-    opts = gd.MpDistSamplingWorkerOptions(num_workers=args.workers, worker_concurrency=4, master_addr=args.master_addr,
-                                          master_port=args.master_port + 1, pin_memory=cuda)
-  else:
-    opts = gd.CollocatedDistSamplingWorkerOptions(master_addr=args.master_addr, master_port=args.master_port + 1)
-  loader = gd.DistNeighborLoader(ds, [15, 10, 5], train, batch_size=512, shuffle=True, drop_last=False,
-                                 collect_features=True, to_device=device, worker_options=opts)
+
+  def worker_options(port):    # every loader has its own sampling-worker group, hence its own rendezvous port
+    if args.workers > 0:
+      return gd.MpDistSamplingWorkerOptions(num_workers=args.workers, worker_concurrency=4,
+                                            master_addr=args.master_addr, master_port=port, pin_memory=cuda)
+    return gd.CollocatedDistSamplingWorkerOptions(master_addr=args.master_addr, master_port=port)
+
+  loader = gd.DistNeighborLoader(ds, [15, 10, 5], train, batch_size=args.batch, shuffle=True, drop_last=False,
+                                 collect_features=True, to_device=device,
+                                 worker_options=worker_options(args.master_port + 1))
+  test_file = os.path.join(args.root, 'test_idx.pt')
+  test_loader = None
+  if args.eval_every > 0 and os.path.exists(test_file):
+    test = torch.load(test_file)
+    test = test[ds.node_pb[test] == args.rank]         # each rank scores the test seeds of its own partition
+    test_loader = gd.DistNeighborLoader(ds, [15, 10, 5], test, batch_size=args.batch, shuffle=False, drop_last=False,
+                                        collect_features=True, to_device=device,
+                                        worker_options=worker_options(args.master_port + 2))
   n_cls = int(ds.node_labels.max()) + 1
   model = torch.nn.parallel.DistributedDataParallel(GraphSAGE(ds.node_features.shape[1], 256, n_cls, 3).to(device))
   opt = torch.optim.Adam(model.parameters(), lr=3e-3)
+
+  @torch.no_grad()
+  def test_accuracy():
+    # reference examples/distributed/dist_train_sage_supervised.py:31-52: per-rank hits summed over the group.
+    # The un-wrapped module is used: ranks see different numbers of test batches, DDP forward hooks must not fire.
+    net = model.module
+    net.eval()
+    stat = torch.zeros(2, device=device)
+    for b in test_loader:
+      out = net(b.x, b.edge_index, b.num_sampled_nodes, b.num_sampled_edges)[:b.batch_size]
+      stat[0] += (out.argmax(1) == b.y[:b.batch_size]).sum()
+      stat[1] += b.batch_size
+    net.train()
+    dist.all_reduce(stat)
+    return float(stat[0] / stat[1].clamp(min=1)), int(stat[1])
+
   for epoch in range(args.epochs):
-    for b in loader:
-      out = model(b.x, b.edge_index, b.num_sampled_nodes, b.num_sampled_edges)[:b.batch_size]
-      loss = F.cross_entropy(out, b.y[:b.batch_size])
-      opt.zero_grad(); loss.backward(); opt.step()
-    print(f'[rank {args.rank}] epoch {epoch} loss {float(loss.detach()):.4f}')
+    t0 = time.time()
+    with Join([model]):                                 # partitions hold different numbers of training seeds
+      for b in loader:
+        out = model(b.x, b.edge_index, b.num_sampled_nodes, b.num_sampled_edges)[:b.batch_size]
+        loss = F.cross_entropy(out, b.y[:b.batch_size])
+        opt.zero_grad(); loss.backward(); opt.step()
+    print(f'[rank {args.rank}] epoch {epoch} loss {float(loss.detach()):.4f} time {time.time() - t0:.2f}s')
+    if test_loader is not None and (epoch + 1) % args.eval_every == 0:
+      dist.barrier()
+      acc, n = test_accuracy()
+      if args.rank == 0:
+        print(f'epoch {epoch} test acc {acc:.4f} ({n} nodes)')
   loader.shutdown()
+  if test_loader is not None:
+    test_loader.shutdown()
   dist.barrier()
   if gd.rpc_is_initialized():
     gd.barrier()

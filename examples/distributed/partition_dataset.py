@@ -8,24 +8,26 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from common import glt, synthetic_homo  # noqa: E402
+from common import add_dataset_args, glt, load_homo  # noqa: E402
 from graphlearn_for_pytorch_b200.partition import FrequencyPartitioner, RandomPartitioner  # noqa: E402
 from graphlearn_for_pytorch_b200.sampler import NeighborSampler, NodeSamplerInput  # noqa: E402
 
 p = argparse.ArgumentParser()
 p.add_argument('--out', required=True)
 p.add_argument('--parts', type=int, default=2)
-p.add_argument('--nodes', type=int, default=50_000)
-p.add_argument('--edges', type=int, default=500_000)
+add_dataset_args(p, nodes=50_000, edges=500_000)   # --root <dir with ogbn_products/>: partition the real dataset
 p.add_argument('--strategy', default='frequency', choices=['frequency', 'random'])
 p.add_argument('--cache-ratio', type=float, default=0.05)
 args = p.parse_args()
 
-ei, x, y = synthetic_homo(args.nodes, args.edges)
+ei, x, y, split, args.nodes = load_homo(args)
 os.makedirs(args.out, exist_ok=True)
 torch.save(y, os.path.join(args.out, 'labels.pt'))
-train = torch.randperm(args.nodes)[: args.nodes // 10]
+train = split['train']
 torch.save(train, os.path.join(args.out, 'train_idx.pt'))
+for name in ('valid', 'test'):                      # evaluation seeds travel with the partitions, as in the reference
+  if name in split:                                 # (examples/distributed/partition_ogbn_dataset.py:62-84)
+    torch.save(split[name], os.path.join(args.out, f'{name}_idx.pt'))
 if args.strategy == 'random':
   RandomPartitioner(args.out, args.parts, args.nodes, ei, node_feat=x).partition()
 else:

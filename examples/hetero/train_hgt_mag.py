@@ -19,13 +19,47 @@ from common import glt, synthetic_mag  # noqa: E402
 from graphlearn_for_pytorch_b200.models import HGT  # noqa: E402
 
 
+def load_mag_from_disk(root, name='ogbn-mag'):
+  """ogbn-mag from its OGB directory: reverse relations are added (what T.ToUndirected(merge=True) does in the
+  reference script) and node types that ship without features get the mean of their featured neighbours' rows,
+  propagated until every type has some (author <- papers written, institution <- authors, field <- papers); the
+  reference substitutes pre-trained metapath2vec vectors there (examples/hetero/train_hgt_mag.py:33-36)."""
+  d = glt.utils.load_ogb_hetero_dataset(root, name)
+  edges = dict(d['edge_index'])
+  for (s, r, t), ei in list(edges.items()):
+    if s == t:
+      edges[(s, r, t)] = torch.cat([ei, ei.flip(0)], 1)
+    elif (t, f'rev_{r}', s) not in edges:
+      edges[(t, f'rev_{r}', s)] = ei.flip(0)
+  sizes, feats = dict(d['num_nodes']), dict(d['x'])
+  while len(feats) < len(sizes):
+    progressed = False
+    for (s, r, t), ei in edges.items():
+      if s in feats and t not in feats:
+        acc = torch.zeros(sizes[t], feats[s].shape[1]).index_add_(0, ei[1], feats[s][ei[0]])
+        deg = torch.zeros(sizes[t]).index_add_(0, ei[1], torch.ones(ei.shape[1]))
+        feats[t] = acc / deg.clamp(min=1).unsqueeze(1)
+        progressed = True
+    if not progressed:
+      raise ValueError(f'node types without features and without a featured neighbour type: '
+                       f'{sorted(set(sizes) - set(feats))}')
+  labels = {t: v.to(torch.int64) for t, v in d['y'].items()}
+  return edges, feats, labels, sizes, d['split']
+
+
 def build_dataset(args, cuda, device_index=0):
-  edges, feats, labels, sizes = synthetic_mag(args.papers)
+  split = None
+  if getattr(args, 'root', None):
+    edges, feats, labels, sizes, split = load_mag_from_disk(args.root, args.dataset)
+  else:
+    edges, feats, labels, sizes = synthetic_mag(args.papers)
   ds = glt.data.Dataset()
   ds.init_graph(edges, graph_mode=('ZERO_COPY' if args.zero_copy else 'CUDA') if cuda else 'CPU', num_nodes=sizes,
                 device=device_index)
   ds.init_node_features(feats, split_ratio=args.split_ratio if cuda else 0.0, with_gpu=cuda, device=device_index)
   ds.init_node_labels(labels)
+  if split and 'train' in split and 'paper' in split['train']:
+    return ds, sizes, labels, split['train']['paper'], split.get('valid', split['train'])['paper']
   n = sizes['paper']
   perm = torch.randperm(n, generator=torch.Generator().manual_seed(1))
   return ds, sizes, labels, perm[: n // 2], perm[n // 2: n // 2 + n // 10]
@@ -33,7 +67,8 @@ def build_dataset(args, cuda, device_index=0):
 
 def make_model(ds, sizes, labels, loader, args, device):
   first = next(iter(loader))
-  return HGT(list(sizes.keys()), list(first.edge_index_dict.keys()), 128, args.hidden, int(labels['paper'].max()) + 1,
+  in_dim = ds.node_features['paper'].shape[1]
+  return HGT(list(sizes.keys()), list(first.edge_index_dict.keys()), in_dim, args.hidden, int(labels['paper'].max()) + 1,
              num_layers=2, heads=args.heads, node_type='paper').to(device)
 
 
@@ -62,6 +97,8 @@ def evaluate(model, loader, device):
 
 def parse():
   p = argparse.ArgumentParser()
+  p.add_argument('--root', default=None, help='directory that contains ogbn_mag/ (OGB raw layout); default: synthetic')
+  p.add_argument('--dataset', default='ogbn-mag')
   p.add_argument('--papers', type=int, default=30_000)
   p.add_argument('--epochs', type=int, default=3)
   p.add_argument('--batch', type=int, default=1024)

@@ -11,13 +11,12 @@ import time
 import torch
 import torch.nn.functional as F
 
-from common import glt, synthetic_homo
+from common import add_dataset_args, glt, load_homo
 from graphlearn_for_pytorch_b200.models import GraphSAGE, GraphSageEngine
 
 p = argparse.ArgumentParser()
 p.add_argument('--mode', default='loader', choices=['loader', 'engine'])
-p.add_argument('--nodes', type=int, default=100_000)
-p.add_argument('--edges', type=int, default=2_000_000)
+add_dataset_args(p)        # --root <dir with ogbn_products/> --dataset ogbn-products, or synthetic --nodes / --edges
 p.add_argument('--epochs', type=int, default=2)
 p.add_argument('--batch', type=int, default=1024)
 p.add_argument('--dropout', type=float, default=0.5, help='hidden-layer dropout (engine mode and loader-mode model)')
@@ -26,9 +25,10 @@ args = p.parse_args()
 
 cuda = torch.cuda.is_available()
 device = torch.device('cuda', 0) if cuda else torch.device('cpu')
-ei, x, y = synthetic_homo(args.nodes, args.edges)     # <- replace with the real ogbn-products tensors
+ei, x, y, split, num_nodes = load_homo(args)
+args.nodes = num_nodes
 n_cls = int(y.max()) + 1
-train_idx = torch.randperm(args.nodes)[: args.nodes // 10]
+train_idx = split['train']
 
 if args.mode == 'loader':
   ds = glt.data.Dataset()
@@ -39,6 +39,18 @@ if args.mode == 'loader':
                                      drop_last=True, device=device)
   model = GraphSAGE(x.shape[1], 256, n_cls, num_layers=3, dropout=args.dropout).to(device)
   opt = torch.optim.Adam(model.parameters(), lr=3e-3)
+
+  @torch.no_grad()
+  def accuracy(idx):
+    # reference examples/train_sage_ogbn_products.py:62-75: a second loader over the evaluation split
+    model.eval()
+    hit = tot_n = 0
+    for b in glt.loader.NeighborLoader(ds, [15, 10, 5], idx, batch_size=args.batch, shuffle=False, device=device):
+      out = model(b.x, b.edge_index, b.num_sampled_nodes, b.num_sampled_edges)[:b.batch_size]
+      hit += int((out.argmax(1) == b.y[:b.batch_size].to(device)).sum()); tot_n += b.batch_size
+    model.train()
+    return hit / max(tot_n, 1)
+
   for epoch in range(args.epochs):
     t0, tot, correct, seen = time.time(), 0.0, 0, 0
     for b in loader:
@@ -48,6 +60,7 @@ if args.mode == 'loader':
       opt.zero_grad(); loss.backward(); opt.step()
       tot += float(loss.detach()); correct += int((out.argmax(1) == tgt).sum()); seen += b.batch_size
     print(f'epoch {epoch}: loss {tot / len(loader):.4f} acc {correct / seen:.4f} time {time.time() - t0:.2f}s')
+  print(f"valid acc {accuracy(split['valid']):.4f}  test acc {accuracy(split['test']):.4f}")
 elif not cuda:
   # no GPU: the same step-level loop on the device-agnostic trainer (sampler + eager GraphSAGE + torch Adam)
   from graphlearn_for_pytorch_b200.models import GraphSageTrainer
@@ -89,3 +102,9 @@ else:
     l, c, n = eng.evaluate_batch(train_idx[:args.batch].to(device))
     print(f'epoch {epoch}: loss {sum(losses) / max(len(losses), 1):.4f} eval-acc {c / n:.4f} '
           f'time {time.time() - t0:.2f}s ({perm.numel() / (time.time() - t0):.0f} seeds/s)')
+  hit = tot_n = 0
+  test_idx = split['test'].to(device)
+  for i in range(0, test_idx.numel() - args.batch + 1, args.batch):
+    _, c, n = eng.evaluate_batch(test_idx[i:i + args.batch])
+    hit += c; tot_n += n
+  print(f'test acc {hit / max(tot_n, 1):.4f} ({tot_n} nodes)')

@@ -51,6 +51,8 @@ class ConcurrentEventLoop(object):
     if self._loop.is_running():
       self._loop.call_soon_threadsafe(self._loop.stop)
       self._thread.join(timeout=5)
+    if not self._loop.is_running() and not self._loop.is_closed():
+      self._loop.close()                       # releases the selector + self-pipe (else a ResourceWarning at exit)
 
   def wait_all(self, raise_errors: bool = True):
     """Block until every submitted task finished; re-raise the first task error."""

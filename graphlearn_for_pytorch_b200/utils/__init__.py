@@ -1,7 +1,8 @@
 """Utilities: every public name of the sub-modules is re-exported here (`glt.utils.get_free_port`, ...)."""
 import importlib
 
-_SUBMODULES = ('tensor', 'common', 'device', 'units', 'exit_status', 'mixin', 'singleton', 'topo', 'synthetic', 'tracing')
+_SUBMODULES = ('tensor', 'common', 'device', 'units', 'exit_status', 'mixin', 'singleton', 'topo', 'synthetic', 'tracing',
+               'ogb_io')
 
 for _name in _SUBMODULES:
   _mod = importlib.import_module(f'{__name__}.{_name}')

@@ -102,6 +102,7 @@ def test_distributed_examples_and_benchmark(tmp_path):
   outs = _run_ranks([['examples/distributed/dist_train_sage.py', '--root', parts, '--rank', str(r), '--world', '2',
                       '--epochs', '1', '--workers', '1', '--master-port', str(port)] for r in (0, 1)])
   assert all('epoch 0 loss' in o for o in outs.values())
+  assert 'epoch 0 test acc' in outs[0]                  # second (test) loader, hits all-reduced over the ranks
   port = get_free_port()
   outs = _run_ranks([['benchmarks/bench_dist_neighbor_loader.py', '--root', parts, '--rank', str(r), '--world', '2',
                       '--epochs', '1', '--workers', '1', '--master-port', str(port)] for r in (0, 1)])
