@@ -152,3 +152,43 @@ def test_cuda_classes():
     [torch.tensor([1, 2, 3], device=dev), torch.tensor([9], device=dev)],
     [torch.tensor([2, 1], device=dev), torch.tensor([1], device=dev)], [])
   assert nb.tolist() == [1, 2, 9, 3] and nn.tolist() == [2, 1, 1]
+
+
+def test_inducer_matches_the_reference_native_contract():
+  """Inputs and expected outputs of the reference's own native test (test/cpp/test_inducer.cu:56-100): first-seen
+  numbering, only unseen nodes reported per hop, one source entry per neighbour-count entry."""
+  srcs1, nbrs1, num1 = torch.tensor([0, 1, 2, 2, 3]), torch.tensor([1, 2, 2, 3, 4, 5, 4, 5, 1]), torch.tensor([2, 2, 2, 2, 1])
+  srcs2, nbrs2, num2 = torch.tensor([0, 1, 2, 3, 4, 5]), torch.tensor([1, 7, 2, 3, 4, 6, 7]), torch.tensor([1, 1, 1, 2, 1, 1])
+  ind = pywrap.CPUInducer(srcs1.numel() + nbrs1.numel() + srcs2.numel() + nbrs2.numel())
+  assert ind.init_node(srcs1).tolist() == [0, 1, 2, 3]
+  nodes, rows, cols = ind.induce_next(srcs1, nbrs1, num1)
+  assert (nodes.tolist(), rows.tolist(), cols.tolist()) == \
+      ([4, 5], [0, 0, 1, 1, 2, 2, 2, 2, 3], [1, 2, 2, 3, 4, 5, 4, 5, 1])
+  nodes, rows, cols = ind.induce_next(srcs2, nbrs2, num2)
+  assert (nodes.tolist(), rows.tolist(), cols.tolist()) == ([7, 6], [0, 1, 2, 3, 3, 4, 5], [1, 6, 2, 3, 4, 7, 6])
+
+
+def test_hetero_inducer_matches_the_reference_native_contract():
+  """test/cpp/test_hetero_inducer.cu:30-80 (meta-path a -> b, a -> c)."""
+  hi = pywrap.CPUHeteroInducer({'a': 10, 'b': 10, 'c': 10})
+  assert hi.init_node({'a': torch.tensor([0, 1, 2, 2, 3])})['a'].tolist() == [0, 1, 2, 3]
+  a2b, a2c = ('a', 'a2b', 'b'), ('a', 'a2c', 'c')
+  nodes, rows, cols = hi.induce_next({
+    a2b: (torch.tensor([0, 1, 2, 2, 3]), torch.tensor([1, 2, 2, 3, 4, 5, 4, 5, 1]), torch.tensor([2, 2, 2, 2, 1])),
+    a2c: (torch.tensor([2, 1, 3, 2, 3]), torch.tensor([3, 5, 2, 3, 4, 3, 1, 2, 1]), torch.tensor([1, 2, 2, 3, 1]))})
+  assert nodes['b'].tolist() == [1, 2, 3, 4, 5] and nodes['c'].tolist() == [3, 5, 2, 4, 1] and 'a' not in nodes
+  assert rows[a2b].tolist() == [0, 0, 1, 1, 2, 2, 2, 2, 3] and cols[a2b].tolist() == [0, 1, 1, 2, 3, 4, 3, 4, 0]
+  assert rows[a2c].tolist() == [2, 1, 1, 3, 3, 2, 2, 2, 3] and cols[a2c].tolist() == [0, 1, 2, 0, 3, 0, 4, 2, 4]
+
+
+def test_stitch_matches_the_reference_native_contract():
+  """test/cpp/test_stitch_sample_results.cu:26-60: three partitions answer for interleaved positions of six seeds."""
+  T = torch.tensor
+  nbrs, num, eids = pywrap.cpu_stitch_sample_results(
+    T([1, 2, 3, 4, 5, 6]), [T([0, 2]), T([1, 5]), T([3, 4])],
+    [T([4, 5]), T([3, 7, 8, 9, 10, 11]), T([5, 6, 7, 6, 7, 8, 9])],
+    [T([0, 2]), T([1, 5]), T([3, 4])],
+    [T([1, 2]), T([0, 10, 11, 12, 13, 14]), T([3, 4, 5, 6, 7, 8, 9])])
+  assert num.tolist() == [0, 1, 2, 3, 4, 5]
+  assert nbrs.tolist() == [3, 4, 5, 5, 6, 7, 6, 7, 8, 9, 7, 8, 9, 10, 11]
+  assert eids.tolist() == [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14]
