@@ -62,15 +62,16 @@ class HGTConv(nn.Module):
       n = x.shape[0]
       if t in per_dst:
         dst = torch.cat([p[0] for p in per_dst[t]])
-        score = torch.cat([p[1] for p in per_dst[t]])
+        score = torch.cat([p[1] for p in per_dst[t]]).float()     # fp32 softmax / weighted sum also under autocast
         msg = torch.cat([p[2] for p in per_dst[t]])
         mx = torch.full((n, H), -1e30, dtype=score.dtype, device=score.device)
         mx = mx.scatter_reduce(0, dst.unsqueeze(1).expand(-1, H), score, reduce='amax')
         e = torch.exp(score - mx[dst])
         den = torch.zeros(n, H, dtype=e.dtype, device=e.device).index_add_(0, dst, e)
         w = e / den[dst].clamp(min=1e-16)
-        agg = torch.zeros(n, H, D, dtype=msg.dtype, device=msg.device).index_add_(0, dst, msg * w.unsqueeze(-1))
-        h = self.a[t](F.gelu(agg.reshape(n, H * D)))
+        agg = torch.zeros(n, H, D, dtype=torch.float32, device=msg.device).index_add_(0, dst,
+                                                                                      msg.float() * w.unsqueeze(-1))
+        h = self.a[t](F.gelu(agg.reshape(n, H * D).to(msg.dtype)))
       else:
         h = torch.zeros(n, H * D, dtype=x.dtype, device=x.device)
       alpha = torch.sigmoid(self.skip[t])

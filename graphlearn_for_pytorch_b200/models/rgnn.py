@@ -17,12 +17,13 @@ EdgeType = Tuple[str, str, str]
 def _segment_mean(src_feat: torch.Tensor, dst_index: torch.Tensor, n_dst: int) -> torch.Tensor:
   out = torch.zeros(n_dst, src_feat.shape[1], dtype=src_feat.dtype, device=src_feat.device)
   out.index_add_(0, dst_index, src_feat)
+  # degrees are counted in fp32: bf16 holds integers exactly only up to 256
   if dst_index.is_cuda:   # bincount synchronises with the host on CUDA (it needs max()); index_add does not
-    deg = torch.zeros(n_dst, dtype=src_feat.dtype, device=src_feat.device)
-    deg.index_add_(0, dst_index, torch.ones_like(dst_index, dtype=src_feat.dtype))
+    deg = torch.zeros(n_dst, dtype=torch.float32, device=src_feat.device)
+    deg.index_add_(0, dst_index, torch.ones_like(dst_index, dtype=torch.float32))
   else:
-    deg = torch.bincount(dst_index, minlength=n_dst).to(src_feat.dtype)
-  return out / deg.clamp(min=1).unsqueeze(1)
+    deg = torch.bincount(dst_index, minlength=n_dst).to(torch.float32)
+  return out * (1.0 / deg.clamp(min=1)).to(out.dtype).unsqueeze(1)
 
 
 class RelSAGEConv(nn.Module):
@@ -76,15 +77,17 @@ class RelGATConv(nn.Module):
     hs = self.lin_src(x_src).view(-1, self.h, self.c)
     hd = self.lin_dst(x_dst).view(-1, self.h, self.c)
     a = (hs * self.att_src).sum(-1)[edge_index[0]] + (hd * self.att_dst).sum(-1)[edge_index[1]]
-    a = F.leaky_relu(a, 0.2)
+    # scores, softmax and the weighted sum run in fp32 whatever the activations' dtype is (bf16 under autocast):
+    # the index_add_ operands then agree and the normalisation keeps its precision
+    a = F.leaky_relu(a, 0.2).float()
     amax = torch.full((n_dst, self.h), -1e30, dtype=a.dtype, device=a.device)
     amax = amax.scatter_reduce(0, edge_index[1].unsqueeze(1).expand(-1, self.h), a, reduce='amax')
     e = torch.exp(a - amax[edge_index[1]])
     denom = torch.zeros(n_dst, self.h, dtype=a.dtype, device=a.device).index_add_(0, edge_index[1], e)
     w = e / denom[edge_index[1]].clamp(min=1e-16)
-    out = torch.zeros(n_dst, self.h, self.c, dtype=hs.dtype, device=hs.device)
-    out.index_add_(0, edge_index[1], hs[edge_index[0]] * w.unsqueeze(-1))
-    return out.reshape(n_dst, -1) + self.bias
+    out = torch.zeros(n_dst, self.h, self.c, dtype=torch.float32, device=hs.device)
+    out.index_add_(0, edge_index[1], hs[edge_index[0]].float() * w.unsqueeze(-1))
+    return out.reshape(n_dst, -1).to(hs.dtype) + self.bias
 
 
 _CONVS = {'rsage': RelSAGEConv, 'rgcn': RelGCNConv, 'rgat': RelGATConv}

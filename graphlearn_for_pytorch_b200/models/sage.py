@@ -42,9 +42,9 @@ class SAGEConv(nn.Module):
     src, dst = edge_index[0], edge_index[1]
     agg = torch.zeros(n_dst, x_src.shape[1], dtype=x_src.dtype, device=x_src.device)
     agg.index_add_(0, dst, x_src[src])
-    deg = torch.zeros(n_dst, dtype=x_src.dtype, device=x_src.device)
-    deg.index_add_(0, dst, torch.ones_like(dst, dtype=x_src.dtype))
-    agg = agg / deg.clamp(min=1).unsqueeze(1)
+    deg = torch.zeros(n_dst, dtype=torch.float32, device=x_src.device)       # fp32: bf16 counts exactly only to 256
+    deg.index_add_(0, dst, torch.ones_like(dst, dtype=torch.float32))
+    agg = agg * (1.0 / deg.clamp(min=1)).to(agg.dtype).unsqueeze(1)
     return self.lin_l(agg) + self.lin_r(x_dst)
 
 

@@ -44,12 +44,15 @@ def test_igbh_pipeline_single_and_distributed(tmp_path):
 
   def rank(r):
     outs[r] = _run(['examples/igbh/dist_train_rgnn.py', '--path', parts, '--rank', str(r), '--world', '2',
-                    '--fan_out', '4,4', '--epochs', '1', '--max_steps', '4', '--batch_size', '128',
-                    '--master_port', str(port)], timeout=500)
+                    '--fan_out', '4,4', '--epochs', '1', '--batch_size', '128', '--master_port', str(port),
+                    # MLPerf-run options of the reference script: in-epoch validation, bf16 autocast, seed
+                    '--validation_frac_within_epoch', '0.5', '--precision', 'bf16', '--random_seed', '3',
+                    '--num_heads', '2', '--validation_acc', '0.99'], timeout=500)
   th = [threading.Thread(target=rank, args=(r,)) for r in (0, 1)]
   [t.start() for t in th]
   [t.join() for t in th]
   assert 'val-acc' in outs.get(0, '') and 'RUN_STOP' in outs.get(0, '')
+  assert 'epoch 0 step' in outs[0]                      # the in-epoch validation ran
 
 
 def test_table_examples_single_and_distributed(tmp_path):

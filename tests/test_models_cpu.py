@@ -53,6 +53,26 @@ def test_rgnn_variants_on_hetero_batches():
     out.sum().backward()
     out_t = model(b.x_dict, b.edge_index_dict, b.num_sampled_nodes, b.num_sampled_edges)
     assert out_t.shape[1] == 2 and out_t.shape[0] >= b['user'].batch_size
+    # bf16 autocast (the --precision bf16 recipe of the IGBH trainers): attention softmax / weighted sums and the
+    # degree counts stay in fp32 inside the layers, results agree with the fp32 forward to bf16 accuracy
+    model.eval()
+    with torch.no_grad():
+      ref = model(b.x_dict, b.edge_index_dict)
+      with torch.autocast('cpu', dtype=torch.bfloat16):
+        low = model(b.x_dict, b.edge_index_dict)
+    assert torch.allclose(low.float(), ref, atol=0.1, rtol=0.1), (kind, (low.float() - ref).abs().max())
+  hgt = HGT(['user', 'item'], etypes, 8, 16, 2, num_layers=2, heads=2, node_type='user').eval()
+  with torch.no_grad():
+    ref = hgt(b.x_dict, b.edge_index_dict)
+    with torch.autocast('cpu', dtype=torch.bfloat16):
+      low = hgt(b.x_dict, b.edge_index_dict)
+  assert torch.allclose(low.float(), ref, atol=0.1, rtol=0.1)
+  # degree counts beyond bf16's exact-integer range (256): a 600-neighbour mean of bf16 rows still divides by 600
+  from graphlearn_for_pytorch_b200.models.rgnn import _segment_mean
+  rows = torch.zeros(600, 4, dtype=torch.bfloat16)
+  rows[0] = 600.0
+  m = _segment_mean(rows, torch.zeros(600, dtype=torch.int64), 1)
+  assert m.dtype == torch.bfloat16 and abs(float(m[0, 0]) - 1.0) < 0.02
 
 
 def test_drnl_and_dgcnn():
