@@ -170,6 +170,9 @@ def main(args, baseline_samples_per_s, canonical_config, metric):
 
     def timed(read_loss):
       blocks = []
+      sampler = getattr(args, '_clock_sampler', None)
+      if sampler is not None:
+        sampler.gate.set()               # SM-clock samples are taken inside the timed regions only
       while True:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier(); e0.record()
@@ -179,6 +182,8 @@ def main(args, baseline_samples_per_s, canonical_config, metric):
         blocks.append(max_ranks(e0.elapsed_time(e1)))
         if sum(blocks) >= min_time * 1e3 or len(blocks) >= 2000:
           break
+      if sampler is not None:
+        sampler.gate.clear()
       tot = sum(blocks)
       return {'ms_per_step': tot / (len(blocks) * K), 'blocks': len(blocks), 'steps_total': len(blocks) * K,
               'seconds': tot / 1e3, 'first_block_ms_per_step': blocks[0] / K,
@@ -242,6 +247,7 @@ def main(args, baseline_samples_per_s, canonical_config, metric):
       'e2e': {'value': per_step / (e2e_t['ms_per_step'] / 1e3), 'unit': 'samples/s', 'ms_per_step': e2e_t['ms_per_step'],
               'h2d_bytes_per_step': bs * 8, 'd2h_bytes_per_step': 4, 'timed': e2e_t},
       'arms': arms,
+      'clocks': args._clock_sampler.summary() if getattr(args, '_clock_sampler', None) is not None else None,
     }), flush=True)
   if world > 1:
     dist.destroy_process_group()

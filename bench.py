@@ -159,6 +159,8 @@ class ClockSampler(threading.Thread):
     self.samples = []          # (sm_mhz, reasons bitmask)
     self.sm_max = None
     self._stop_evt = threading.Event()
+    self.gate = threading.Event()      # samples are kept only while set (the reference arm opens it around its timed
+    self.gate.set()                    # regions; this arm samples from start() to stop())
 
   def run(self):
     try:
@@ -169,7 +171,8 @@ class ClockSampler(threading.Thread):
       get_reasons = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or \
           nv.nvmlDeviceGetCurrentClocksThrottleReasons
       while not self._stop_evt.is_set():
-        self.samples.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(get_reasons(h))))
+        if self.gate.is_set():
+          self.samples.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(get_reasons(h))))
         time.sleep(0.001)
     except Exception:
       self._smi_fallback()
@@ -178,6 +181,9 @@ class ClockSampler(threading.Thread):
     q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
     while not self._stop_evt.is_set():
+      if not self.gate.is_set():
+        time.sleep(0.01)
+        continue
       try:
         out = subprocess.run(['nvidia-smi', f'--query-gpu={q}', '--format=csv,noheader,nounits', '-i',
                               str(self.gpu_index)], capture_output=True, text=True, timeout=5).stdout
@@ -621,6 +627,13 @@ def run_reference(args):
   try:
     sys.path.insert(0, os.path.join(ROOT, 'baseline'))
     import ref_bench
+    try:       # SM clocks / throttle reasons of the reference arm's timed regions (same sampler as this arm's)
+      clocks = ClockSampler(int(os.environ.get('LOCAL_RANK', '0')))
+      clocks.gate.clear()
+      clocks.start()
+      args._clock_sampler = clocks
+    except Exception:
+      args._clock_sampler = None
     ref_bench.main(args, BASELINE_SAMPLES_PER_S, canonical_config(args, int(os.environ.get('WORLD_SIZE', '1'))), metric_name(args))
   except Exception as e:  # the reference arm must never break the driver
     if int(os.environ.get('RANK', '0')) == 0:
