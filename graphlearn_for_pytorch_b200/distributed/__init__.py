@@ -3,7 +3,10 @@ from .dist_context import DistRole, DistContext, get_context, init_worker_group
 from .dist_dataset import DistDataset
 from .dist_feature import PartialFeature, DistFeature
 from .dist_graph import DistGraph
-from .dist_loader import DistLoader, DistNeighborLoader, DistLinkNeighborLoader, DistSubGraphLoader
+from .dist_loader import DistLoader
+from .dist_neighbor_loader import DistNeighborLoader
+from .dist_link_neighbor_loader import DistLinkNeighborLoader
+from .dist_subgraph_loader import DistSubGraphLoader
 from .dist_neighbor_sampler import DistNeighborSampler
 from .dist_options import (CollocatedDistSamplingWorkerOptions, MpDistSamplingWorkerOptions,
                            RemoteDistSamplingWorkerOptions)
@@ -16,5 +19,3 @@ from .rpc import (init_rpc, shutdown_rpc, rpc_is_initialized, get_rpc_master_add
                   all_gather, barrier, global_all_gather, global_barrier, RpcDataPartitionRouter,
                   rpc_sync_data_partitions, RpcCalleeBase, rpc_register, rpc_request_async, rpc_request,
                   rpc_global_request_async, rpc_global_request)
-# module-path aliases of the loader classes, importable as attributes like in the reference package
-from . import dist_link_neighbor_loader, dist_neighbor_loader, dist_subgraph_loader  # noqa: E402,F401

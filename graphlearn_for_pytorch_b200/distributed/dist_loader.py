@@ -1,21 +1,18 @@
-"""DistLoader and its neighbour / link / subgraph flavours.
+"""DistLoader: the base of the distributed loaders (`dist_neighbor_loader.py`, `dist_link_neighbor_loader.py`,
+`dist_subgraph_loader.py`).
 
-Parity: reference python/distributed/dist_loader.py:46-451, dist_neighbor_loader.py:29-118,
-dist_link_neighbor_loader.py, dist_subgraph_loader.py:28-94.  A loader owns (a) a sampling
+Parity: reference python/distributed/dist_loader.py:46-451.  A loader owns (a) a sampling
 producer chosen by the worker options (collocated / multiprocess / remote server) and
 (b) the message -> Data/HeteroData collation.
 """
-from typing import Optional, Union
+from typing import Optional
 
 import torch
 
 from ..channel import QueueTimeoutError, RemoteReceivingChannel, SampleMessage, ShmChannel
-from ..loader.data import Data, HeteroData
 from ..loader.transform import to_data, to_hetero_data
-from ..loader.link_loader import get_edge_label_index
-from ..sampler import (EdgeSamplerInput, HeteroSamplerOutput, NegativeSampling, NodeSamplerInput,
-                       RemoteSamplerInput, SamplerOutput, SamplingConfig, SamplingType)
-from ..typing import EdgeType, NodeType, Split, from_str, reverse_edge_type
+from ..sampler import HeteroSamplerOutput, SamplerOutput, SamplingConfig
+from ..typing import from_str
 from ..utils.exit_status import is_python_exiting
 from .dist_context import get_context
 from .dist_dataset import DistDataset
@@ -231,70 +228,11 @@ def _loader_repr(self) -> str:
 DistLoader.__repr__ = _loader_repr
 
 
-class DistNeighborLoader(DistLoader):
-  """Distributed NeighborLoader (node seeds).  `input_nodes`: tensor, (ntype, tensor), or in
-  remote mode a Split / path(s) resolved on the server."""
-
-  def __init__(self, data: Optional[DistDataset], num_neighbors, input_nodes, batch_size: int = 1,
-               shuffle: bool = False, drop_last: bool = False, with_edge: bool = False,
-               with_weight: bool = False, edge_dir: str = 'out', collect_features: bool = False,
-               to_device: Optional[torch.device] = None, random_seed: Optional[int] = None,
-               worker_options: Optional[AllDistSamplingWorkerOptions] = None):
-    if isinstance(input_nodes, tuple):
-      input_type, seeds = input_nodes
-    else:
-      input_type, seeds = None, input_nodes
-    from ..sampler import RemoteNodePathSamplerInput, RemoteNodeSplitSamplerInput
-    if isinstance(seeds, Split):
-      input_data = RemoteNodeSplitSamplerInput(seeds, input_type)
-    elif isinstance(seeds, str):
-      input_data = RemoteNodePathSamplerInput(seeds, input_type)
-    elif isinstance(seeds, list) and seeds and isinstance(seeds[0], str):
-      input_data = [RemoteNodePathSamplerInput(p, input_type) for p in seeds]
-    elif isinstance(seeds, RemoteSamplerInput) or (isinstance(seeds, list) and seeds and
-                                                   isinstance(seeds[0], RemoteSamplerInput)):
-      input_data = seeds
-    else:
-      input_data = NodeSamplerInput(node=torch.as_tensor(seeds), input_type=input_type)
-    cfg = SamplingConfig(SamplingType.NODE, num_neighbors, batch_size, shuffle, drop_last, with_edge,
-                         collect_features, False, with_weight, edge_dir, random_seed)
-    super().__init__(data, input_data, cfg, to_device, worker_options)
-
-
-class DistLinkNeighborLoader(DistLoader):
-  """Distributed LinkNeighborLoader (link seeds + negatives)."""
-
-  def __init__(self, data: Optional[DistDataset], num_neighbors, batch_size: int = 1, edge_label_index=None,
-               edge_label: Optional[torch.Tensor] = None, neg_sampling: Optional[NegativeSampling] = None,
-               shuffle: bool = False, drop_last: bool = False, with_edge: bool = False,
-               with_weight: bool = False, edge_dir: str = 'out', collect_features: bool = False,
-               to_device: Optional[torch.device] = None, random_seed: Optional[int] = None,
-               worker_options: Optional[AllDistSamplingWorkerOptions] = None):
-    edge_type, ei = get_edge_label_index(data, edge_label_index)
-    neg_sampling = NegativeSampling.cast(neg_sampling)
-    if neg_sampling is not None and neg_sampling.is_binary() and edge_label is not None and \
-        edge_label.dtype in (torch.int32, torch.int64):
-      edge_label = edge_label + 1
-    input_data = EdgeSamplerInput(row=ei[0].clone(), col=ei[1].clone(), label=edge_label, input_type=edge_type,
-                                  neg_sampling=neg_sampling)
-    cfg = SamplingConfig(SamplingType.LINK, num_neighbors, batch_size, shuffle, drop_last, with_edge,
-                         collect_features, neg_sampling is not None, with_weight, edge_dir, random_seed)
-    super().__init__(data, input_data, cfg, to_device, worker_options)
-
-
-class DistSubGraphLoader(DistLoader):
-  """Distributed SubGraphLoader (induced enclosing subgraphs)."""
-
-  def __init__(self, data: Optional[DistDataset], input_nodes, num_neighbors=None, batch_size: int = 1,
-               shuffle: bool = False, drop_last: bool = False, with_edge: bool = False,
-               with_weight: bool = False, edge_dir: str = 'out',
-               collect_features: bool = False, to_device: Optional[torch.device] = None,
-               random_seed: Optional[int] = None, worker_options: Optional[AllDistSamplingWorkerOptions] = None):
-    if isinstance(input_nodes, tuple):
-      input_type, seeds = input_nodes
-    else:
-      input_type, seeds = None, input_nodes
-    input_data = NodeSamplerInput(node=torch.as_tensor(seeds), input_type=input_type)
-    cfg = SamplingConfig(SamplingType.SUBGRAPH, num_neighbors, batch_size, shuffle, drop_last, with_edge,
-                         collect_features, False, with_weight, edge_dir, random_seed)
-    super().__init__(data, input_data, cfg, to_device, worker_options)
+def __getattr__(name):
+  # the three flavours lived in this module before they moved next to their reference counterparts
+  import importlib
+  home = {'DistNeighborLoader': 'dist_neighbor_loader', 'DistLinkNeighborLoader': 'dist_link_neighbor_loader',
+          'DistSubGraphLoader': 'dist_subgraph_loader'}.get(name)
+  if home is None:
+    raise AttributeError(name)
+  return getattr(importlib.import_module(f'{__package__}.{home}'), name)
