@@ -132,6 +132,20 @@ def save_feature_partition_cache(output_dir: str, partition_idx: int, feature_pa
     torch.save(feature_partition.cache_ids, os.path.join(d, 'cache_ids.pt'))
 
 
+def _for_each_part(fn, num_parts: int):
+  """Run fn(p) for every partition on a few threads: each partition owns its files, and the row gathers, the
+  serialisation memcpys and the file writes all release the GIL, so the writers overlap."""
+  workers = min(num_parts, max(1, (os.cpu_count() or 2) // 2), 8)
+  if workers <= 1:
+    for p in range(num_parts):
+      fn(p)
+    return
+  from concurrent.futures import ThreadPoolExecutor
+  with ThreadPoolExecutor(workers) as pool:
+    for f in [pool.submit(fn, p) for p in range(num_parts)]:
+      f.result()                      # re-raises a writer's exception
+
+
 # ----------------------------------------------------------------------------- partitioner
 class PartitionerBase(ABC):
   """Splits nodes, then edges (by source or destination owner), then features; writes the
@@ -219,7 +233,7 @@ class PartitionerBase(ABC):
 
   # ---- features
   def _save_feats(self, feat, ids_per_part, cache_ids, group, t):
-    for p in range(self.num_parts):
+    def save_part(p):
       d = _feat_dir(self.output_dir, p, group, t)
       for name in ('feats.pkl', 'ids.pkl'):
         if os.path.exists(os.path.join(d, name)):
@@ -234,6 +248,7 @@ class PartitionerBase(ABC):
       if cache_ids is not None and cache_ids[p] is not None and cache_ids[p].numel() > 0:
         save_feature_partition_cache(self.output_dir, p,
                                      FeaturePartitionData(None, None, feat[cache_ids[p]], cache_ids[p]), group, t)
+    _for_each_part(save_part, self.num_parts)
 
   def _process_node(self, ntype, with_feature):
     ids_per_part, pb = self._partition_node(ntype)
@@ -249,8 +264,7 @@ class PartitionerBase(ABC):
     if graph_caching:
       save_graph_cache(self.output_dir, parts, etype)
     else:
-      for p, g in enumerate(parts):
-        save_graph_partition(self.output_dir, p, g, etype)
+      _for_each_part(lambda p: save_graph_partition(self.output_dir, p, parts[p], etype), self.num_parts)
     feat = self.get_edge_feat(etype)
     if with_feature and feat is not None:
       self._save_feats(feat, [g.eids for g in parts], None, 'edge_feat', etype)

@@ -92,3 +92,42 @@ def test_range_partition_book():
   assert pb.id2index[torch.tensor([10, 12])].tolist() == [0, 2]
   assert pb.id_filter(pb, 2).tolist() == list(range(25, 40))
   assert pb.bounds == [0, 10, 25, 40]
+
+
+def test_frequency_chunk_assignment_respects_quota_and_follows_hotness():
+  """The vectorised chunk assignment gives every node an owner, never exceeds the per-chunk quota, and agrees with
+  the sequential "best (partition, node) pairs first" walk it replaced (ties aside)."""
+  from graphlearn_for_pytorch_b200.partition.frequency_partitioner import _assign_chunk
+
+  def sequential(score, quota):
+    P, c = score.shape
+    owner, load = [-1] * c, [0] * P
+    for flat in torch.argsort(score.flatten(), descending=True).tolist():
+      p, v = divmod(flat, c)
+      if owner[v] < 0 and load[p] < quota:
+        owner[v], load[p] = p, load[p] + 1
+    return torch.tensor(owner)
+  g = torch.Generator().manual_seed(3)
+  for P, c in ((4, 2000), (7, 701), (2, 5)):
+    probs = torch.rand(P, c, generator=g) ** 3
+    score = P * probs - probs.sum(0, keepdim=True)
+    quota = (c + P - 1) // P
+    own = _assign_chunk(score, quota)
+    assert int(own.min()) >= 0 and int(torch.bincount(own, minlength=P).max()) <= quota
+    ref = sequential(score, quota)
+    assert float((own == ref).float().mean()) > 0.97
+    mass, ref_mass = probs[own, torch.arange(c)].sum(), probs[ref, torch.arange(c)].sum()
+    assert float(mass) >= 0.995 * float(ref_mass)
+  cold = _assign_chunk(torch.zeros(4, 10), 3)                 # no hotness information: still balanced
+  assert int(cold.min()) >= 0 and int(torch.bincount(cold, minlength=4).max()) <= 3
+
+
+def test_partition_benchmark_runs_small():
+  import os
+  import subprocess
+  import sys
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  for kind in ('random', 'frequency'):
+    out = subprocess.run([sys.executable, 'benchmarks/bench_partition_cpu.py', 'ours', kind], cwd=root,
+                         capture_output=True, text=True, timeout=300, env=dict(os.environ, N='20000', E='200000'))
+    assert out.returncode == 0 and '"M_edges_per_s"' in out.stdout, out.stderr[-2000:]
