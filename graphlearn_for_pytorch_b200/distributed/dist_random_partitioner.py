@@ -115,7 +115,7 @@ class DistRandomPartitioner(object):
       if own.numel() == 0:
         break
       # one stable sort per chunk instead of num_parts boolean masks
-      order = torch.argsort(own, stable=True)
+      order = torch.argsort(own.to(torch.int16), stable=True)   # narrow keys take torch's radix path
       counts = torch.bincount(own, minlength=self.num_parts).tolist()
       sorted_chunk = {k: v[b:b + chunk][order] for k, v in tensors.items()}
       off = 0
