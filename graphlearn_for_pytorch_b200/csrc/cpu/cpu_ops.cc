@@ -108,16 +108,65 @@ std::tuple<Tensor, Tensor, Tensor, Tensor> coo_to_csr(
   }
   Tensor indptr = torch::zeros({num_rows + 1}, torch::kInt64);
   int64_t* ip = indptr.data_ptr<int64_t>();
-  for (int64_t i = 0; i < E; ++i) {
-    TORCH_CHECK(r[i] >= 0 && r[i] < num_rows, "row id out of range");
-    ip[r[i] + 1]++;
+  // Large inputs: the histogram and the bucket scatter -- the two passes with random accesses -- are split by ROW
+  // RANGE over T threads.  Every thread streams the whole row array (sequential reads are cheap) and touches only
+  // the counters / output slots of its own rows, so there is nothing to merge, the accessed slice of `indptr` /
+  // `perm` shrinks to 1/T (cache-resident counters), and edges keep their input order inside a row exactly as in
+  // the serial pass.
+  const int64_t T = std::min<int64_t>(at::get_num_threads(), 16);
+  const bool par = T > 1 && E >= (int64_t(1) << 20) && num_rows >= T && !at::in_parallel_region();
+  if (par) {
+    std::atomic<bool> bad{false};
+    glt::parallel_for(0, E, int64_t(1) << 18, [&](int64_t b, int64_t e) {
+      for (int64_t i = b; i < e; ++i)
+        if (r[i] < 0 || r[i] >= num_rows) { bad.store(true, std::memory_order_relaxed); return; }
+    });
+    TORCH_CHECK(!bad.load(), "row id out of range");
+    glt::parallel_for(0, T, 1, [&](int64_t tb, int64_t te) {
+      for (int64_t t = tb; t < te; ++t) {
+        const int64_t lo = num_rows * t / T, hi = num_rows * (t + 1) / T;
+        const uint64_t span = (uint64_t)(hi - lo);
+        for (int64_t i = 0; i < E; ++i) {
+          const int64_t row = r[i];
+          if ((uint64_t)(row - lo) < span) ip[row + 1]++;
+        }
+      }
+    });
+  } else {
+    for (int64_t i = 0; i < E; ++i) {
+      TORCH_CHECK(r[i] >= 0 && r[i] < num_rows, "row id out of range");
+      ip[r[i] + 1]++;
+    }
   }
   for (int64_t i = 0; i < num_rows; ++i) ip[i + 1] += ip[i];
   // perm[pos] = original edge position
   std::vector<int64_t> perm(E);
   {
     std::vector<int64_t> cursor(ip, ip + num_rows);
-    for (int64_t i = 0; i < E; ++i) perm[cursor[r[i]]++] = i;
+    if (par) {
+      std::vector<int64_t> bound(T + 1, num_rows);      // row ranges holding ~E/T edges each
+      bound[0] = 0;
+      for (int64_t t = 1; t < T; ++t) {
+        const int64_t at_edge = E / T * t;
+        int64_t row = std::lower_bound(ip, ip + num_rows + 1, at_edge) - ip;
+        bound[t] = std::min(std::max(row, bound[t - 1]), num_rows);
+      }
+      int64_t* cur = cursor.data();
+      int64_t* pm = perm.data();
+      glt::parallel_for(0, T, 1, [&](int64_t tb, int64_t te) {
+        for (int64_t t = tb; t < te; ++t) {
+          const int64_t lo = bound[t], hi = bound[t + 1];
+          if (lo >= hi) continue;
+          const uint64_t span = (uint64_t)(hi - lo);
+          for (int64_t i = 0; i < E; ++i) {
+            const int64_t row = r[i];
+            if ((uint64_t)(row - lo) < span) pm[cur[row]++] = i;
+          }
+        }
+      });
+    } else {
+      for (int64_t i = 0; i < E; ++i) perm[cursor[r[i]]++] = i;
+    }
   }
   if (sort_cols) {
     glt::parallel_for(0, num_rows, 1024, [&](int64_t b, int64_t e) {

@@ -43,3 +43,29 @@ def test_typing_helpers():
   assert reverse_edge_type(('b', 'rev_r', 'a')) == ('a', 'r', 'b')
   assert reverse_edge_type(('a', 'r', 'a')) == ('a', 'r', 'a')
   assert glt.utils.parse_size('2GB') == 2 * 2 ** 30
+
+
+def test_large_coo_to_csr_threaded_path_matches_stable_sort():
+  """>= 2^20 edges take the row-range-parallel histogram / scatter of the native conversion: result must equal a
+  stable (row, column) sort of the input, edge ids and weights included, with hub rows, empty rows and duplicates."""
+  import torch
+  from graphlearn_for_pytorch_b200.utils.topo import coo_to_csr
+  g = torch.Generator().manual_seed(11)
+  n, e = 50_000, (1 << 20) + 12_345
+  rows = torch.randint(0, n, (e,), generator=g)
+  rows[: e // 8] = 7                                       # a hub row
+  rows[rows == 13] = 14                                    # an empty row
+  cols = torch.randint(0, 1000, (e,), generator=g)         # many duplicate (row, col) pairs
+  w = torch.rand(e, generator=g)
+  eid = torch.randperm(e, generator=g)
+  torch.set_num_threads(max(torch.get_num_threads(), 2))
+  ptr, ind, oe, ow = coo_to_csr(rows, cols, eid, w, node_sizes=(n, 1000))
+  perm = torch.argsort(cols, stable=True)
+  perm = perm[torch.argsort(rows[perm], stable=True)]
+  assert torch.equal(ptr[1:] - ptr[:-1], torch.bincount(rows, minlength=n)) and int(ptr[-1]) == e
+  assert torch.equal(ind, cols[perm]) and torch.equal(oe, eid[perm]) and torch.equal(ow, w[perm])
+  import pytest
+  bad = rows.clone()
+  bad[-1] = n
+  with pytest.raises(RuntimeError):
+    coo_to_csr(bad, cols, None, None, node_sizes=(n, 1000))
