@@ -490,19 +490,50 @@ std::tuple<Tensor, Tensor> cpu_negative_sample(
   TORCH_CHECK(num_cols > 0, "num_cols must be positive");
   std::vector<int64_t> r(req), c(req);
   std::vector<uint8_t> ok(req, 0);
+  // The membership test of a candidate is two dependent cache misses (indptr[row], then the row's column list) on
+  // a graph far larger than the caches.  Candidates are therefore handled in groups of 16: draw all, prefetch their
+  // indptr entries, prefetch their column lists, then search -- the misses of a group overlap instead of
+  // serialising.  Draw (i, t) is the same Philox value as in a one-at-a-time loop, so results do not depend on the
+  // grouping or on the thread count.
+  constexpr int64_t G = 16;
   glt::parallel_for(0, req, 2048, [&](int64_t b, int64_t e) {
-    for (int64_t i = b; i < e; ++i) {
+    int64_t rr[G], cc[G];
+    for (int64_t g0 = b; g0 < e; g0 += G) {
+      const int64_t gn = std::min<int64_t>(G, e - g0);
       for (int64_t t = 0; t < trials; ++t) {
-        int64_t rr = bounded(philox_draw(seed, stream, i, 2 * t), (uint32_t)num_rows);
-        int64_t cc = bounded(philox_draw(seed, stream, i, 2 * t + 1), (uint32_t)num_cols);
-        bool hit = rr < csr_rows && edge_in_row(ind, ip[rr], ip[rr + 1], cc, sorted);
-        if (!hit) { r[i] = rr; c[i] = cc; ok[i] = 1; break; }
+        bool any = false;
+        for (int64_t j = 0; j < gn; ++j) {
+          const int64_t i = g0 + j;
+          if (ok[i]) continue;
+          any = true;
+          rr[j] = bounded(philox_draw(seed, stream, i, 2 * t), (uint32_t)num_rows);
+          cc[j] = bounded(philox_draw(seed, stream, i, 2 * t + 1), (uint32_t)num_cols);
+          if (rr[j] < csr_rows) __builtin_prefetch(ip + rr[j]);
+        }
+        if (!any) break;
+        for (int64_t j = 0; j < gn; ++j) {
+          if (ok[g0 + j] || rr[j] >= csr_rows) continue;
+          const int64_t lo = ip[rr[j]], hi = ip[rr[j] + 1];
+          if (hi > lo) {
+            __builtin_prefetch(ind + lo);
+            __builtin_prefetch(ind + lo + (hi - lo) / 2);
+          }
+        }
+        for (int64_t j = 0; j < gn; ++j) {
+          const int64_t i = g0 + j;
+          if (ok[i]) continue;
+          bool hit = rr[j] < csr_rows && edge_in_row(ind, ip[rr[j]], ip[rr[j] + 1], cc[j], sorted);
+          if (!hit) { r[i] = rr[j]; c[i] = cc[j]; ok[i] = 1; }
+        }
       }
-      if (!ok[i] && padding) {
-        // non-strict fill, same as the reference's padding pass (:63-67)
-        r[i] = bounded(philox_draw(seed, stream + 0x40000000u, i, 0), (uint32_t)num_rows);
-        c[i] = bounded(philox_draw(seed, stream + 0x40000000u, i, 1), (uint32_t)num_cols);
-        ok[i] = 1;
+      if (padding) {
+        for (int64_t i = g0; i < g0 + gn; ++i) {
+          if (ok[i]) continue;
+          // non-strict fill, same as the reference's padding pass (:63-67)
+          r[i] = bounded(philox_draw(seed, stream + 0x40000000u, i, 0), (uint32_t)num_rows);
+          c[i] = bounded(philox_draw(seed, stream + 0x40000000u, i, 1), (uint32_t)num_cols);
+          ok[i] = 1;
+        }
       }
     }
   });
