@@ -205,4 +205,6 @@ def test_cpu_mode_distributed_loader_benchmark_runs():
   out = _run(['benchmarks/bench_dist_loader_cpu.py', 'ours', '--nodes', '20000', '--edges', '200000', '--workers', '1',
               '--epochs', '2', '--train-frac', '0.2'], timeout=400)
   line = json.loads([ln for ln in out.splitlines() if ln.startswith('{')][-1])
-  assert line['impl'] == 'ours' and line['best_epoch']['batches'] == 4 and line['best_epoch']['M_edges_per_s'] > 0
+  # 4000 training seeds over 2 randomly drawn partitions, batch 1024: 2 batches per trainer, 3 for a trainer whose
+  # partition happens to own more than 2048 of them
+  assert line['impl'] == 'ours' and line['best_epoch']['batches'] in (4, 5) and line['best_epoch']['M_edges_per_s'] > 0
